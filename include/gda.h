@@ -1,0 +1,219 @@
+/* libgda -- C ABI of the B200-native PyGDA hot path (sm_100a).
+ *
+ * The reference (pygda-team/pygda) is pure Python and has NO FFI/plugin
+ * interface; its hot path reaches native code only through torch / PyG /
+ * torch_scatter operators.  Each entry point below therefore names the
+ * reference operator call site (file:line under /root/reference) it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the
+ * reference side.
+ *
+ * Conventions
+ *  - plain C symbols, `int` return: 0 = ok, negative = GDA_E_* ; never throws or
+ *    aborts across the ABI.  `gda_last_error()` returns a thread-local message.
+ *  - every buffer is a CALLER-ALLOCATED DEVICE pointer (the caller's allocator --
+ *    torch in this repo -- owns all memory).  The library retains nothing beyond
+ *    the call except the opaque `gda_graph_t` (CSR/CSC + weights), which is
+ *    explicitly created and destroyed.
+ *  - every call takes the CUDA stream to run on (`void*` == cudaStream_t) and is
+ *    asynchronous with respect to the host unless stated otherwise.
+ *  - re-entrant; no hidden global state.  A `gda_graph_t` may be used from
+ *    several host threads as long as calls on it are ordered on one stream at a
+ *    time (PyTorch's autograd thread uses the forward's stream).
+ *  - row-major matrices with explicit leading dimensions in ELEMENTS.
+ */
+#ifndef GDA_H_
+#define GDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDA_VERSION 100          /* 0.1.0 */
+
+/* error codes */
+#define GDA_OK              0
+#define GDA_E_INVALID      -1    /* bad argument (null pointer, negative size, bad flag) */
+#define GDA_E_CUDA         -2    /* CUDA runtime error; see gda_last_error() */
+#define GDA_E_INDEX        -3    /* edge_index entry outside [0, N) */
+#define GDA_E_UNSUPPORTED  -4    /* shape/dtype combination not built */
+#define GDA_E_WORKSPACE    -5    /* workspace too small */
+
+typedef void* gda_stream_t;      /* cudaStream_t */
+typedef struct gda_graph gda_graph_t;
+
+int         gda_version(void);
+int         gda_sm_arch(void);   /* 100: built for sm_100a only */
+const char* gda_last_error(void);
+
+/* ------------------------------------------------------------------ graph --
+ * gda_graph_create replaces, in one device pass, what the reference recomputes
+ * on every conv call:
+ *   gcn_norm            pygda/nn/prop_gcn_conv.py:24-81   (GDA_NORM_SYM_COL)
+ *   CachedGCNConv.norm  pygda/nn/cached_gcn_conv.py:63-103 (GDA_NORM_SYM_ROW)
+ *   add_remaining_self_loops / scatter_add call sites therein (:71-78 / :95-99)
+ * plus the COO -> CSR (by destination) and CSC (by source) builds that the
+ * aggregation kernels need.  Index results are bit-exact with the reference
+ * (kept edges in order, then loops 0..N-1); within a CSR row entries keep COO
+ * order, so the fp32 summation order equals a sequential scatter_add.
+ *
+ * edge_index: device int64 [2, E] (row 0 = source, row 1 = target), edge_weight:
+ * device float [E] or NULL (= ones).  Synchronises `stream` once (it has to read
+ * the surviving edge count). */
+#define GDA_SELF_LOOPS    1      /* add_remaining_self_loops */
+#define GDA_IMPROVED      2      /* fill value 2 instead of 1 */
+#define GDA_NORM_SYM_COL  4      /* D^-1/2 A D^-1/2, degree summed at the target index */
+#define GDA_NORM_SYM_ROW  8      /* same, degree summed at the source index */
+int gda_graph_create(const int64_t* edge_index, int64_t E, int64_t N,
+                     const float* edge_weight, int flags, gda_stream_t stream,
+                     gda_graph_t** out);
+int gda_graph_destroy(gda_graph_t* g);
+int gda_graph_info(const gda_graph_t* g, int64_t* N, int64_t* nnz,
+                   int64_t* num_long_rows, int64_t* num_long_rows_t);
+/* self-looped, normalised COO in the reference's order: edge_index_out int64 [2,nnz],
+ * weight_out float [nnz]  (what gcn_norm returns, prop_gcn_conv.py:81) */
+int gda_graph_export_coo(const gda_graph_t* g, int64_t* edge_index_out, float* weight_out,
+                         gda_stream_t stream);
+/* CSR of A_hat (transpose=0: rows = targets, cols = sources) or of A_hat^T
+ * (transpose=1): rowptr int32 [N+1], colidx int32 [nnz], vals float [nnz] */
+int gda_graph_export_csr(const gda_graph_t* g, int transpose, int32_t* rowptr,
+                         int32_t* colidx, float* vals, gda_stream_t stream);
+
+/* ------------------------------------------------------------ aggregation --
+ * Y = A_hat * X (transpose=0) or A_hat^T * X (transpose=1, the backward of the
+ * former).  Replaces MessagePassing.propagate = index_select -> mul ->
+ * scatter_add_ at pygda/nn/prop_gcn_conv.py:208-210 (+message :238) and
+ * pygda/nn/cached_gcn_conv.py:138 (+message :156), and its autograd backward.
+ * X [N,H] (ldx), Y [N,H] (ldy), fp32; X and Y must not alias.
+ * Optional fused epilogue on Y: + bias[H] (prop_gcn_conv.py:212-213 /
+ * cached_gcn_conv.py:171-172), then ReLU, then inverted dropout with keep mask
+ * hash(seed + *seed_offset, row*H+col) (a2gnn_base.py:136-138).  bias may be NULL;
+ * seed_offset is a device uint64 (or NULL = 0) so that a captured CUDA graph draws
+ * a fresh mask on every replay.
+ * workspace: device scratch of gda_spmm_workspace_bytes(); may be NULL when that
+ * is 0 (no rows longer than the split threshold). */
+#define GDA_EPI_RELU      1
+#define GDA_EPI_DROPOUT   2
+int64_t gda_spmm_workspace_bytes(const gda_graph_t* g, int transpose, int H);
+int gda_spmm_f32(const gda_graph_t* g, int transpose, const float* X, int64_t ldx,
+                 float* Y, int64_t ldy, int H, const float* bias, int epi_flags,
+                 float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                 void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+/* bf16 features, fp32 edge weights and accumulation (BASELINE config 3) */
+int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ldx,
+                  void* Y, int64_t ldy, int H, const float* bias, int epi_flags,
+                  float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                  void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+
+/* ------------------------------------------------------------ dense GEMM --
+ * C[M,N] = alpha * op(A) * op(B) + beta * C, fp32 row-major, op = transpose when
+ * the flag is set (A is [M,K] or [K,M]; B is [K,N] or [N,K]).
+ * Replaces `self.lin(x)` (prop_gcn_conv.py:205, PyG Linear = x @ W^T),
+ * `torch.matmul(x, self.weight)` (cached_gcn_conv.py:130), the nn.Linear heads
+ * (a2gnn_base.py:67,70; udagcn_base.py:155-162; grade_base.py:63-74) and their
+ * autograd backward GEMMs.  Large aligned shapes run on tcgen05 tensor cores
+ * with a split-bf16 (3-term) decomposition that keeps fp32-level accuracy
+ * (DESIGN.md section 4); everything else on a SIMT fp32 kernel. */
+int64_t gda_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K);
+int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+                 const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                 float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
+                 gda_stream_t stream);
+
+/* ------------------------------------------------------------ elementwise --
+ * y = dropout(act(x + bias)) and its backward; act: 0 none, 1 relu.  The keep
+ * mask is regenerated from (seed, element index): nothing is stored.
+ * Replaces `self.act(x)` + `F.dropout` (a2gnn_base.py:136-138, udagcn_base.py:86-88).
+ * x,y [rows, cols] contiguous; y may alias x.  bias may be NULL. */
+int gda_bias_act_dropout_fwd(const float* x, const float* bias, float* y, int64_t rows,
+                             int64_t cols, int act, float dropout_p, uint64_t seed,
+                             const uint64_t* seed_offset, gda_stream_t stream);
+/* gx = gy * act'(y) * keep/(1-p) ; `y` is the forward OUTPUT.  gbias [cols] (may be
+ * NULL) receives the column sums of gx (it is overwritten, not accumulated). */
+int gda_bias_act_dropout_bwd(const float* gy, const float* y, float* gx, float* gbias,
+                             int64_t rows, int64_t cols, int act, float dropout_p,
+                             uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream);
+/* column sums: out[cols] = sum_r x[r, :]   (bias gradients) */
+int gda_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out,
+                   gda_stream_t stream);
+
+/* ------------------------------------------------------------------ losses --
+ * Mean cross-entropy of log_softmax(logits) against integer labels, forward and
+ * backward in one pass.  Replaces F.nll_loss(F.log_softmax(..)) (models/a2gnn.py:182),
+ * F.cross_entropy on the domain logits (a2gnn.py:204, udagcn.py:180-187, grade.py:176).
+ * labels: int64 [rows] or NULL; when NULL the label of row r is (r >= split) --
+ * the reference's `[0]*N_s + [1]*N_t` host list (a2gnn.py:200-202) folded into the
+ * kernel.  loss_out: device float[1] (overwritten).  dlogits (may be NULL):
+ * d(mean CE)/dlogits, [rows, C].  C <= 64. */
+int gda_softmax_ce_fwd_bwd(const float* logits, int64_t rows, int C, int64_t ld,
+                           const int64_t* labels, int64_t split, float* loss_out,
+                           float* dlogits, gda_stream_t stream);
+/* Target-entropy term of UDAGCN (models/udagcn.py:193-199): mean_r sum_c -p log p with
+ * p = clamp(softmax(logits), 1e-9, 1); backward into dlogits. */
+int gda_softmax_entropy_fwd_bwd(const float* logits, int64_t rows, int C, int64_t ld,
+                                float* loss_out, float* dlogits, gda_stream_t stream);
+
+/* --------------------------------------------------------------------- MMD --
+ * Multi-bandwidth Gaussian MMD between sampled source/target rows.
+ * Replaces pygda/utils/mmd.py:4-158 (guassian_kernel :4-55, get_MMD :57-107, MMD
+ * :109-158) without the n x n x d temporary.  The sample indices are INPUTS
+ * (drawn by the host exactly as mmd.py:148-149 draws them).
+ *  src [Ns, d] (lds), tgt [Nt, d] (ldt) fp32; src_idx / tgt_idx int64 [times, b].
+ *  loss_out: device float[1] = mean over `times` of get_MMD.
+ *  workspace holds, per sample, the n x n matrix (n = 2b) that the backward
+ *  re-uses; keep it alive until gda_mmd_bwd has run.
+ * gda_mmd_bwd ACCUMULATES grad_scale * dloss/dsrc into gsrc [Ns,d] and
+ * dloss/dtgt into gtgt [Nt,d] (atomic adds: sampled rows repeat). */
+int64_t gda_mmd_workspace_bytes(int times, int b, int d);
+int gda_mmd_fwd(const float* src, int64_t lds, const float* tgt, int64_t ldt, int d,
+                const int64_t* src_idx, const int64_t* tgt_idx, int times, int b,
+                float kernel_mul, int kernel_num, float* loss_out, void* workspace,
+                int64_t workspace_bytes, gda_stream_t stream);
+int gda_mmd_bwd(const float* src, int64_t lds, const float* tgt, int64_t ldt, int d,
+                const int64_t* src_idx, const int64_t* tgt_idx, int times, int b,
+                const float* grad_scale /* device float[1] */, float* gsrc, int64_t ldgs,
+                float* gtgt, int64_t ldgt, void* workspace, int64_t workspace_bytes,
+                gda_stream_t stream);
+
+/* ---------------------------------------------------------------- pooling --
+ * global_mean_pool over a sorted `batch` vector given as CSR-style ptr
+ * (int64 [G+1]).  Call sites: a2gnn_base.py:141, adagcn_base.py:94,
+ * grade_base.py:154,157, models/udagcn.py:169-170. */
+int gda_segment_mean_fwd(const float* x, int64_t ldx, const int64_t* ptr, int64_t G, int H,
+                         float* out, gda_stream_t stream);
+int gda_segment_mean_bwd(const float* gout, const int64_t* ptr, int64_t G, int H,
+                         float* gx, int64_t ldgx, gda_stream_t stream);
+
+/* --------------------------------------------------------------- optimiser --
+ * torch.optim.Adam (L2 weight decay, no amsgrad) over up to GDA_ADAM_MAX_TENSORS
+ * tensors in ONE launch (models/a2gnn.py:292-296,317-319).  `state` is a device
+ * float[4] owned by the caller, zero-initialised: {step, bias_corr1, bias_corr2, -}.
+ * gda_adam_step first advances state (so it is CUDA-graph replayable), then
+ * updates p, m, v in place. */
+#define GDA_ADAM_MAX_TENSORS 48
+int gda_adam_step(int num_tensors, float* const* params, const float* const* grads,
+                  float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float* state, gda_stream_t stream);
+
+/* ------------------------------------------------------------------ misc ---
+ * fill / axpy helpers so the hot path never falls back to framework kernels */
+int gda_fill_f32(float* x, int64_t n, float value, gda_stream_t stream);
+int gda_axpy_f32(float* y, const float* x, int64_t n, float alpha, gda_stream_t stream); /* y += alpha*x */
+/* y = alpha * x : backward of GradReverse (pygda/nn/reverse_layer.py:65-66) with alpha := -alpha */
+int gda_scale_f32(float* y, const float* x, int64_t n, float alpha, gda_stream_t stream);
+/* y = alpha * (*alpha_dev) * x with a DEVICE scalar (loss-gradient scaling without a host sync) */
+int gda_scale_dev_f32(float* y, const float* x, int64_t n, float alpha, const float* alpha_dev,
+                      gda_stream_t stream);
+/* *counter += 1 (device uint64): advances the dropout seed offset inside a CUDA graph */
+int gda_counter_inc(uint64_t* counter, gda_stream_t stream);
+/* out[0] = sum_i w[i] * (*terms[i]) for up to 8 device scalars: the loss combination
+ * `loss = cls + weight * mmd` (models/a2gnn.py:183-209) without framework kernels */
+int gda_combine_scalars(int n, const float* const* terms, const float* weights, float* out,
+                        gda_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* GDA_H_ */

@@ -1,0 +1,218 @@
+"""Oracle restatement of the pygda.nn modules on the hot path (CPU, plain torch).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Each class cites the reference
+file:line it follows.  State-dict parameter names match the reference so that
+weights can be copied between oracle, golden fixtures and the CUDA modules.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import pyg_ops as P
+
+
+class GradReverse(torch.autograd.Function):
+    """pygda/nn/reverse_layer.py:16-66: identity forward (:39), backward
+    ``-alpha * g`` (:65-66)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = alpha
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.neg() * ctx.alpha, None
+
+
+class PropGCNConv(nn.Module):
+    """pygda/nn/prop_gcn_conv.py:84-264.
+
+    forward (:153-215): gcn_norm recomputed on every call (``cached=False``
+    default, :182-192) -> ``lin`` (:205) -> ``prop_nums`` x propagate (:208-210)
+    -> in-place ``+= bias`` (:212-213).
+    """
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False,
+                 add_self_loops=True, normalize=True, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached = improved, cached
+        self.add_self_loops, self.normalize = add_self_loops, normalize
+        self._cached_edge_index = None
+        self.lin = P.Linear(in_channels, out_channels, bias=False)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x, edge_index, prop_nums=1, edge_weight=None):
+        if self.normalize:
+            cache = self._cached_edge_index
+            if cache is None:
+                edge_index, edge_weight = P.gcn_norm_by_col(
+                    edge_index, edge_weight, x.size(0), self.improved, self.add_self_loops,
+                    dtype=x.dtype)
+                if self.cached:
+                    self._cached_edge_index = (edge_index, edge_weight)
+            else:
+                edge_index, edge_weight = cache
+        out = self.lin(x)
+        for _ in range(prop_nums):
+            out = P.propagate(edge_index, out, edge_weight)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+class GCNConv(PropGCNConv):
+    """Stock PyG ``GCNConv`` = PropGCNConv with exactly one
+    propagate.  Call sites: pygda/nn/grade_base.py:58-61, adagcn_base.py:49-52,
+    gnn_base.py:65-71."""
+
+    def forward(self, x, edge_index, edge_weight=None):
+        return super().forward(x, edge_index, 1, edge_weight)
+
+
+class A2GNNBase(nn.Module):
+    """pygda/nn/a2gnn_base.py:57-203."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=1, adv=False,
+                 dropout=0.1, act=F.relu, mode="node", **kwargs):
+        super().__init__()
+        self.in_dim, self.hid_dim, self.num_classes = in_dim, hid_dim, num_classes
+        self.num_layers, self.adv, self.dropout = num_layers, adv, dropout
+        self.act, self.mode = act, mode
+        self.convs = nn.ModuleList([PropGCNConv(in_dim, hid_dim)])
+        for _ in range(num_layers - 1):
+            self.convs.append(PropGCNConv(hid_dim, hid_dim))
+        if mode == "node":
+            self.cls = PropGCNConv(hid_dim, num_classes)
+        else:
+            self.cls = nn.Linear(hid_dim, num_classes)
+        if adv:
+            self.domain_discriminator = nn.Linear(hid_dim, 2)
+
+    def forward(self, data, prop_nums):                       # :72-104
+        batch = None if self.mode == "node" else data.batch
+        x = self.feat_bottleneck(data.x, data.edge_index, batch, prop_nums=prop_nums)
+        return self.feat_classifier(x, data.edge_index, batch, prop_nums=1)
+
+    def feat_bottleneck(self, x, edge_index, batch, prop_nums=30):   # :106-143
+        for conv in self.convs:
+            x = conv(x, edge_index, prop_nums)
+            x = self.act(x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        if self.mode == "graph":
+            x = P.global_mean_pool(x, batch)
+        return x
+
+    def feat_classifier(self, x, edge_index, batch, prop_nums=1):    # :145-176
+        if self.mode == "node":
+            return self.cls(x, edge_index, prop_nums)
+        return self.cls(x)
+
+    def domain_classifier(self, x, alpha):                            # :178-203
+        return self.domain_discriminator(GradReverse.apply(x, alpha))
+
+
+class CachedGCNConv(nn.Module):
+    """pygda/nn/cached_gcn_conv.py:35-174: ``x @ W`` (:130), norm cached per
+    ``cache_name`` forever (:132-136, degree by ROW :98-103), one propagate
+    (:138), ``+ bias`` in ``update`` (:158-174).  ``weight`` is [in, out]."""
+
+    def __init__(self, in_channels, out_channels, weight=None, bias=None,
+                 improved=False, use_bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.improved = in_channels, out_channels, improved
+        self.cache_dict = {}
+        if weight is None:
+            self.weight = nn.Parameter(torch.empty(in_channels, out_channels, dtype=torch.float32))
+            P.glorot_(self.weight)
+        else:
+            self.weight = weight
+        if bias is None:
+            if use_bias:
+                self.bias = nn.Parameter(torch.zeros(out_channels, dtype=torch.float32))
+            else:
+                self.register_parameter("bias", None)
+        else:
+            self.bias = bias
+
+    def forward(self, x, edge_index, cache_name="default_cache", edge_weight=None):
+        x = torch.matmul(x, self.weight)
+        if cache_name not in self.cache_dict:
+            edge_index, norm = P.gcn_norm_by_row(edge_index, x.size(0), edge_weight,
+                                                 self.improved, x.dtype)
+            self.cache_dict[cache_name] = edge_index, norm
+        else:
+            edge_index, norm = self.cache_dict[cache_name]
+        out = P.propagate(edge_index, x, norm)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+class Attention(nn.Module):
+    """pygda/nn/attention.py:6-55."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.dense_weight = nn.Linear(in_channels, 1)
+        self.dropout = nn.Dropout(0.1)
+
+    def forward(self, inputs):
+        stacked = torch.stack(inputs, dim=1)
+        weights = F.softmax(self.dense_weight(stacked), dim=1)
+        return torch.sum(stacked * weights, dim=1)
+
+
+class UDAGCNEncoder(nn.Module):
+    """``GNN`` of pygda/nn/udagcn_base.py:9-89 (gcn type only; the PPMI graph
+    builder is out of scope).  ``dropout_layers`` is a plain
+    Python list in the reference (:47) so it is never switched to eval mode --
+    reproduced here."""
+
+    def __init__(self, in_dim, hid_dim, num_layers=3, base_model=None, act=F.relu):
+        super().__init__()
+        if base_model is None:
+            weights, biases = [None] * num_layers, [None] * num_layers
+        else:
+            weights = [c.weight for c in base_model.conv_layers]
+            biases = [c.bias for c in base_model.conv_layers]
+        self.dropout_layers = [nn.Dropout(0.1) for _ in weights]
+        self.act = act
+        self.conv_layers = nn.ModuleList()
+        self.conv_layers.append(CachedGCNConv(in_dim, hid_dim, weight=weights[0], bias=biases[0]))
+        for i in range(1, num_layers):
+            self.conv_layers.append(CachedGCNConv(hid_dim, hid_dim, weight=weights[i], bias=biases[i]))
+
+    def forward(self, x, edge_index, cache_name):
+        for i, conv in enumerate(self.conv_layers):
+            x = conv(x, edge_index, cache_name)
+            if i < len(self.conv_layers) - 1:
+                x = self.act(x)
+                x = self.dropout_layers[i](x)
+        return x
+
+
+class UDAGCNBase(nn.Module):
+    """pygda/nn/udagcn_base.py:92-267 with ``ppmi=False`` (the only
+    configuration in scope)."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0.1,
+                 act=F.relu, ppmi=False, adv_dim=40, **kwargs):
+        super().__init__()
+        assert not ppmi, "oracle restates the ppmi=False path only"
+        self.ppmi = ppmi
+        self.encoder = UDAGCNEncoder(in_dim, hid_dim, num_layers=num_layers, act=act)
+        self.cls_model = nn.Sequential(nn.Linear(hid_dim, num_classes))
+        self.domain_model = nn.Sequential(
+            nn.Linear(hid_dim, adv_dim), nn.ReLU(), nn.Dropout(0.1), nn.Linear(adv_dim, 2))
+        self.att_model = Attention(hid_dim)
+        self.models = [self.encoder, self.cls_model, self.domain_model]
+        self.loss_func = nn.CrossEntropyLoss()
+
+    def encode(self, data, cache_name, mask=None):
+        out = self.encoder(data.x, data.edge_index, cache_name)
+        return out if mask is None else out[mask]

@@ -1,0 +1,45 @@
+// gda_gemm_f32 dispatcher: tcgen05 split-bf16 kernel for the large aligned shapes,
+// SIMT fp32 kernel for everything else.  Replaces `self.lin(x)`
+// (pygda/nn/prop_gcn_conv.py:205), `torch.matmul(x, self.weight)`
+// (pygda/nn/cached_gcn_conv.py:130), the nn.Linear heads and their backward GEMMs.
+#include <cstdlib>
+
+#include "gemm.cuh"
+
+namespace gda {
+namespace {
+bool tc_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("GDA_DISABLE_TC");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+}  // namespace
+}  // namespace gda
+
+extern "C" {
+
+int64_t gda_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
+  int64_t a = gda::simt_workspace_bytes(M, N, K);
+  int64_t b = gda::tc_workspace_bytes(transA, transB, M, N, K);
+  return a > b ? a : b;
+}
+
+int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* workspace,
+                 int64_t workspace_bytes, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gda_gemm_f32: negative dimension");
+  if (M == 0 || N == 0) return GDA_OK;
+  GDA_REQUIRE(C != nullptr, "gda_gemm_f32: C is NULL");
+  GDA_REQUIRE(K == 0 || (A && B), "gda_gemm_f32: NULL operand");
+  GDA_REQUIRE(ldc >= N, "gda_gemm_f32: ldc < N");
+  GDA_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gda_gemm_f32: leading dimension too small");
+  cudaStream_t st = as_stream(stream);
+  if (tc_enabled() && tc_supported(transA, transB, M, N, K, lda, ldb, ldc, A, B, C))
+    return gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
+  return gemm_simt(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
+}
+
+}  // extern "C"

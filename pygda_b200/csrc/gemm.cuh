@@ -1,0 +1,19 @@
+// Internal GEMM entry points (see gemm.cu for the dispatcher).
+#pragma once
+#include "common.cuh"
+
+namespace gda {
+int simt_splits(int64_t M, int64_t N, int64_t K);
+int64_t simt_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* ws, int64_t ws_bytes,
+              cudaStream_t st);
+
+// tcgen05 split-bf16 path (gemm_tc.cu): returns true when the shape is handled there
+bool tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                  const float* A, const float* B, const float* C);
+int64_t tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K);
+int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+            const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* ws, int64_t ws_bytes,
+            cudaStream_t st);
+}  // namespace gda

@@ -1,0 +1,48 @@
+// Internal layout of gda_graph_t (HBM-resident, int32 indices, fp32 weights).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gda {
+
+// Rows with more than this many non-zeros are split into segments of this size so
+// that no warp walks a hub row alone (see spmm.cu).
+constexpr int kLongRowSegment = 64;
+
+struct Csr {
+  int32_t* rowptr = nullptr;   // [N+1]
+  int32_t* colidx = nullptr;   // [nnz]
+  float*   vals = nullptr;     // [nnz]
+  // long-row split
+  int32_t  num_long = 0;       // rows with degree > seg
+  int32_t  num_segs = 0;       // total segments over those rows
+  int32_t* long_rows = nullptr;     // [num_long] row ids
+  int32_t* long_seg_ptr = nullptr;  // [num_long+1] first segment of each long row
+  int32_t* seg_long = nullptr;      // [num_segs] long-row index of each segment
+  int32_t* counters = nullptr;      // [num_long] arrival counters, zero between launches
+};
+
+}  // namespace gda
+
+struct gda_graph {
+  int64_t N = 0, E = 0, nnz = 0;
+  int flags = 0, device = 0, seg = gda::kLongRowSegment;
+  // COO in the reference's order (kept edges, then loops), normalised weights
+  int32_t* coo_src = nullptr;
+  int32_t* coo_dst = nullptr;
+  float*   coo_w = nullptr;
+  float*   dinv = nullptr;     // [N] deg^-1/2
+  gda::Csr csr;                // rows = targets: Y = A_hat X
+  gda::Csr csr_t;              // rows = sources: Y = A_hat^T X
+  ~gda_graph();
+};
+
+namespace gda {
+int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int flags, cudaStream_t st,
+                 gda_graph** out);
+int graph_export_coo(const gda_graph* g, int64_t* ei_out, float* w_out, cudaStream_t st);
+int graph_export_csr(const gda_graph* g, int transpose, int32_t* rowptr, int32_t* colidx, float* vals,
+                     cudaStream_t st);
+}  // namespace gda

@@ -1,0 +1,283 @@
+// Sparse neighbour aggregation  Y = A_hat X  /  Y = A_hat^T X   (HBM / L2 gather bound).
+//
+// Replaces MessagePassing.propagate (index_select -> mul -> scatter_add_) at
+// pygda/nn/prop_gcn_conv.py:208-210,238 and pygda/nn/cached_gcn_conv.py:138,156,
+// and its autograd backward (the same product with A_hat^T).
+//
+// Layout: CSR with int32 indices and fp32 weights (graph.cu); features row-major.
+// A group of LPR lanes owns one output row and walks its neighbour list: the group
+// loads LPR (colidx, weight) pairs with one coalesced access, broadcasts them with
+// shuffles and gathers the neighbour rows with 16-byte loads, U gathers in flight per
+// lane.  Accumulation is fp32, sequential in CSR (= COO) order, hence deterministic.
+// Rows longer than `seg` non-zeros are cut into segments handled by separate groups
+// that are scheduled FIRST; the last segment to finish reduces the partial sums in
+// segment order (still deterministic) -- no hub row is walked by a single warp.
+#include <cuda_bf16.h>
+
+#include "graph.cuh"
+
+namespace gda {
+namespace {
+
+struct Epilogue {
+  const float* bias;   // may be null
+  int flags;           // GDA_EPI_*
+  uint32_t thresh;     // dropout threshold
+  float scale;         // 1/(1-p)
+  uint64_t seed;
+  const uint64_t* seed_offset;   // device, may be null
+};
+
+template <typename T, int VEC> struct VecIO;
+
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct VecIO<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[1]) { f[0] = __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[1]) { *p = f[0]; }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct VecIO<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[1]) {
+    f[0] = __bfloat162float(*p);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[1]) {
+    *p = __float2bfloat16_rn(f[0]);
+  }
+};
+
+template <int VEC>
+__device__ __forceinline__ void apply_epilogue(float (&acc)[VEC], const Epilogue& epi, int64_t row, int c0, int H) {
+  uint64_t seed = epi.seed;
+  if ((epi.flags & GDA_EPI_DROPOUT) && epi.seed_offset) seed += __ldg(epi.seed_offset);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float y = acc[v];
+    if (epi.bias) y += __ldg(epi.bias + c0 + v);
+    if (epi.flags & GDA_EPI_RELU) y = fmaxf(y, 0.f);
+    if (epi.flags & GDA_EPI_DROPOUT)
+      y = dropout_keep(seed, static_cast<uint64_t>(row) * H + c0 + v, epi.thresh) ? y * epi.scale : 0.f;
+    acc[v] = y;
+  }
+}
+
+template <typename T, int VEC, int LPR, int U>
+__global__ void __launch_bounds__(256)
+k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
+       int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
+       const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
+       const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int N, int H,
+       Epilogue epi, float* __restrict__ partial) {
+  constexpr int GPW = 32 / LPR;                         // groups per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int64_t warp = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t group = warp * GPW + sub;
+  if (group >= static_cast<int64_t>(num_segs) + N) return;
+
+  int row, start, end, L = -1;
+  if (group < num_segs) {                               // a segment of a long row
+    L = __ldg(seg_long + group);
+    row = __ldg(long_rows + L);
+    const int j = static_cast<int>(group) - __ldg(long_seg_ptr + L);
+    const int rs = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
+    start = rs + j * seg;
+    end = min(start + seg, re);
+  } else {
+    row = static_cast<int>(group - num_segs);
+    start = __ldg(rowptr + row);
+    end = __ldg(rowptr + row + 1);
+    if (end - start > seg) return;                      // covered by its segments
+  }
+
+  for (int cb = 0; cb < H; cb += LPR * VEC) {
+    const int c0 = cb + l * VEC;
+    const bool active = c0 < H;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+
+    for (int base = start; base < end; base += LPR) {
+      const int idx = base + l;
+      int myc = 0;
+      float myv = 0.f;
+      if (idx < end) { myc = __ldg(colidx + idx); myv = __ldg(vals + idx); }
+      const int cnt = min(LPR, end - base);
+      for (int j = 0; j < cnt; j += U) {
+        float xv[U][VEC];
+        float wv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cj = __shfl_sync(gmask, myc, j + u, LPR);
+          wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
+          const bool p = active && (j + u < cnt);
+          if (p) {
+            VecIO<T, VEC>::load(X + static_cast<int64_t>(cj) * ldx + c0, xv[u]);
+          } else {
+            wv[u] = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) xv[u][v] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+        }
+      }
+    }
+
+    if (!active) continue;
+    if (L < 0) {
+      apply_epilogue<VEC>(acc, epi, row, c0, H);
+      VecIO<T, VEC>::store(Y + static_cast<int64_t>(row) * ldy + c0, acc);
+    } else {
+      float* dst = partial + static_cast<int64_t>(group) * H + c0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+    }
+  }
+
+  if (L >= 0) {                                         // last segment to arrive reduces, in order
+    __threadfence();
+    __syncwarp(gmask);
+    int old = 0;
+    const int first = __ldg(long_seg_ptr + L), nseg = __ldg(long_seg_ptr + L + 1) - first;
+    if (l == 0) old = atomicAdd(counters + L, 1);
+    old = __shfl_sync(gmask, old, 0, LPR);
+    if (old == nseg - 1) {
+      __threadfence();
+      for (int cb = 0; cb < H; cb += LPR * VEC) {
+        const int c0 = cb + l * VEC;
+        if (c0 >= H) continue;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int s = 0; s < nseg; ++s) {
+          const float* src = partial + static_cast<int64_t>(first + s) * H + c0;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(src + v);
+        }
+        apply_epilogue<VEC>(acc, epi, row, c0, H);
+        VecIO<T, VEC>::store(Y + static_cast<int64_t>(row) * ldy + c0, acc);
+      }
+      if (l == 0) counters[L] = 0;                      // ready for the next launch
+    }
+  }
+}
+
+template <typename T, int VEC, int LPR, int U>
+int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
+           const Epilogue& epi, float* partial, cudaStream_t st) {
+  constexpr int kBlock = 256;
+  constexpr int groups_per_block = (kBlock / 32) * (32 / LPR);
+  const int64_t groups = static_cast<int64_t>(c.num_segs) + N;
+  if (groups == 0) return GDA_OK;
+  const unsigned grid = static_cast<unsigned>(ceil_div(groups, groups_per_block));
+  k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
+                                                 c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
+                                                 static_cast<int>(N), H, epi, partial);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+inline int pow2_at_least(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <typename T, int VEC>
+int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
+                 const Epilogue& epi, float* partial, cudaStream_t st) {
+  int lanes = pow2_at_least(static_cast<int>(ceil_div(H, VEC)));
+  if (lanes > 32) lanes = 32;
+  if (lanes < 4) lanes = 4;
+  constexpr int U = (VEC * sizeof(T) >= 16) ? 8 : 4;
+  switch (lanes) {
+    case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
+    case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
+    case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
+    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
+  }
+}
+
+template <typename T, int WIDE>
+int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, int64_t ldy, int H,
+             const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+             void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  GDA_REQUIRE(g != nullptr, "gda_spmm: graph is NULL");
+  GDA_REQUIRE(H > 0, "gda_spmm: H must be positive");
+  if (g->N == 0) return GDA_OK;
+  GDA_REQUIRE(X && Y, "gda_spmm: NULL feature pointer");
+  GDA_REQUIRE(X != Y, "gda_spmm: X and Y must not alias");
+  GDA_REQUIRE(ldx >= H && ldy >= H, "gda_spmm: leading dimension smaller than H");
+  GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm: dropout_p outside [0,1)");
+  const Csr& c = transpose ? g->csr_t : g->csr;
+  const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need))
+    return fail(GDA_E_WORKSPACE, "gda_spmm: workspace smaller than gda_spmm_workspace_bytes()");
+  Epilogue epi;
+  epi.bias = bias;
+  epi.flags = epi_flags;
+  epi.thresh = dropout_threshold(dropout_p);
+  epi.scale = 1.0f / (1.0f - dropout_p);
+  epi.seed = seed;
+  epi.seed_offset = seed_offset;
+  float* partial = static_cast<float*>(workspace);
+  const bool wide_ok = (H % WIDE == 0) && (ldx % WIDE == 0) && (ldy % WIDE == 0) &&
+                       (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
+  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st);
+  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st);
+}
+
+}  // namespace
+}  // namespace gda
+
+extern "C" {
+
+int64_t gda_spmm_workspace_bytes(const gda_graph_t* g, int transpose, int H) {
+  if (!g || H <= 0) return 0;
+  const gda::Csr& c = transpose ? g->csr_t : g->csr;
+  return static_cast<int64_t>(c.num_segs) * H * static_cast<int64_t>(sizeof(float));
+}
+
+int gda_spmm_f32(const gda_graph_t* g, int transpose, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                 int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                 const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  return gda::spmm_any<float, 4>(g, transpose, X, ldx, Y, ldy, H, bias, epi_flags, dropout_p, seed, seed_offset,
+                                 workspace, workspace_bytes, gda::as_stream(stream));
+}
+
+int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ldx, void* Y, int64_t ldy,
+                  int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                  const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  return gda::spmm_any<__nv_bfloat16, 8>(g, transpose, static_cast<const __nv_bfloat16*>(X), ldx,
+                                         static_cast<__nv_bfloat16*>(Y), ldy, H, bias, epi_flags, dropout_p,
+                                         seed, seed_offset, workspace, workspace_bytes, gda::as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+"""Graph containers and loaders for the hot path.
+
+PyG (``torch_geometric.data.Data`` / ``Batch`` / ``NeighborLoader`` /
+``DataLoader``) is what the reference's ``fit`` feeds the models
+(pygda/models/a2gnn.py:254-288); it is not installable here, so these are the
+duck-typed equivalents the estimators in ``pygda_b200.models`` accept.  Any
+object with ``.x [N,F]``, ``.edge_index [2,E] int64``, ``.y`` (and ``.batch``
+in graph mode) and ``.to(device)`` works, including real PyG objects.
+"""
+import torch
+
+
+class Data:
+    def __init__(self, x=None, edge_index=None, y=None, batch=None, num_graphs=None, **kw):
+        self.x = x
+        self.edge_index = edge_index
+        self.y = y
+        self.batch = batch
+        self.num_graphs = num_graphs
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    # ---- PyG-compatible surface used by the reference's estimators ----
+    def to(self, device, non_blocking=False):
+        dev = torch.device(device)
+        if all((not torch.is_tensor(v)) or v.device == dev for v in self.__dict__.values()):
+            return self                      # same no-op PyG performs when already resident
+        out = self.__class__.__new__(self.__class__)
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) else v
+        ei, src = out.__dict__.get("edge_index"), self.edge_index
+        if torch.is_tensor(ei) and ei is not src:
+            # The normalised CSR is a pure function of edge_index: key the device copy by the
+            # tensor it was copied from, so that re-sending the same host graph every step
+            # (what the reference's fit loop does, a2gnn.py:311-312) maps to one gda_graph_t.
+            ei._gda_key = getattr(src, "_gda_key", None) or (
+                "src", src.data_ptr(), src._version, tuple(src.shape), str(src.device))
+            ei._gda_keepalive = getattr(src, "_gda_keepalive", src)
+        return out
+
+    def pin_memory(self):
+        out = Data.__new__(Data)
+        for k, v in self.__dict__.items():
+            out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v
+        return out
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+    @property
+    def num_features(self):
+        return self.x.size(1)
+
+    def __len__(self):
+        # ``len(Batch)`` is the number of graphs (used by pygda/models/a2gnn.py:270-271)
+        return self.num_graphs if self.num_graphs is not None else 1
+
+    def __repr__(self):
+        parts = [f"{k}={list(v.shape)}" for k, v in self.__dict__.items() if torch.is_tensor(v)]
+        return "Data(" + ", ".join(parts) + ")"
+
+
+class Batch(Data):
+    @staticmethod
+    def from_data_list(graphs):
+        xs, eis, ys, bs, ptr = [], [], [], [], [0]
+        off = 0
+        for g, d in enumerate(graphs):
+            xs.append(d.x)
+            eis.append(d.edge_index + off)
+            ys.append(d.y.view(-1))
+            bs.append(torch.full((d.x.size(0),), g, dtype=torch.long, device=d.x.device))
+            off += d.x.size(0)
+            ptr.append(off)
+        return Batch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), y=torch.cat(ys),
+                     batch=torch.cat(bs), num_graphs=len(graphs),
+                     ptr=torch.tensor(ptr, dtype=torch.long))
+
+
+class NeighborLoader:
+    """Full-batch stand-in for ``NeighborLoader(data, [-1]*L, batch_size=N)``:
+    one batch per epoch = the whole graph, node order preserved, edges regrouped
+    by destination (stable), exactly what PyG yields when every node is a seed
+    (SURVEY.md Appendix A.6).  Sampled mini-batching (``batch_size < N``) is the
+    reference's own scaling tool and is replaced here by node partitioning
+    (DESIGN.md section 6); asking for it raises."""
+
+    def __init__(self, data, num_neighbors, batch_size=None, **kw):
+        n = data.x.shape[0]
+        if batch_size is not None and batch_size != n:
+            raise NotImplementedError(
+                "pygda_b200 runs node-level models full-batch (batch_size=0); "
+                "neighbour-sampled mini-batches are not part of the accelerated path")
+        self.data = data
+        ei = data.edge_index
+        order = torch.argsort(ei[1], stable=True)
+        extra = {k: v for k, v in data.__dict__.items()
+                 if k not in ("x", "edge_index", "y", "batch", "num_graphs")}
+        self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
+                           batch=data.batch, num_graphs=data.num_graphs, **extra)
+
+    def __iter__(self):
+        yield self._batch
+
+    def __len__(self):
+        return 1
+
+
+class DataLoader:
+    """``DataLoader(dataset, batch_size, shuffle)`` over a sequence of graphs."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+        self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        order = torch.randperm(n).tolist() if self.shuffle else list(range(n))
+        for s in range(0, n, self.batch_size):
+            yield Batch.from_data_list([self.dataset[i] for i in order[s:s + self.batch_size]])

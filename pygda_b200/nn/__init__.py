@@ -1,0 +1,6 @@
+"""``pygda.nn`` modules on the accelerated path."""
+from .reverse_layer import GradReverse
+from .prop_gcn_conv import PropGCNConv, GCNConv, gcn_norm
+from .a2gnn_base import A2GNNBase
+
+__all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase"]

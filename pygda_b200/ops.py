@@ -1,0 +1,431 @@
+"""torch.autograd.Function shims over the C ABI (include/gda.h).
+
+Everything numeric on the hot path is a libgda kernel; torch supplies device
+memory, the autograd tape and the current stream.  Backward passes run on
+PyTorch's autograd thread: every call therefore reads the *current* stream of
+the calling thread.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import gda, load
+
+EPI_RELU, EPI_DROPOUT = 1, 2
+_NULL = C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return _NULL if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError("pygda_b200 kernels run on the GPU only (no CPU fallback)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ raw kernels
+def spmm(graph, x, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, out=None,
+         seed_offset=None):
+    """One aggregation Y = A_hat X (or A_hat^T X) with the optional fused epilogue."""
+    x = x if x.is_contiguous() else x.contiguous()
+    n, h = x.shape
+    if n != graph.num_nodes:
+        raise ValueError(f"x has {n} rows but the graph has {graph.num_nodes} nodes")
+    if out is None:
+        out = torch.empty_like(x)
+    ws = graph.workspace(transpose, h)
+    flags = (EPI_RELU if relu else 0) | (EPI_DROPOUT if dropout_p > 0 else 0)
+    args = (graph.handle, int(bool(transpose)), _p(x), h, _p(out), h, h, _p(bias), flags,
+            float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_offset), _p(ws), ws.numel(),
+            _stream())
+    if x.dtype == torch.float32:
+        gda.spmm_f32(*args)
+    elif x.dtype == torch.bfloat16:
+        gda.spmm_bf16(*args)
+    else:
+        raise TypeError(f"aggregation supports float32 and bfloat16 features, got {x.dtype}")
+    return out
+
+
+def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0,
+           seed_offset=None):
+    """A_hat^k X with ping-pong buffers; the epilogue is applied on the last step."""
+    if k == 0:
+        raise ValueError("spmm_k needs k >= 1")
+    cur, bufs = x, [None, None]
+    for i in range(k):
+        last = i == k - 1
+        dst = bufs[i & 1]
+        if dst is None:
+            dst = bufs[i & 1] = torch.empty_like(x)
+        cur = spmm(graph, cur, transpose, bias if last else None, relu and last,
+                   dropout_p if last else 0.0, seed, out=dst, seed_offset=seed_offset)
+    return cur
+
+
+def gemm(a, b, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None):
+    """out[M,N] = alpha * op(a) @ op(b) + beta * out   (fp32, row-major)."""
+    a, b = _f32c(a), _f32c(b)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    kb, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if k != kb:
+        raise ValueError(f"gemm inner dimensions differ: {k} vs {kb}")
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    nbytes = load().gda_gemm_workspace_bytes(int(trans_a), int(trans_b), m, n, k)
+    ws = _workspace(nbytes, a.device)
+    gda.gemm_f32(int(trans_a), int(trans_b), m, n, k, float(alpha), _p(a), a.stride(0), _p(b),
+                 b.stride(0), float(beta), _p(out), out.stride(0), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def colsum(x):
+    x = _f32c(x)
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    gda.colsum_f32(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream())
+    return out
+
+
+def scale(x, alpha):
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    gda.scale_f32(_p(y), _p(x), x.numel(), float(alpha), _stream())
+    return y
+
+
+class DropoutRng:
+    """Seeds for the counter-based dropout masks.
+
+    The reference draws dropout masks from the CUDA generator and the MMD sample
+    indices from the CPU generator (pygda/utils/mmd.py:148-149); to keep the latter
+    bit-exact nothing here touches the CPU generator.  seed = f(torch.cuda seed,
+    call counter); ``offset`` is an optional device uint64 added inside the kernels so
+    that a captured CUDA graph gets a fresh mask per replay (gda_counter_inc)."""
+
+    def __init__(self):
+        self.counter = 0
+        self.offset = None
+
+    def next(self):
+        self.counter += 1
+        base = torch.cuda.initial_seed() if torch.cuda.is_available() else torch.initial_seed()
+        return (base * 0x9E3779B97F4A7C15 + self.counter * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+    def enable_device_offset(self, device):
+        self.offset = torch.zeros(1, dtype=torch.int64, device=device)
+        return self.offset
+
+    def advance_offset(self):
+        if self.offset is not None:
+            gda.counter_inc(_p(self.offset), _stream())
+
+
+dropout_rng = DropoutRng()
+
+
+def next_seed():
+    return dropout_rng.next()
+
+
+# ------------------------------------------------------------------ autograd nodes
+class PropagateFn(torch.autograd.Function):
+    """A_hat^k x; backward (A_hat^T)^k g.  (prop_gcn_conv.py:208-210 / cached_gcn_conv.py:138)"""
+
+    @staticmethod
+    def forward(ctx, x, graph, k):
+        ctx.graph, ctx.k = graph, k
+        return spmm_k(graph, x, k)
+
+    @staticmethod
+    def backward(ctx, g):
+        return spmm_k(ctx.graph, g.contiguous(), ctx.k, transpose=True), None, None
+
+
+class GraphConvFn(torch.autograd.Function):
+    """y = A_hat^k (x W^T) + b as ONE tape node (PropGCNConv.forward,
+    prop_gcn_conv.py:205-213; CachedGCNConv.forward with ``w_in_out``,
+    cached_gcn_conv.py:130-138,171-172).  k = 0 is the plain Linear + bias."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, k, w_in_out):
+        x = _f32c(x)
+        w = _f32c(weight)
+        h = gemm(x, w, trans_b=not w_in_out)
+        if k > 0:
+            y = spmm_k(graph, h, k, bias=bias)
+        elif bias is not None:
+            y = h
+            gda.bias_act_dropout_fwd(_p(h), _p(bias), _p(y), h.shape[0], h.shape[1], 0, 0.0, 0, _NULL, _stream())
+        else:
+            y = h
+        ctx.save_for_backward(x, w)
+        ctx.graph, ctx.k, ctx.w_in_out, ctx.has_bias = graph, k, w_in_out, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _f32c(gy)
+        gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        g0 = spmm_k(ctx.graph, gy, ctx.k, transpose=True) if ctx.k > 0 else gy
+        gw = gx = None
+        if ctx.needs_input_grad[1]:
+            # W [out,in]: dW = g0^T x ; W [in,out]: dW = x^T g0
+            gw = gemm(x, g0, trans_a=True) if ctx.w_in_out else gemm(g0, x, trans_a=True)
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g0, w, trans_b=ctx.w_in_out)
+        return gx, gw, gb, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear: y = x W^T + b (heads at a2gnn_base.py:67,70; udagcn_base.py:155-162)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, w = _f32c(x), _f32c(weight)
+        y = gemm(x, w, trans_b=True)
+        if bias is not None:
+            gda.bias_act_dropout_fwd(_p(y), _p(bias), _p(y), y.shape[0], y.shape[1], 0, 0.0, 0, _NULL, _stream())
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _f32c(gy)
+        gx = gemm(gy, w) if ctx.needs_input_grad[0] else None
+        gw = gemm(gy, x, trans_a=True) if ctx.needs_input_grad[1] else None
+        gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+class ActDropoutFn(torch.autograd.Function):
+    """dropout(relu(x)) (or dropout alone) with the keep mask regenerated from the seed."""
+
+    @staticmethod
+    def forward(ctx, x, act, p, seed):
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        rows = x.shape[0] if x.dim() > 1 else 1
+        cols = x.numel() // max(rows, 1)
+        off = dropout_rng.offset if p > 0 else None
+        gda.bias_act_dropout_fwd(_p(x), _NULL, _p(y), rows, cols, act, float(p), seed, _p(off), _stream())
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, float(p), seed, rows, cols, off)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        act, p, seed, rows, cols, off = ctx.cfg
+        gy = _f32c(gy)
+        gx = torch.empty_like(gy)
+        gda.bias_act_dropout_bwd(_p(gy), _p(y), _p(gx), _NULL, rows, cols, act, p, seed, _p(off), _stream())
+        return gx, None, None, None
+
+
+def act_dropout(x, act, p, training):
+    """``dropout(act(x))`` as the reference applies it (a2gnn_base.py:136-138).
+    ``act`` is a callable; relu is fused, anything else is applied by the caller's
+    callable and only the dropout runs here."""
+    import torch.nn.functional as F
+    p_eff = float(p) if training else 0.0
+    if act is F.relu or act is torch.relu:
+        return ActDropoutFn.apply(x, 1, p_eff, next_seed() if p_eff > 0 else 0)
+    if act is not None:
+        x = act(x)
+    if p_eff > 0:
+        return ActDropoutFn.apply(x, 0, p_eff, next_seed())
+    return x
+
+
+class GradReverse(torch.autograd.Function):
+    """pygda/nn/reverse_layer.py:4-66: identity forward, -alpha * g backward."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        ctx.alpha = alpha
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return scale(g, -float(ctx.alpha)), None
+
+
+class SoftmaxCEFn(torch.autograd.Function):
+    """mean CE(log_softmax(logits), labels); labels=None means row r has label (r >= split)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, split):
+        z = _f32c(logits)
+        rows, c = z.shape
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z)
+        if labels is not None:
+            labels = labels.contiguous()
+            if labels.dtype != torch.int64 or labels.numel() != rows:
+                raise ValueError("labels must be int64 with one entry per row")
+        gda.softmax_ce_fwd_bwd(_p(z), rows, c, z.stride(0), _p(labels), int(split), _p(loss), _p(dz), _stream())
+        ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return _scale_by_scalar(dz, g), None, None
+
+
+class SoftmaxEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        z = _f32c(logits)
+        rows, c = z.shape
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z)
+        gda.softmax_entropy_fwd_bwd(_p(z), rows, c, z.stride(0), _p(loss), _p(dz), _stream())
+        ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return _scale_by_scalar(dz, g)
+
+
+def _scale_by_scalar(t, g):
+    """t * g for a 0-dim DEVICE scalar g, without a host sync."""
+    out = torch.empty_like(t)
+    gs = g.reshape(1).to(torch.float32)
+    gda.scale_dev_f32(_p(out), _p(t), t.numel(), 1.0, _p(gs), _stream())
+    return out
+
+
+class CombineFn(torch.autograd.Function):
+    """sum_i w_i * t_i over 0-dim device scalars (the loss combination at
+    models/a2gnn.py:183-209, udagcn.py:189-199) in one tiny kernel."""
+
+    @staticmethod
+    def forward(ctx, weights, *terms):
+        n = len(terms)
+        ts = [t.reshape(1).to(torch.float32) for t in terms]
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        ws = (C.c_float * n)(*[float(w) for w in weights])
+        out = torch.empty((), dtype=torch.float32, device=ts[0].device)
+        gda.combine_scalars(n, ptrs, ws, _p(out), _stream())
+        ctx.weights = [float(w) for w in weights]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.reshape(1).to(torch.float32).contiguous()
+        outs = []
+        for w in ctx.weights:
+            y = torch.empty((), dtype=torch.float32, device=g.device)
+            gda.scale_f32(_p(y), _p(g), 1, w, _stream())
+            outs.append(y)
+        return (None, *outs)
+
+
+def combine(pairs):
+    """pairs: [(scalar_tensor, weight), ...] -> sum_i weight_i * tensor_i."""
+    return CombineFn.apply([w for _, w in pairs], *[t for t, _ in pairs])
+
+
+class MMDFn(torch.autograd.Function):
+    """pygda/utils/mmd.py:109-158 with the sample indices as inputs."""
+
+    @staticmethod
+    def forward(ctx, src, tgt, src_idx, tgt_idx, kernel_mul, kernel_num):
+        src, tgt = _f32c(src), _f32c(tgt)
+        times, b = src_idx.shape
+        d = src.shape[1]
+        if tgt.shape[1] != d or tgt_idx.shape != src_idx.shape:
+            raise ValueError("MMD: source/target feature widths and sample shapes must match")
+        nbytes = load().gda_mmd_workspace_bytes(times, b, d)
+        ws = _workspace(nbytes, src.device)
+        loss = torch.empty((), dtype=torch.float32, device=src.device)
+        gda.mmd_fwd(_p(src), src.stride(0), _p(tgt), tgt.stride(0), d, _p(src_idx), _p(tgt_idx), times, b,
+                    float(kernel_mul), int(kernel_num), _p(loss), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(src, tgt, src_idx, tgt_idx, ws)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        src, tgt, src_idx, tgt_idx, ws = ctx.saved_tensors
+        times, b = src_idx.shape
+        d = src.shape[1]
+        gs, gt = torch.empty_like(src), torch.empty_like(tgt)
+        gda.fill_f32(_p(gs), gs.numel(), 0.0, _stream())
+        gda.fill_f32(_p(gt), gt.numel(), 0.0, _stream())
+        gscale = g.reshape(1).to(torch.float32).contiguous()
+        gda.mmd_bwd(_p(src), src.stride(0), _p(tgt), tgt.stride(0), d, _p(src_idx), _p(tgt_idx), times, b,
+                    _p(gscale), _p(gs), gs.stride(0), _p(gt), gt.stride(0), _p(ws), ws.numel(), _stream())
+        return gs, gt, None, None, None, None
+
+
+class SegmentMeanFn(torch.autograd.Function):
+    """global_mean_pool over a sorted batch vector given as ptr [G+1]."""
+
+    @staticmethod
+    def forward(ctx, x, ptr):
+        x = _f32c(x)
+        g = ptr.numel() - 1
+        out = torch.empty(g, x.shape[1], dtype=torch.float32, device=x.device)
+        gda.segment_mean_fwd(_p(x), x.stride(0), _p(ptr), g, x.shape[1], _p(out), _stream())
+        ctx.save_for_backward(ptr)
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (ptr,) = ctx.saved_tensors
+        gout = _f32c(gout)
+        gx = torch.empty(ctx.rows, gout.shape[1], dtype=torch.float32, device=gout.device)
+        gda.segment_mean_bwd(_p(gout), _p(ptr), ptr.numel() - 1, gout.shape[1], _p(gx), gx.stride(0), _stream())
+        return gx, None
+
+
+def global_mean_pool(x, batch, size=None):
+    """PyG ``global_mean_pool`` (a2gnn_base.py:141): ``batch`` sorted graph ids."""
+    if batch is None:
+        ptr = torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device)
+        return SegmentMeanFn.apply(x, ptr)
+    g = int(batch.max().item()) + 1 if size is None else int(size)
+    counts = torch.bincount(batch, minlength=g)
+    ptr = torch.zeros(g + 1, dtype=torch.int64, device=x.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return SegmentMeanFn.apply(x, ptr)
+
+
+def graph_conv(x, weight, bias, graph, k, w_in_out=False):
+    return GraphConvFn.apply(x, weight, bias, graph, int(k), bool(w_in_out))
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)
+
+
+def softmax_cross_entropy(logits, labels):
+    return SoftmaxCEFn.apply(logits, labels, 0)
+
+
+def domain_cross_entropy(logits, split):
+    """CE against the implicit domain labels [0]*split + [1]*(rows-split) (a2gnn.py:200-204)."""
+    return SoftmaxCEFn.apply(logits, None, int(split))
+
+
+def softmax_entropy(logits):
+    return SoftmaxEntropyFn.apply(logits)

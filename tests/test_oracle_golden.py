@@ -1,0 +1,104 @@
+"""The oracle against the vectors produced by executing the reference's own source
+files (tests/golden/make_golden.py).  Index results bit-exact, fp32 within 1e-5."""
+import torch
+
+from oracle import mmd as OM
+from oracle import nn as ONN
+from oracle import pyg_ops as P
+from oracle.data import Data
+from oracle.models import A2GNN as OracleA2GNN
+from conftest import assert_close, load_golden
+
+
+def test_gcn_norm_cases():
+    g = load_golden("gcn_norm")
+    kw = {"plain": {}, "improved": {"improved": True}, "weighted": {"edge_weight": g["edge_weight"]},
+          "noloops": {"add_self_loops_": False}}
+    for name, case in g["cases"].items():
+        k = kw[name]
+        ei, w = P.gcn_norm_by_col(g["edge_index"], k.get("edge_weight"), g["num_nodes"],
+                                  k.get("improved", False), k.get("add_self_loops_", True))
+        assert torch.equal(ei, case["edge_index_out"]), name
+        assert_close(w, case["weight_out"], 1e-6, name)
+
+
+def test_cached_norm():
+    g = load_golden("cached_norm")
+    ei, w = P.gcn_norm_by_row(g["edge_index"], g["num_nodes"])
+    assert torch.equal(ei, g["edge_index_out"])
+    assert_close(w, g["weight_out"], 1e-6, "cached norm")
+
+
+def test_prop_gcn_conv_forward_backward():
+    g = load_golden("prop_gcn_conv")
+    conv = ONN.PropGCNConv(12, 8)
+    conv.load_state_dict(g["state"])
+    for k in (0, 1, 3):
+        x = g["x"].clone().requires_grad_(True)
+        conv.zero_grad()
+        y = conv(x, g["edge_index"], k)
+        (y * torch.linspace(-1, 1, y.numel()).view_as(y)).sum().backward()
+        assert_close(y, g["out"][k], 1e-5, f"out k={k}")
+        assert_close(conv.lin.weight.grad, g["grad_w"][k], 1e-5, f"grad_w k={k}")
+        assert_close(x.grad, g["grad_x"][k], 1e-5, f"grad_x k={k}")
+
+
+def test_cached_gcn_conv():
+    g = load_golden("cached_gcn_conv")
+    conv = ONN.CachedGCNConv(12, 8)
+    conv.load_state_dict(g["state"])
+    assert_close(conv(g["x"], g["edge_index"], "c"), g["out"], 1e-5, "cached conv")
+
+
+def test_mmd_value_grads_and_index_draws():
+    g = load_golden("mmd")
+    torch.manual_seed(g["seed"])
+    s_idx, t_idx = OM.draw_mmd_indices(70, 55, g["sampling_num"], g["times"])
+    assert torch.equal(s_idx, g["source_idx"]) and torch.equal(t_idx, g["target_idx"])
+    s, t = g["source"].clone().requires_grad_(True), g["target"].clone().requires_grad_(True)
+    loss = OM.MMD(s, t, indices=(s_idx, t_idx))
+    loss.backward()
+    assert_close(loss, g["loss"], 1e-5, "mmd loss")
+    assert_close(s.grad, g["grad_source"], 1e-5, "mmd grad source")
+    assert_close(t.grad, g["grad_target"], 1e-5, "mmd grad target")
+    assert_close(OM.get_mmd(g["source"][:50], g["target"][:50]), g["get_mmd_full"], 1e-5, "get_MMD")
+
+
+def test_grad_reverse():
+    g = load_golden("grad_reverse")
+    x = g["x"].clone().requires_grad_(True)
+    y = ONN.GradReverse.apply(x, g["alpha"])
+    y.backward(torch.ones_like(y) * 2.0)
+    assert torch.equal(y, g["y"]) and torch.allclose(x.grad, g["grad"])
+
+
+def _run_a2gnn(name):
+    g = load_golden(name)
+    est = OracleA2GNN(device="cpu", **g["hparams"])
+    est.a2gnn.load_state_dict(g["state"])
+    est.a2gnn.train()
+    est.mmd_indices = (g["source_idx"], g["target_idx"])
+    src, tgt = Data(**g["source"]), Data(**g["target"])
+    loss, s_logits, t_logits = est.forward_model(src, tgt, g["alpha"])
+    est.a2gnn.zero_grad()
+    loss.backward()
+    assert_close(loss, g["loss"], 1e-5, name + " loss")
+    assert_close(s_logits, g["source_logits"], 1e-5, name + " source logits")
+    assert_close(t_logits, g["target_logits"], 1e-5, name + " target logits")
+    for k, p in est.a2gnn.named_parameters():
+        assert_close(p.grad, g["grads"][k], 1e-4, name + " grad " + k)
+
+
+def test_a2gnn_forward_model_mmd():
+    _run_a2gnn("a2gnn_mmd")
+
+
+def test_a2gnn_forward_model_adv():
+    _run_a2gnn("a2gnn_adv")
+
+
+def test_a2gnn_mmd_indices_follow_cpu_generator():
+    g = load_golden("a2gnn_mmd")
+    torch.manual_seed(g["seed"])
+    s_idx, t_idx = OM.draw_mmd_indices(60, 50)
+    assert torch.equal(s_idx, g["source_idx"]) and torch.equal(t_idx, g["target_idx"])
