@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- A2GNN training epochs/sec on the BASELINE.json config-2 workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (hyper-parameters of
+benchmark/node/run_citation.sh:92): synthetic citation-shaped source/target graphs,
+per domain 100 000 nodes / 1 000 000 directed edges / 6 775 features / 5 classes, fp32;
+A2GNN with 2 PropGCNConv layers, hid 128, s_pnums 0, t_pnums 10, dropout 0.5, MMD weight 10,
+Adam lr 0.01 wd 0.005.  Full-batch node mode: one epoch == one optimiser step
+(pygda/models/a2gnn.py:300-319); per-epoch sklearn F1 + printing are excluded from both arms.
+
+One JSON line on stdout (rank 0):
+  value     epochs/sec with the inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the estimator API from pinned HOST buffers: every step copies
+            x / edge_index / y of both graphs host->device and reads the loss back
+  roofline  aggregation kernel (A_hat x, H=128, target graph): algorithmic bytes per launch
+            B_alg = 4(N+1) + 8 nnz + 2*4*N*H  divided by the mean per-launch CUDA-event time
+            measured in an instrumented repeat of the timed steps; peak = MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restatement of the reference's torch op sequence) on this
+            box's host cores, on a bounded sample (see `sample`)
+`--impl reference` prints the reference arm alone: the oracle on the host CPU.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(nodes=100_000, edges=1_000_000, feats=6775, classes=5, hid=128, layers=2, s_pnums=0,
+           t_pnums=10, dropout=0.5, weight=10, lr=0.01, weight_decay=0.005, epochs=200)
+METRIC = "a2gnn_train_epochs_per_sec"
+UNIT = "epochs/s"
+
+
+def workload_name():
+    return ("A2GNN synthetic citation-shape %dk nodes / %dM edges / %d feat / %d classes, fp32 "
+            "(BASELINE.json configs[1])" % (CFG["nodes"] // 1000, CFG["edges"] // 1_000_000,
+                                            CFG["feats"], CFG["classes"]))
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.thread, self.gpu = [], None, None, str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", self.gpu], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(scale=20, mmd_times_full=5, threads=None):
+    """One bounded sample of the reference arm: an oracle A2GNN train step
+    (forward_model + zero_grad + backward + Adam.step, pygda/models/a2gnn.py:314-319) on a
+    1/scale-size pair of graphs with ONE MMD sample, plus a stand-alone timing of that MMD
+    sample; full-step estimate = scale * (t_step - t_mmd) + 5 * t_mmd  (graph terms scale
+    linearly in N and nnz; the MMD term is size-independent: n = 2000 rows, 5 samples)."""
+    import torch
+    from oracle import mmd as OM
+    from oracle.data import Data as OData
+    from oracle.models import A2GNN as OracleA2GNN
+    from pygda_b200.synthetic import domain_pair
+
+    if threads:
+        torch.set_num_threads(threads)
+    n, e = CFG["nodes"] // scale, CFG["edges"] // scale
+    st = cpu_reference_sample.__dict__.setdefault("state", {})
+    if not st:
+        src, tgt = domain_pair(n, e, CFG["feats"], CFG["classes"], seed=0)
+        torch.manual_seed(0)
+        est = OracleA2GNN(CFG["feats"], CFG["hid"], CFG["classes"], num_layers=CFG["layers"],
+                          dropout=CFG["dropout"], s_pnums=CFG["s_pnums"], t_pnums=CFG["t_pnums"],
+                          weight=CFG["weight"], weight_decay=CFG["weight_decay"], lr=CFG["lr"],
+                          epoch=CFG["epochs"], device="cpu")
+        st.update(src=OData(x=src.x, edge_index=src.edge_index, y=src.y),
+                  tgt=OData(x=tgt.x, edge_index=tgt.edge_index, y=tgt.y), est=est)
+    est = st["est"]
+    est.mmd_indices = OM.draw_mmd_indices(n, n, 1000, 1)
+    t0 = time.perf_counter()
+    est.train_step(st["src"], st["tgt"], epoch=0)
+    t_step = time.perf_counter() - t0
+    a = torch.randn(1000, CFG["hid"], requires_grad=True)
+    b = torch.randn(1000, CFG["hid"], requires_grad=True)
+    t0 = time.perf_counter()
+    OM.get_mmd(a, b).backward()              # reference-faithful n x n x d broadcast (mmd.py:44-46)
+    t_mmd = time.perf_counter() - t0
+    full = scale * max(t_step - t_mmd, 0.0) + mmd_times_full * t_mmd
+    return full, t_step, t_mmd
+
+
+def run_reference_arm(args, rank, world):
+    import torch
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scale = 20
+    for _ in range(max(args.warmup, 0) and 1):       # one warm-up sample is enough on the CPU
+        cpu_reference_sample(scale)
+    fulls, steps, mmds = [], [], []
+    t_begin = time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        f, s, m = cpu_reference_sample(scale)
+        fulls.append(f); steps.append(s); mmds.append(m)
+        if time.perf_counter() - t_begin > 150:       # keep the arm within a few minutes
+            break
+    full = statistics.mean(fulls)
+    sample = ("oracle A2GNN train step on a 1/%d-scale graph pair (%d nodes, %d edges, F=%d) with one MMD "
+              "sample; full step estimated as %d*(t_step - t_mmd) + 5*t_mmd; t_step=%.2fs t_mmd=%.2fs, %d samples"
+              % (scale, CFG["nodes"] // scale, CFG["edges"] // scale, CFG["feats"], scale,
+                 statistics.mean(steps), statistics.mean(mmds), len(fulls)))
+    value = 1.0 / full
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(fulls), "warmup": min(args.warmup, 1), "ms_per_step": full * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(), "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def data_bytes(d):
+    import torch
+    return sum(v.numel() * v.element_size() for v in d.__dict__.values() if torch.is_tensor(v))
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pygda_b200 import ops
+    from pygda_b200._lib import load
+    from pygda_b200.graph import graph_for
+    from pygda_b200.models import A2GNN
+    from pygda_b200.optim import Adam
+    from pygda_b200.synthetic import domain_pair
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # Each rank holds one source/target pair of the config-2 shape (weak scaling: per-GPU work
+    # fixed); ranks average weight gradients (see DESIGN.md section 6 for the node-partitioned path).
+    src, tgt = domain_pair(CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=10 * rank,
+                           device=dev)
+    torch.manual_seed(0)
+    model = A2GNN(in_dim=CFG["feats"], hid_dim=CFG["hid"], num_classes=CFG["classes"], mode="node",
+                  num_layers=CFG["layers"], dropout=CFG["dropout"], s_pnums=CFG["s_pnums"],
+                  t_pnums=CFG["t_pnums"], adv=False, weight=CFG["weight"], weight_decay=CFG["weight_decay"],
+                  lr=CFG["lr"], epoch=CFG["epochs"], device=str(dev), verbose=0)
+    model._build_loaders(src, tgt)
+    model.a2gnn = model.init_model()
+    params = list(model.a2gnn.parameters())
+    opt = Adam(params, lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
+
+    class SyncedAdam:
+        """Adam preceded by the weight-gradient all-reduce (mean) across ranks."""
+        def zero_grad(self):
+            opt.zero_grad()
+
+        def step(self):
+            if distributed:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+                off = 0
+                for p in params:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad)); off += p.numel()
+            opt.step()
+
+    sopt = SyncedAdam()
+    step_no = [0]
+
+    def one_step(sb, tb):
+        alpha = model.alpha_at(step_no[0] % CFG["epochs"], CFG["epochs"])
+        step_no[0] += 1
+        loss, _, _, _ = model.train_step(sb, tb, alpha, sopt)
+        return loss
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    warm = args.warmup if args.skip_e2e else max(args.warmup, 3)      # profiling runs may use fewer
+    for _ in range(warm):
+        one_step(s_batch, t_batch)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gda_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = one_step(s_batch, t_batch)
+    ev1.record()
+    barrier()
+    launches = lib.gda_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps / (ms_total / 1e3)
+    final_loss = float(loss.item())
+
+    # ---------------- roofline of the aggregation kernel (instrumented repeat) ----------------
+    ops.PROFILE = []
+    for _ in range(min(args.steps, 5)):
+        one_step(s_batch, t_batch)
+    torch.cuda.synchronize()
+    recs, ops.PROFILE = ops.PROFILE, None
+    tg = graph_for(t_batch.edge_index, CFG["nodes"])
+    n_nodes, nnz, H = CFG["nodes"], tg.nnz, CFG["hid"]
+    b_alg = 4 * (n_nodes + 1) + 8 * nnz + 2 * 4 * n_nodes * H
+    times = [a.elapsed_time(b) for (a, b, meta) in recs if meta == (n_nodes, H, "float32")]
+    spmm_ms = statistics.mean(times) if times else float("nan")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = b_alg / (spmm_ms * 1e-3) / 1e9
+    per_step_spmm = len(times) / max(min(args.steps, 5), 1)
+    roofline = {"bound": "hbm", "kernel": "k_spmm<float,4,32,8> (A_hat x, H=128, N=100k, nnz=%d)" % nnz,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "traffic": None, "alg_bytes_per_launch": b_alg, "us_per_launch": spmm_ms * 1e3,
+                "launches_per_step": per_step_spmm,
+                "share_of_step": per_step_spmm * spmm_ms / (ms_total / args.steps),
+                "how": "CUDA events around each gda_spmm_f32 launch in an instrumented repeat of the timed steps"}
+
+    # ---------------- end to end from pinned host buffers (`e2e`) ----------------
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_total / args.steps,
+                              "gpu_launches": int(launches), "roofline": roofline, "note": "profiling run"}), flush=True)
+        return
+    src_h, tgt_h = src.to("cpu").pin_memory(), tgt.to("cpu").pin_memory()
+    model._build_loaders(src_h, tgt_h)
+    sb_h, tb_h = next(iter(model.source_loader)), next(iter(model.target_loader))
+    sb_h, tb_h = sb_h.pin_memory(), tb_h.pin_memory()
+    h2d = data_bytes(sb_h) + data_bytes(tb_h)
+    del src, tgt, s_batch, t_batch
+    torch.cuda.empty_cache()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        one_step(sb_h, tb_h).item()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        one_step(sb_h, tb_h).item()              # host->device copies + loss read-back every step
+    t1.record()
+    barrier()
+    t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "hid": CFG["hid"], "layers": CFG["layers"],
+                       "s_pnums": CFG["s_pnums"], "t_pnums": CFG["t_pnums"], "dropout": CFG["dropout"],
+                       "mmd_weight": CFG["weight"], "optimizer": "Adam lr=0.01 wd=0.005",
+                       "epoch_definition": "full-batch: 1 epoch = 1 optimiser step; F1/logging excluded",
+                       "parallelism": "1 graph pair per GPU, weight-gradient all-reduce" if world > 1 else "single GPU",
+                       "l2_policy": "inputs larger than L2 (x is 2.7 GB per domain, streamed every step); "
+                                    "no explicit flush",
+                       "final_loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_reference_sample(20)
+        full, t_step, t_mmd = cpu_reference_sample(20)
+        line["cpu_baseline"] = {
+            "value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle train step on a 1/20-scale graph pair (5000 nodes, 50000 edges, F=6775) with one "
+                      "MMD sample, full step = 20*(t_step - t_mmd) + 5*t_mmd; t_step=%.2fs t_mmd=%.2fs" % (t_step, t_mmd)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: device-resident phase only")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_gpu_arm(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ typedef struct gda_graph gda_graph_t;
 int         gda_version(void);
 int         gda_sm_arch(void);   /* 100: built for sm_100a only */
 const char* gda_last_error(void);
+/* number of kernels this library has launched in this process (statistics for bench.py) */
+uint64_t    gda_launch_count(void);
 
 /* ------------------------------------------------------------------ graph --
  * gda_graph_create replaces, in one device pass, what the reference recomputes
@@ -120,6 +122,22 @@ int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float 
                  const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                  float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
                  gda_stream_t stream);
+
+/* Split-bf16 operands for the tensor-core path.  gda_split_bf16 writes hi = bf16(x) and
+ * lo = bf16(x - hi) as [rows, ld_out] bf16 (ld_out >= cols, multiple of 8, pad columns zeroed;
+ * outputs 16-byte aligned).  gda_gemm_bf16x3 computes C = op(A) op(B) in fp32 from such pairs on
+ * tcgen05 (Ah*Bh + Ah*Bl + Al*Bh, fp32 accumulation in TMEM); lda/ldb are the bf16 leading
+ * dimensions (multiples of 8).  Requirements: N >= 64, K >= 64 (gda_gemm_bf16x3_supported).
+ * A constant operand (the input features x, models/a2gnn.py:181-211) is split once and re-used
+ * by every forward (x W^T) and backward (G^T x) pass. */
+int     gda_split_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, void* hi, void* lo,
+                       int64_t ld_out, gda_stream_t stream);
+int     gda_gemm_bf16x3_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb);
+int64_t gda_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int     gda_gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* a_hi,
+                        const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+                        float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
+                        gda_stream_t stream);
 
 /* ------------------------------------------------------------ elementwise --
  * y = dropout(act(x + bias)) and its backward; act: 0 none, 1 relu.  The keep

@@ -24,6 +24,7 @@ SIGNATURES = {
     "gda_version": (i32, []),
     "gda_sm_arch": (i32, []),
     "gda_last_error": (C.c_char_p, []),
+    "gda_launch_count": (u64, []),
     "gda_graph_create": (i32, [vp, i64, i64, vp, i32, vp, C.POINTER(vp)]),
     "gda_graph_destroy": (i32, [vp]),
     "gda_graph_info": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
@@ -34,6 +35,10 @@ SIGNATURES = {
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_gemm_workspace_bytes": (i64, [i32, i32, i64, i64, i64]),
     "gda_gemm_f32": (i32, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, vp, i64, vp]),
+    "gda_split_bf16": (i32, [vp, i64, i64, i64, vp, vp, i64, vp]),
+    "gda_gemm_bf16x3_supported": (i32, [i64, i64, i64, i64, i64]),
+    "gda_gemm_bf16x3_workspace_bytes": (i64, [i64, i64, i64]),
+    "gda_gemm_bf16x3": (i32, [i32, i32, i64, i64, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
     "gda_bias_act_dropout_fwd": (i32, [vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_bwd": (i32, [vp, vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_colsum_f32": (i32, [vp, i64, i64, i64, vp, vp]),
@@ -54,7 +59,7 @@ SIGNATURES = {
 }
 
 # calls whose int return is a status code to check
-_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is i32 and k not in ("gda_version", "gda_sm_arch")}
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is i32 and k not in ("gda_version", "gda_sm_arch", "gda_gemm_bf16x3_supported")}
 
 
 def load():

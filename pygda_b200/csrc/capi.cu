@@ -1,4 +1,6 @@
 // C-ABI glue: error string, version, graph handle wrappers (see include/gda.h).
+#include <atomic>
+
 #include "graph.cuh"
 
 namespace gda {
@@ -6,6 +8,8 @@ namespace {
 thread_local std::string g_last_error;
 }
 void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace gda
 
 extern "C" {
@@ -13,6 +17,7 @@ extern "C" {
 int gda_version(void) { return GDA_VERSION; }
 int gda_sm_arch(void) { return 100; }
 const char* gda_last_error(void) { return gda::g_last_error.c_str(); }
+uint64_t gda_launch_count(void) { return gda::g_launches.load(std::memory_order_relaxed); }
 
 int gda_graph_create(const int64_t* edge_index, int64_t E, int64_t N, const float* edge_weight, int flags,
                      gda_stream_t stream, gda_graph_t** out) {

@@ -10,6 +10,7 @@
 namespace gda {
 
 void set_error(const std::string& msg);          // capi.cu (thread-local)
+void count_launch();                             // capi.cu (statistics only)
 
 inline int fail(int code, const std::string& msg) {
   set_error(msg);
@@ -26,6 +27,7 @@ inline int fail(int code, const std::string& msg) {
 
 #define GDA_LAUNCH_CHECK()                                                          \
   do {                                                                              \
+    ::gda::count_launch();                                                          \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       return ::gda::fail(GDA_E_CUDA, std::string(__FILE__) + ":" + std::to_string(__LINE__) + \

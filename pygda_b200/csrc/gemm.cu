@@ -42,4 +42,24 @@ int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float 
   return gemm_simt(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
 }
 
+int gda_split_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, void* hi, void* lo, int64_t ld_out,
+                   gda_stream_t stream) {
+  return gda::split_bf16(x, rows, cols, ldx, hi, lo, ld_out, gda::as_stream(stream));
+}
+
+int gda_gemm_bf16x3_supported(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb) {
+  return gda::bf16x3_shape_ok(M, N, K, lda, ldb) ? 1 : 0;
+}
+
+int64_t gda_gemm_bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  return gda::bf16x3_workspace_bytes(M, N, K);
+}
+
+int gda_gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_lo,
+                    int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc,
+                    void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  return gda::gemm_bf16x3(transA, transB, M, N, K, a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, workspace,
+                          workspace_bytes, gda::as_stream(stream));
+}
+
 }  // extern "C"

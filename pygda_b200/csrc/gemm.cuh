@@ -16,4 +16,11 @@ int64_t tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t
 int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* ws, int64_t ws_bytes,
             cudaStream_t st);
+int split_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, void* hi, void* lo, int64_t ldo,
+               cudaStream_t st);
+bool bf16x3_shape_ok(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb);
+int64_t bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_lo,
+                int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc, void* ws,
+                int64_t ws_bytes, cudaStream_t st);
 }  // namespace gda

@@ -109,6 +109,15 @@ __global__ void k_splitk_reduce(const float* __restrict__ part, int splits, int6
 
 }  // namespace
 
+int splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float alpha, float beta, float* C, int64_t ldc,
+                  cudaStream_t st) {
+  const int64_t MN = M * N;
+  if (MN == 0) return GDA_OK;
+  k_splitk_reduce<<<static_cast<unsigned>(ceil_div(MN, 256)), 256, 0, st>>>(part, splits, MN, (int)N, alpha, beta, C, ldc);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
 int simt_splits(int64_t M, int64_t N, int64_t K) {
   const int bn = N > 32 ? 128 : 32;
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, bn);

@@ -1,13 +1,453 @@
-// tcgen05 split-bf16 GEMM -- placeholder until the kernel lands (next milestone):
-// reports "not supported" so gda_gemm_f32 routes everything to the SIMT kernel.
+// Dense GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+// C[M,N] (fp32) = op(A) * op(B) with each fp32 operand given as a SPLIT-BF16 pair
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi), |x - hi - lo| <= 2^-17 |x|).  The product is
+// evaluated as  Ah*Bh + Ah*Bl + Al*Bh  -- three kind::f16 UMMAs per K step accumulating in one
+// fp32 TMEM tile -- which keeps the relative error of every product term below ~2^-16, i.e.
+// inside the 1e-4 fp32 parity bar of the reference's `x @ W^T` (pygda/nn/prop_gcn_conv.py:205),
+// while streaming the same 4 bytes per element as fp32 would.  Plain bf16 or TF32 alone miss
+// that bar (2^-9 / 2^-11 per term).
+//
+// One CTA = one 128x128 output tile (optionally one K split of it), 192 threads:
+//   warp 0    TMA producer : cp.async.bulk.tensor (SWIZZLE_128B boxes) into a 3-stage smem ring
+//   warp 1    MMA issuer   : one elected lane issues tcgen05.mma (M=128, N=128, K=16), commits to
+//                            the stage's `empty` mbarrier; owns the TMEM allocation (128 columns)
+//   warps 2-5 epilogue     : tcgen05.ld 32x32b.x32 -> registers -> global (row = TMEM lane)
+// Operand majors: row-major A[M,K] / B[N,K] are K-major (box 64 x 128, SBO = 1024 B); the
+// transposed forms A[K,M] / B[K,N] are MN-major (two boxes 64 x 64, LBO = 8192 B, SBO = 1024 B),
+// so weight gradients  dW = G^T X  (reduction over the node dimension) need no transposes.
+// Out-of-bounds parts of a box are zero-filled by TMA; the epilogue masks rows/columns.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "gemm.cuh"
 
 namespace gda {
-bool tc_supported(int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, const float*,
-                  const float*) { return false; }
-int64_t tc_workspace_bytes(int, int, int64_t, int64_t, int64_t) { return 0; }
-int gemm_tc(int, int, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t, float,
-            float*, int64_t, void*, int64_t, cudaStream_t) {
-  return fail(GDA_E_UNSUPPORTED, "tcgen05 GEMM not built");
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, TC_THREADS = 192;
+constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand half
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // Ah, Al, Bh, Bl
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp layout): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
+         (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
+         (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+              const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+              float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split, int64_t split_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B wants 1024 B alignment
+  const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
+  const uint32_t tmem_slot = bars + 16 * STAGES + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb_total = (K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(nkb_total, kb_begin + kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapAh); tma_prefetch_desc(&mapAl); tma_prefetch_desc(&mapBh); tma_prefetch_desc(&mapBl);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+        const uint32_t st = tiles + stage * STAGE_BYTES;
+        const uint32_t bar = full0 + 8 * stage;
+        mbar_expect_tx(bar, STAGE_BYTES);
+        const int k0 = (kb_begin + kb) * BK;
+        if (!A_MN) {
+          tma_load_2d(st, &mapAh, bar, k0, m0);
+          tma_load_2d(st + TILE_BYTES, &mapAl, bar, k0, m0);
+        } else {
+          tma_load_2d(st, &mapAh, bar, m0, k0);
+          tma_load_2d(st + TILE_BYTES / 2, &mapAh, bar, m0 + 64, k0);
+          tma_load_2d(st + TILE_BYTES, &mapAl, bar, m0, k0);
+          tma_load_2d(st + TILE_BYTES + TILE_BYTES / 2, &mapAl, bar, m0 + 64, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(st + 2 * TILE_BYTES, &mapBh, bar, k0, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &mapBl, bar, k0, n0);
+        } else {
+          tma_load_2d(st + 2 * TILE_BYTES, &mapBh, bar, n0, k0);
+          tma_load_2d(st + 2 * TILE_BYTES + TILE_BYTES / 2, &mapBh, bar, n0 + 64, k0);
+          tma_load_2d(st + 3 * TILE_BYTES, &mapBl, bar, n0, k0);
+          tma_load_2d(st + 3 * TILE_BYTES + TILE_BYTES / 2, &mapBl, bar, n0 + 64, k0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t st = tiles + stage * STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          // K-major: +32 B per K=16 step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
+          const uint32_t a_off = A_MN ? ks * 2048u : ks * 32u;
+          const uint32_t b_off = B_MN ? ks * 2048u : ks * 32u;
+          const uint32_t a_lbo = A_MN ? TILE_BYTES / 2 : 16u, b_lbo = B_MN ? TILE_BYTES / 2 : 16u;
+          const uint64_t ah = make_desc(st + a_off, a_lbo, 1024u);
+          const uint64_t al = make_desc(st + TILE_BYTES + a_off, a_lbo, 1024u);
+          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + b_off, b_lbo, 1024u);
+          const uint64_t bl = make_desc(st + 3 * TILE_BYTES + b_off, b_lbo, 1024u);
+          umma_bf16(tmem_base, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, ah, bl, idesc, 1u);
+          umma_bf16(tmem_base, al, bh, idesc, 1u);
+        }
+        umma_commit(empty0 + 8 * stage);          // frees the smem stage once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full);                     // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + blockIdx.z * split_stride + static_cast<int64_t>(row) * ldc + n0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0) && (ldc % 4 == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      if (row < M) {
+        const int col0 = n0 + c * 32;
+        if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(crow + c * 32 + 4 * j) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) crow[c * 32 + j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> split bf16
+__global__ void k_split_bf16(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ldx,
+                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ldo) {
+  const int64_t groups = ldo / 8;                               // 8 output columns per thread
+  const int64_t total = rows * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups, c0 = (i % groups) * 8;
+    float v[8];
+    const float* src = x + r * ldx + c0;
+    if (c0 + 8 <= cols && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      h[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      l[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldo + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + r * ldo + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor [outer, inner] with row stride `ld` elements; box = 64 (inner) x box_outer
+int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GDA_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(GDA_E_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string(rc) + ")");
+  return GDA_OK;
+}
+
+int pick_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int64_t nkb = ceil_div(K, BK);
+  if (tiles >= kNumSMs) return 1;
+  int64_t s = (4 * kNumSMs + tiles / 2) / tiles;
+  const int64_t cap = nkb / 8 > 0 ? nkb / 8 : 1;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : static_cast<int>(s);
+}
+
+template <bool A_MN, bool B_MN>
+int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, float* C,
+              int64_t ldc, int64_t M, int64_t N, int64_t K, int splits, int64_t split_stride, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDA_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nkb = static_cast<int>(ceil_div(K, BK));
+  const int kbps = static_cast<int>(ceil_div(nkb, splits));
+  dim3 grid(static_cast<unsigned>(ceil_div(N, BN)), static_cast<unsigned>(ceil_div(M, BM)),
+            static_cast<unsigned>(ceil_div(nkb, kbps)));
+  k_gemm_bf16x3<A_MN, B_MN><<<grid, TC_THREADS, SMEM_BYTES, st>>>(ah, al, bh, bl, C, ldc, (int)M, (int)N, (int)K, kbps,
+                                                                  split_stride);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+}  // namespace
+
+int splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float alpha, float beta, float* C, int64_t ldc,
+                  cudaStream_t st);   // gemm_simt.cu
+
+int64_t round_up8(int64_t x) { return (x + 7) / 8 * 8; }
+
+int split_bf16(const float* x, int64_t rows, int64_t cols, int64_t ldx, void* hi, void* lo, int64_t ldo,
+               cudaStream_t st) {
+  GDA_REQUIRE(rows >= 0 && cols >= 0 && ldx >= cols, "gda_split_bf16: bad shape");
+  GDA_REQUIRE(ldo >= cols && ldo % 8 == 0, "gda_split_bf16: ld_out must be >= cols and a multiple of 8");
+  if (rows == 0 || cols == 0) return GDA_OK;
+  GDA_REQUIRE(x && hi && lo, "gda_split_bf16: NULL pointer");
+  GDA_REQUIRE((reinterpret_cast<uintptr_t>(hi) % 16 == 0) && (reinterpret_cast<uintptr_t>(lo) % 16 == 0),
+              "gda_split_bf16: outputs must be 16-byte aligned");
+  const int64_t total = rows * (ldo / 8);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  k_split_bf16<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, rows, cols, ldx, static_cast<__nv_bfloat16*>(hi),
+                                                             static_cast<__nv_bfloat16*>(lo), ldo);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+bool bf16x3_shape_ok(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb) {
+  return M >= 1 && N >= 64 && K >= 64 && lda % 8 == 0 && ldb % 8 == 0 && M < (int64_t(1) << 31) &&
+         N < (int64_t(1) << 31) && K < (int64_t(1) << 31) && ceil_div(M, BM) <= 65535;
+}
+
+int64_t bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  const int s = pick_splits(M, N, K);
+  return s > 1 ? static_cast<int64_t>(s) * M * N * sizeof(float) : 0;
+}
+
+int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_lo,
+                int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc, void* ws,
+                int64_t ws_bytes, cudaStream_t st) {
+  GDA_REQUIRE(a_hi && a_lo && b_hi && b_lo && C, "gda_gemm_bf16x3: NULL pointer");
+  GDA_REQUIRE(bf16x3_shape_ok(M, N, K, lda, ldb), "gda_gemm_bf16x3: needs N >= 64, K >= 64 and lda, ldb multiples of 8");
+  GDA_REQUIRE(ldc >= N, "gda_gemm_bf16x3: ldc < N");
+  for (const void* p : {a_hi, a_lo, b_hi, b_lo})
+    GDA_REQUIRE(reinterpret_cast<uintptr_t>(p) % 16 == 0, "gda_gemm_bf16x3: operands must be 16-byte aligned");
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  // A row-major [M,K] (K-major): inner = K, outer = M, box 64 x 128.  A^T stored [K,M] (MN-major):
+  // inner = M, outer = K, box 64 x 64.  Same for B with N.
+  const int64_t a_in = transA ? M : K, a_out = transA ? K : M;
+  const int64_t b_in = transB ? K : N, b_out = transB ? N : K;
+  const int a_box = transA ? BK : BM, b_box = transB ? BN : BK;
+  if ((rc = make_map(&ah, a_hi, a_in, a_out, lda, a_box)) || (rc = make_map(&al, a_lo, a_in, a_out, lda, a_box)) ||
+      (rc = make_map(&bh, b_hi, b_in, b_out, ldb, b_box)) || (rc = make_map(&bl, b_lo, b_in, b_out, ldb, b_box)))
+    return rc;
+  const int splits = pick_splits(M, N, K);
+  float* out = C;
+  int64_t out_ld = ldc, stride = 0;
+  if (splits > 1) {
+    const int64_t need = static_cast<int64_t>(splits) * M * N * sizeof(float);
+    if (!ws || ws_bytes < need) return fail(GDA_E_WORKSPACE, "gda_gemm_bf16x3: workspace too small");
+    out = static_cast<float*>(ws); out_ld = N; stride = M * N;
+  }
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  if (!a_mn && !b_mn) rc = launch_tc<false, false>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
+  else if (!a_mn && b_mn) rc = launch_tc<false, true>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
+  else if (a_mn && !b_mn) rc = launch_tc<true, false>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
+  else rc = launch_tc<true, true>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    const int nkb = static_cast<int>(ceil_div(K, BK));
+    const int kbps = static_cast<int>(ceil_div(nkb, splits));
+    const int used = static_cast<int>(ceil_div(nkb, kbps));
+    return splitk_reduce(static_cast<float*>(ws), used, M, N, 1.f, 0.f, C, ldc, st);
+  }
+  return GDA_OK;
+}
+
+// ---- fp32-operand entry used by gda_gemm_f32: split both operands into the workspace first ----
+bool tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t, int64_t, int64_t, const float*,
+                  const float*, const float*) {
+  (void)transA; (void)transB;
+  // worth it only when the SIMT kernel would be compute-bound: >= ~0.5 GFLOP and tensor-core friendly
+  return N >= 64 && K >= 64 && M >= 128 && 2.0 * M * N * K >= 5e8 && encode_fn() != nullptr;
+}
+
+static void f32_layout(int trans, int64_t rows_logical, int64_t cols_logical, int64_t* r, int64_t* c) {
+  // stored shape of op(X): not transposed -> [rows, cols]; transposed -> [cols, rows]
+  *r = trans ? cols_logical : rows_logical;
+  *c = trans ? rows_logical : cols_logical;
+}
+
+int64_t tc_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
+  if (!(N >= 64 && K >= 64 && M >= 128 && 2.0 * M * N * K >= 5e8)) return 0;
+  int64_t ar, ac, br, bc;
+  f32_layout(transA, M, K, &ar, &ac);
+  f32_layout(!transB, N, K, &br, &bc);      // B stored [K,N] unless transB ([N,K])
+  const int64_t a_bytes = 2 * ar * round_up8(ac) * 2, b_bytes = 2 * br * round_up8(bc) * 2;
+  return a_bytes + b_bytes + bf16x3_workspace_bytes(M, N, K) + 1024;
+}
+
+int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+            const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* ws, int64_t ws_bytes,
+            cudaStream_t st) {
+  if (alpha != 1.f || beta != 0.f)
+    return gemm_simt(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ws, ws_bytes, st);
+  if (!ws || ws_bytes < tc_workspace_bytes(transA, transB, M, N, K))
+    return fail(GDA_E_WORKSPACE, "gda_gemm_f32: workspace smaller than gda_gemm_workspace_bytes()");
+  int64_t ar, ac, br, bc;
+  f32_layout(transA, M, K, &ar, &ac);
+  f32_layout(!transB, N, K, &br, &bc);
+  const int64_t alo = round_up8(ac), blo = round_up8(bc);
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256);
+  void* a_hi = p; p += ar * alo * 2;
+  void* a_lo = p; p += ar * alo * 2;
+  void* b_hi = p; p += br * blo * 2;
+  void* b_lo = p; p += br * blo * 2;
+  p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) / 256 * 256);
+  int rc;
+  if ((rc = split_bf16(A, ar, ac, lda, a_hi, a_lo, alo, st))) return rc;
+  if ((rc = split_bf16(B, br, bc, ldb, b_hi, b_lo, blo, st))) return rc;
+  const int64_t rest = ws_bytes - (p - static_cast<char*>(ws));
+  return gemm_bf16x3(transA, transB, M, N, K, a_hi, a_lo, alo, b_hi, b_lo, blo, C, ldc, p, rest, st);
+}
+
 }  // namespace gda

@@ -13,6 +13,8 @@ from ._lib import gda, load
 
 EPI_RELU, EPI_DROPOUT = 1, 2
 _NULL = C.c_void_p(0)
+# bench.py sets this to a list to collect (start_event, end_event, (N, H, dtype)) per aggregation launch
+PROFILE = None
 
 
 def _stream():
@@ -50,12 +52,20 @@ def spmm(graph, x, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0
     args = (graph.handle, int(bool(transpose)), _p(x), h, _p(out), h, h, _p(bias), flags,
             float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_offset), _p(ws), ws.numel(),
             _stream())
+    prof = PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     if x.dtype == torch.float32:
         gda.spmm_f32(*args)
     elif x.dtype == torch.bfloat16:
         gda.spmm_bf16(*args)
     else:
         raise TypeError(f"aggregation supports float32 and bfloat16 features, got {x.dtype}")
+    if prof is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        prof.append((e0, e1, (n, h, str(x.dtype).replace("torch.", ""))))
     return out
 
 
@@ -89,6 +99,75 @@ def gemm(a, b, trans_a=False, trans_b=False, alpha=1.0, beta=0.0, out=None):
     gda.gemm_f32(int(trans_a), int(trans_b), m, n, k, float(alpha), _p(a), a.stride(0), _p(b),
                  b.stride(0), float(beta), _p(out), out.stride(0), _p(ws), ws.numel(), _stream())
     return out
+
+
+class Split:
+    """fp32 matrix as a split-bf16 pair (hi + lo) for the tcgen05 GEMM; ``ld`` in elements."""
+    __slots__ = ("hi", "lo", "rows", "cols", "ld")
+
+    def __init__(self, x):
+        x = _f32c(x)
+        self.rows, self.cols = x.shape
+        self.ld = (self.cols + 7) // 8 * 8
+        self.hi = torch.empty(self.rows, self.ld, dtype=torch.bfloat16, device=x.device)
+        self.lo = torch.empty(self.rows, self.ld, dtype=torch.bfloat16, device=x.device)
+        gda.split_bf16(_p(x), self.rows, self.cols, x.stride(0), _p(self.hi), _p(self.lo), self.ld, _stream())
+
+
+class SplitCache:
+    """Splits of CONSTANT operands (the input features ``data.x``), keyed like the graph
+    cache: a tensor that does not require grad and keeps its identity/version is split once
+    and re-used by every forward and backward pass."""
+
+    def __init__(self, capacity=8):
+        self.capacity, self._d = capacity, {}
+
+    def get(self, x):
+        key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
+        hit = self._d.get(key)
+        if hit is not None:
+            return hit[0]
+        sp = Split(x)
+        if len(self._d) >= self.capacity:
+            self._d.pop(next(iter(self._d)))
+        self._d[key] = (sp, x)          # keeps x alive so the data_ptr cannot be recycled
+        return sp
+
+    def clear(self):
+        self._d.clear()
+
+
+split_cache = SplitCache()
+TC_MIN_FLOPS = 5e8      # below this the SIMT kernel is memory-bound anyway
+
+
+def tc_eligible(m, n, k):
+    return n >= 64 and k >= 64 and 2.0 * m * n * k >= TC_MIN_FLOPS and \
+        load().gda_gemm_bf16x3_supported(m, n, k, 8, 8) == 1
+
+
+def gemm_split(a, b, trans_a, trans_b, m, n, k):
+    """C[m,n] = op(a) op(b) from Split operands on the tcgen05 kernel."""
+    out = torch.empty(m, n, dtype=torch.float32, device=a.hi.device)
+    nbytes = load().gda_gemm_bf16x3_workspace_bytes(m, n, k)
+    ws = _workspace(nbytes, out.device)
+    gda.gemm_bf16x3(int(trans_a), int(trans_b), m, n, k, _p(a.hi), _p(a.lo), a.ld, _p(b.hi), _p(b.lo), b.ld,
+                    _p(out), out.stride(0), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def mm(a, b, trans_a=False, trans_b=False, a_split=None, b_split=None, cache_a=False, cache_b=False):
+    """op(a) @ op(b): tensor cores (split-bf16, fp32-accurate) for the big shapes, SIMT otherwise.
+    Returns (result, a_split, b_split) so callers can re-use the splits in the backward."""
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    n = b.shape[0] if trans_b else b.shape[1]
+    if tc_eligible(m, n, k):
+        if a_split is None:
+            a_split = split_cache.get(a) if cache_a else Split(a)
+        if b_split is None:
+            b_split = split_cache.get(b) if cache_b else Split(b)
+        return gemm_split(a_split, b_split, trans_a, trans_b, m, n, k), a_split, b_split
+    return gemm(a, b, trans_a=trans_a, trans_b=trans_b), a_split, b_split
 
 
 def colsum(x):
@@ -162,7 +241,8 @@ class GraphConvFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, graph, k, w_in_out):
         x = _f32c(x)
         w = _f32c(weight)
-        h = gemm(x, w, trans_b=not w_in_out)
+        const_x = not x.requires_grad          # input features: split once, re-used every pass
+        h, xs, ws = mm(x, w, trans_b=not w_in_out, cache_a=const_x)
         if k > 0:
             y = spmm_k(graph, h, k, bias=bias)
         elif bias is not None:
@@ -172,20 +252,25 @@ class GraphConvFn(torch.autograd.Function):
             y = h
         ctx.save_for_backward(x, w)
         ctx.graph, ctx.k, ctx.w_in_out, ctx.has_bias = graph, k, w_in_out, bias is not None
+        ctx.splits = (xs, ws)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
+        xs, ws = ctx.splits
         gy = _f32c(gy)
         gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         g0 = spmm_k(ctx.graph, gy, ctx.k, transpose=True) if ctx.k > 0 else gy
-        gw = gx = None
+        gw = gx = gs = None
         if ctx.needs_input_grad[1]:
             # W [out,in]: dW = g0^T x ; W [in,out]: dW = x^T g0
-            gw = gemm(x, g0, trans_a=True) if ctx.w_in_out else gemm(g0, x, trans_a=True)
+            if ctx.w_in_out:
+                gw, _, gs = mm(x, g0, trans_a=True, a_split=xs)
+            else:
+                gw, gs, _ = mm(g0, x, trans_a=True, b_split=xs)
         if ctx.needs_input_grad[0]:
-            gx = gemm(g0, w, trans_b=ctx.w_in_out)
+            gx, _, _ = mm(g0, w, trans_b=ctx.w_in_out, a_split=gs, b_split=ws)
         return gx, gw, gb, None, None, None
 
 
@@ -195,19 +280,24 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x, w = _f32c(x), _f32c(weight)
-        y = gemm(x, w, trans_b=True)
+        y, xs, ws = mm(x, w, trans_b=True, cache_a=not x.requires_grad)
         if bias is not None:
             gda.bias_act_dropout_fwd(_p(y), _p(bias), _p(y), y.shape[0], y.shape[1], 0, 0.0, 0, _NULL, _stream())
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
+        ctx.splits = (xs, ws)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
+        xs, ws = ctx.splits
         gy = _f32c(gy)
-        gx = gemm(gy, w) if ctx.needs_input_grad[0] else None
-        gw = gemm(gy, x, trans_a=True) if ctx.needs_input_grad[1] else None
+        gx = gw = gs = None
+        if ctx.needs_input_grad[1]:
+            gw, gs, _ = mm(gy, x, trans_a=True, b_split=xs)
+        if ctx.needs_input_grad[0]:
+            gx, _, _ = mm(gy, w, a_split=gs, b_split=ws)
         gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb
 
