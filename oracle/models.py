@@ -72,3 +72,94 @@ class A2GNN:
         self.a2gnn.eval()
         with torch.no_grad():
             return self.a2gnn(data, self.s_pnums if source else self.t_pnums), data.y
+
+
+class UDAGCN:
+    """pygda/models/udagcn.py:64-308 with ``ppmi=False`` (forward_model :131-201, loop body
+    :277-293).  Note the encoder's dropout layers are always active (oracle/nn.py)."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, mode="node", num_layers=2, adv_dim=40,
+                 weight_decay=3e-3, lr=4e-3, epoch=300, act=F.relu, **kwargs):
+        import itertools
+        self.mode, self.epoch = mode, epoch
+        self.udagcn = ONN.UDAGCNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, act=act,
+                                     ppmi=False, adv_dim=adv_dim)
+        params = itertools.chain(*[m.parameters() for m in self.udagcn.models])
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
+
+    def forward_model(self, source_data, target_data, alpha, epoch):
+        net = self.udagcn
+        es = net.encode(source_data, "source")
+        et = net.encode(target_data, "target")
+        if self.mode == "graph":
+            es = P.global_mean_pool(es, source_data.batch)
+            et = P.global_mean_pool(et, target_data.batch)
+        source_logits = net.cls_model(es)
+        cls_loss = net.loss_func(source_logits, source_data.y)
+        sd = net.domain_model(ONN.GradReverse.apply(es, alpha))
+        td = net.domain_model(ONN.GradReverse.apply(et, alpha))
+        loss_grl = net.loss_func(sd, torch.zeros(sd.size(0)).type(torch.LongTensor)) + \
+            net.loss_func(td, torch.ones(td.size(0)).type(torch.LongTensor))
+        loss = cls_loss + loss_grl
+        target_logits = net.cls_model(et)
+        probs = torch.clamp(F.softmax(target_logits, dim=-1), min=1e-9, max=1.0)
+        loss_entropy = torch.mean(torch.sum(-probs * torch.log(probs), dim=-1))
+        loss = loss + loss_entropy * (epoch / self.epoch * 0.01)
+        return loss, source_logits, target_logits
+
+    def train_step(self, source_data, target_data, epoch=0):
+        for m in self.udagcn.models:
+            m.train()
+        alpha = min((epoch + 1) / self.epoch, 0.05)
+        loss, s_logits, t_logits = self.forward_model(source_data, target_data, alpha, epoch)
+        val = loss.item()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return val, s_logits, t_logits
+
+
+class GRADE:
+    """pygda/models/grade.py:62-301 (forward_model :129-197, loop body :271-287)."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, mode="node", num_layers=2, dropout=0.,
+                 act=F.relu, disc="JS", weight=0.01, weight_decay=0.01, lr=0.001, epoch=200, **kwargs):
+        self.mode, self.disc, self.weight, self.epoch = mode, disc, weight, epoch
+        self.grade = ONN.GRADEBase(in_dim, hid_dim, num_classes, num_layers=num_layers,
+                                   dropout=dropout, act=act, disc=disc, mode=mode)
+        self.optimizer = torch.optim.Adam(self.grade.parameters(), lr=lr, weight_decay=weight_decay)
+        self.mmd_indices, self.mmd_sqdist = None, M.pairwise_sqdist_broadcast
+
+    def _num(self, d):
+        return d.x.size(0) if self.mode == "node" else len(d)
+
+    def forward_model(self, source_data, target_data, alpha):
+        net = self.grade
+        source_logits, source_feats = net(source_data)
+        target_logits, target_feats = net(target_data)
+        loss = F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y)
+        domain_loss = 0
+        labels = torch.tensor([0] * self._num(source_data) + [1] * self._num(target_data))
+        if self.disc == "JS":
+            preds = net.discriminator(ONN.GradReverse.apply(torch.cat([source_feats, target_feats], 0), alpha))
+            domain_loss = net.criterion(preds, labels)
+        elif self.disc == "MMD":
+            mind = min(self._num(source_data), self._num(target_data))
+            domain_loss = M.MMD(source_feats[:mind], target_feats[:mind], indices=self.mmd_indices,
+                                sqdist=self.mmd_sqdist)
+        elif self.disc == "C":
+            s_l_f = torch.cat([source_feats, 8 * net.one_hot_embedding(source_data.y)], dim=1)
+            t_l_f = torch.cat([target_feats, 8 * F.softmax(target_logits, dim=1)], dim=1)
+            preds = net.discriminator(ONN.GradReverse.apply(torch.cat([s_l_f, t_l_f], 0), alpha))
+            domain_loss = net.criterion(preds, labels)
+        return loss + domain_loss * self.weight, source_logits, target_logits
+
+    def train_step(self, source_data, target_data, epoch=0):
+        self.grade.train()
+        alpha = 2 / (1 + np.exp(-10 * epoch / self.epoch)) - 1
+        loss, s_logits, t_logits = self.forward_model(source_data, target_data, alpha)
+        val = loss.item()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return val, s_logits, t_logits

@@ -216,3 +216,41 @@ class UDAGCNBase(nn.Module):
     def encode(self, data, cache_name, mask=None):
         out = self.encoder(data.x, data.edge_index, cache_name)
         return out if mask is None else out[mask]
+
+
+class GRADEBase(nn.Module):
+    """pygda/nn/grade_base.py:8-202."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=1, dropout=0.1, act=F.relu,
+                 disc="JS", mode="node", **kwargs):
+        super().__init__()
+        self.num_classes, self.num_layers, self.dropout, self.act, self.mode = \
+            num_classes, num_layers, dropout, act, mode
+        self.convs = nn.ModuleList([GCNConv(in_dim, hid_dim)])
+        for _ in range(num_layers - 1):
+            self.convs.append(GCNConv(hid_dim, hid_dim))
+        self.cls = nn.Linear(hid_dim, num_classes)
+        width = hid_dim * num_layers + (num_classes if disc == "JS" else num_classes * 2)
+        self.discriminator = nn.Sequential(nn.Linear(width, 2))
+        self.criterion = nn.CrossEntropyLoss()
+
+    def forward(self, data):                                             # :78-115
+        batch = None if self.mode == "node" else data.batch
+        x, feats = self.feat_bottleneck(data.x, data.edge_index, batch)
+        x = self.cls(x)
+        feats.append(x)
+        return x, torch.cat(feats, dim=1)
+
+    def feat_bottleneck(self, x, edge_index, batch):                     # :117-159
+        feats = []
+        for conv in self.convs:
+            x = conv(x, edge_index)
+            x = self.act(x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+            feats.append(x if self.mode == "node" else P.global_mean_pool(x, batch))
+        if self.mode == "graph":
+            x = P.global_mean_pool(x, batch)
+        return x, feats
+
+    def one_hot_embedding(self, labels):
+        return torch.eye(self.num_classes)[labels]

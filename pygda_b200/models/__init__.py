@@ -1,5 +1,7 @@
 """``pygda.models`` estimators on the accelerated path."""
 from .base import BaseGDA
 from .a2gnn import A2GNN
+from .udagcn import UDAGCN
+from .grade import GRADE
 
-__all__ = ["BaseGDA", "A2GNN"]
+__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE"]

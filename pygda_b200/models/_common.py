@@ -1,0 +1,77 @@
+"""What every two-domain estimator of the reference repeats verbatim: loader
+construction (pygda/models/a2gnn.py:254-288 == udagcn.py:205-256 == grade.py:201-252 ==
+adagcn.py:200-251), the epoch loop skeleton and ``predict`` (a2gnn.py:356-411)."""
+import time
+
+import torch
+
+from ..data import DataLoader, NeighborLoader
+from ..metrics import eval_micro_f1
+from ..utils import logger
+
+
+class TwoDomainLoop:
+    def _build_loaders(self, source_data, target_data):
+        if self.mode == 'node':
+            self.num_source_nodes, _ = source_data.x.shape
+            self.num_target_nodes, _ = target_data.x.shape
+            if self.batch_size == 0:
+                self.source_batch_size = source_data.x.shape[0]
+                self.source_loader = NeighborLoader(source_data, self.num_neigh,
+                                                    batch_size=self.source_batch_size)
+                self.target_batch_size = target_data.x.shape[0]
+                self.target_loader = NeighborLoader(target_data, self.num_neigh,
+                                                    batch_size=self.target_batch_size)
+            else:
+                self.source_loader = NeighborLoader(source_data, self.num_neigh, batch_size=self.batch_size)
+                self.target_loader = NeighborLoader(target_data, self.num_neigh, batch_size=self.batch_size)
+        elif self.mode == 'graph':
+            if self.batch_size == 0:
+                self.source_loader = DataLoader(source_data, batch_size=len(source_data), shuffle=True)
+                self.target_loader = DataLoader(target_data, batch_size=len(target_data), shuffle=True)
+            else:
+                self.source_loader = DataLoader(source_data, batch_size=self.batch_size, shuffle=True)
+                self.target_loader = DataLoader(target_data, batch_size=self.batch_size, shuffle=True)
+        else:
+            assert self.mode in ('graph', 'node'), 'Invalid train mode'
+
+    def _fit_loop(self, step_fn):
+        """``step_fn(epoch, source_batch, target_batch) -> (loss, source_logits, source_batch_on_device)``"""
+        start_time = time.time()
+        for epoch in range(self.epoch):
+            epoch_loss = 0
+            epoch_source_logits = None
+            epoch_source_labels = None
+            for idx, (sampled_source_data, sampled_target_data) in enumerate(
+                    zip(self.source_loader, self.target_loader)):
+                loss, source_logits, sampled_source_data = step_fn(epoch, sampled_source_data,
+                                                                  sampled_target_data)
+                epoch_loss += loss.item()
+                if idx == 0:
+                    epoch_source_logits, epoch_source_labels = source_logits, sampled_source_data.y
+                else:
+                    epoch_source_logits = torch.cat((epoch_source_logits, source_logits))
+                    epoch_source_labels = torch.cat((epoch_source_labels, sampled_source_data.y))
+            micro_f1_score = None
+            if self.verbose > 1:
+                # the reference scores F1 every epoch even when nothing is printed; the value is
+                # only ever printed, so it is skipped for verbose <= 1 (no observable change)
+                micro_f1_score = eval_micro_f1(epoch_source_labels, epoch_source_logits.argmax(dim=1))
+            logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
+                   time=time.time() - start_time, verbose=self.verbose, train=True)
+
+    def _predict_loop(self, logits_fn, source):
+        """``predict`` ignores its ``data`` argument in the reference and re-iterates the loaders
+        stored by ``fit``; kept."""
+        loader = self.source_loader if source else self.target_loader
+        logits = labels = None
+        for idx, sampled_data in enumerate(loader):
+            sampled_data = sampled_data.to(self.device)
+            with torch.no_grad():
+                out = logits_fn(sampled_data)
+                if idx == 0:
+                    logits, labels = out, sampled_data.y
+                else:
+                    logits = torch.cat((logits, out))
+                    labels = torch.cat((labels, sampled_data.y))
+        return logits, labels

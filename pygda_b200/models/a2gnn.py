@@ -5,22 +5,19 @@ target_data, alpha) -> (loss, source_logits, target_logits)`` (:146-213), ``fit`
 (:215-336) and ``predict(data, source=False)`` (:356-411, which -- like the
 reference -- ignores ``data`` and re-iterates the loaders stored by ``fit``).
 """
-import time
-
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 from . import BaseGDA
 from .. import ops
-from ..data import DataLoader, NeighborLoader
-from ..metrics import eval_micro_f1
 from ..nn import A2GNNBase
 from ..optim import Adam
-from ..utils import MMD, logger
+from ..utils import MMD
+from ._common import TwoDomainLoop
 
 
-class A2GNN(BaseGDA):
+class A2GNN(TwoDomainLoop, BaseGDA):
     def __init__(self, in_dim, hid_dim, num_classes, mode='node', num_layers=3, dropout=0.,
                  act=F.relu, s_pnums=0, t_pnums=30, adv=False, weight=5, weight_decay=0.,
                  lr=4e-3, epoch=200, device='cuda:0', batch_size=0, num_neigh=-1, verbose=2,
@@ -78,32 +75,6 @@ class A2GNN(BaseGDA):
         target_logits = net(target_data, self.t_pnums, first_layer=t1)                    # :211
         return loss, source_logits, target_logits
 
-    def _build_loaders(self, source_data, target_data):
-        if self.mode == 'node':                                                           # :254-276
-            self.num_source_nodes, _ = source_data.x.shape
-            self.num_target_nodes, _ = target_data.x.shape
-            if self.batch_size == 0:
-                self.source_batch_size = source_data.x.shape[0]
-                self.source_loader = NeighborLoader(source_data, self.num_neigh,
-                                                    batch_size=self.source_batch_size)
-                self.target_batch_size = target_data.x.shape[0]
-                self.target_loader = NeighborLoader(target_data, self.num_neigh,
-                                                    batch_size=self.target_batch_size)
-            else:
-                self.source_loader = NeighborLoader(source_data, self.num_neigh,
-                                                    batch_size=self.batch_size)
-                self.target_loader = NeighborLoader(target_data, self.num_neigh,
-                                                    batch_size=self.batch_size)
-        elif self.mode == 'graph':                                                        # :277-286
-            if self.batch_size == 0:
-                self.source_loader = DataLoader(source_data, batch_size=len(source_data), shuffle=True)
-                self.target_loader = DataLoader(target_data, batch_size=len(target_data), shuffle=True)
-            else:
-                self.source_loader = DataLoader(source_data, batch_size=self.batch_size, shuffle=True)
-                self.target_loader = DataLoader(target_data, batch_size=self.batch_size, shuffle=True)
-        else:
-            assert self.mode in ('graph', 'node'), 'Invalid train mode'
-
     @staticmethod
     def alpha_at(epoch, total):
         p = float(epoch) / total                                                          # :305
@@ -126,47 +97,19 @@ class A2GNN(BaseGDA):
         self.a2gnn = self.init_model(**self.kwargs)
         optimizer = Adam(self.a2gnn.parameters(), lr=self.lr, weight_decay=self.weight_decay)
         self.optimizer = optimizer
-        start_time = time.time()
-        for epoch in range(self.epoch):
-            epoch_loss = 0
-            epoch_source_logits = None
-            epoch_source_labels = None
+
+        def step(epoch, sampled_source_data, sampled_target_data):
             alpha = self.alpha_at(epoch, self.epoch)
-            for idx, (sampled_source_data, sampled_target_data) in enumerate(
-                    zip(self.source_loader, self.target_loader)):
-                loss, source_logits, target_logits, sampled_source_data = self.train_step(
-                    sampled_source_data, sampled_target_data, alpha, optimizer)
-                epoch_loss += loss.item()                                                 # :315
-                if idx == 0:
-                    epoch_source_logits, epoch_source_labels = source_logits, sampled_source_data.y
-                else:
-                    epoch_source_logits = torch.cat((epoch_source_logits, source_logits))
-                    epoch_source_labels = torch.cat((epoch_source_labels, sampled_source_data.y))
-            if self.verbose > 1:
-                # the reference scores F1 every epoch even when it prints nothing; the value is
-                # only ever printed, so it is skipped when verbose <= 1 (no observable change)
-                epoch_source_preds = epoch_source_logits.argmax(dim=1)
-                micro_f1_score = eval_micro_f1(epoch_source_labels, epoch_source_preds)
-            else:
-                micro_f1_score = None
-            logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
-                   time=time.time() - start_time, verbose=self.verbose, train=True)
+            loss, source_logits, _, sampled_source_data = self.train_step(
+                sampled_source_data, sampled_target_data, alpha, optimizer)
+            return loss, source_logits, sampled_source_data
+
+        self._fit_loop(step)
 
     def process_graph(self, data):
         pass
 
     def predict(self, data, source=False):
         self.a2gnn.eval()
-        loader = self.source_loader if source else self.target_loader
         pnums = self.s_pnums if source else self.t_pnums
-        logits = labels = None
-        for idx, sampled_data in enumerate(loader):
-            sampled_data = sampled_data.to(self.device)
-            with torch.no_grad():
-                out = self.a2gnn(sampled_data, pnums)
-                if idx == 0:
-                    logits, labels = out, sampled_data.y
-                else:
-                    logits = torch.cat((logits, out))
-                    labels = torch.cat((labels, sampled_data.y))
-        return logits, labels
+        return self._predict_loop(lambda d: self.a2gnn(d, pnums), source)

@@ -2,5 +2,10 @@
 from .reverse_layer import GradReverse
 from .prop_gcn_conv import PropGCNConv, GCNConv, gcn_norm
 from .a2gnn_base import A2GNNBase
+from .cached_gcn_conv import CachedGCNConv
+from .attention import Attention
+from .udagcn_base import UDAGCNBase
+from .grade_base import GRADEBase
 
-__all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase"]
+__all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "Attention",
+           "UDAGCNBase", "GRADEBase"]

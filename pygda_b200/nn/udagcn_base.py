@@ -1,0 +1,73 @@
+"""UDAGCNBase -- drop-in for pygda/nn/udagcn_base.py:9-267.
+
+``GNN`` (:9-89): L shared-weight ``CachedGCNConv`` layers, act + Dropout(0.1) between layers
+(not after the last).  The reference keeps the dropout layers in a plain Python list (:47), so
+they are never registered and stay in training mode even during ``predict``; reproduced
+(``ops.act_dropout(..., training=True)``).  The ctor's ``dropout`` argument is ignored by the
+reference (:136-151) and here.
+
+``ppmi=True`` needs the PPMI graph builder (pygda/nn/ppmi_conv.py:56-184: 40 rounds of Python
+random walks, hours at benchmark scale), which is out of scope; it
+raises here.  Its consumer -- a weighted aggregation -- is ``CachedGCNConv(edge_weight=...)``."""
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .attention import Attention
+from .cached_gcn_conv import CachedGCNConv
+from .layers import Linear, ReLUDropout
+
+
+class GNN(nn.Module):
+    def __init__(self, in_dim, hid_dim, gnn_type='gcn', num_layers=3, base_model=None, act=F.relu, **kwargs):
+        super().__init__()
+        if gnn_type == 'ppmi':
+            raise NotImplementedError("PPMI graph construction is outside the accelerated path "
+                                      "(SURVEY.md section 8 a9); use ppmi=False")
+        if base_model is None:
+            weights, biases = [None] * num_layers, [None] * num_layers
+        else:
+            weights = [c.weight for c in base_model.conv_layers]
+            biases = [c.bias for c in base_model.conv_layers]
+        self.gnn_type, self.act = gnn_type, act
+        self.dropout_p = [0.1 for _ in weights]              # the unregistered nn.Dropout(0.1) list
+        self.conv_layers = nn.ModuleList()
+        self.conv_layers.append(CachedGCNConv(in_dim, hid_dim, weight=weights[0], bias=biases[0], **kwargs))
+        for idx in range(1, num_layers):
+            self.conv_layers.append(CachedGCNConv(hid_dim, hid_dim, weight=weights[idx], bias=biases[idx], **kwargs))
+
+    def forward(self, x, edge_index, cache_name):
+        for i, conv_layer in enumerate(self.conv_layers):
+            x = conv_layer(x, edge_index, cache_name)
+            if i < len(self.conv_layers) - 1:
+                x = ops.act_dropout(x, self.act, self.dropout_p[i], True)   # always "training"
+        return x
+
+
+class UDAGCNBase(nn.Module):
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0.1, act=F.relu, ppmi=True,
+                 adv_dim=40, **kwargs):
+        super().__init__()
+        self.ppmi = ppmi
+        self.encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, gnn_type='gcn', act=act, num_layers=num_layers)
+        if self.ppmi:
+            self.ppmi_encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, base_model=self.encoder,
+                                    num_layers=num_layers, gnn_type='ppmi', path_len=10)
+        self.cls_model = nn.Sequential(Linear(hid_dim, num_classes))
+        self.domain_model = nn.Sequential(Linear(hid_dim, adv_dim), ReLUDropout(0.1), Linear(adv_dim, 2))
+        self.att_model = Attention(hid_dim)
+        self.models = [self.encoder, self.cls_model, self.domain_model]
+        if self.ppmi:
+            self.models.extend([self.ppmi_encoder, self.att_model])
+        self.loss_func = ops.softmax_cross_entropy
+
+    def gcn_encode(self, data, cache_name, mask=None):
+        encoded_output = self.encoder(data.x, data.edge_index, cache_name)
+        return encoded_output if mask is None else encoded_output[mask]
+
+    def encode(self, data, cache_name, mask=None):
+        gcn_output = self.gcn_encode(data, cache_name, mask)
+        if self.ppmi:
+            ppmi_output = self.ppmi_encoder(data.x, data.edge_index, cache_name)
+            return self.att_model([gcn_output, ppmi_output if mask is None else ppmi_output[mask]])
+        return gcn_output

@@ -135,6 +135,61 @@ def main():
             "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
             "target_logits": t_logits.detach().clone(), "grads": grads}
 
+    # ---- UDAGCN.forward_model, ppmi=False (models/udagcn.py:131-201) -------------------------
+    # The encoder's dropout list is always active in the reference (udagcn_base.py:47); the RNG
+    # streams cannot match, so both sides run with those layers replaced by identities and the
+    # registered Dropout of the domain model in eval mode.
+    torch.manual_seed(21)
+    uest = ref.udagcn.UDAGCN(in_dim=24, hid_dim=16, num_classes=4, mode='node', num_layers=2, ppmi=False,
+                             adv_dim=10, epoch=300, device='cpu')
+    uest.udagcn = uest.init_model()
+    uest.udagcn.encoder.dropout_layers = [torch.nn.Identity() for _ in uest.udagcn.encoder.dropout_layers]
+    with torch.no_grad():
+        for p in uest.udagcn.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    for m in uest.udagcn.models:
+        m.eval()
+    ustate = {k: v.clone() for k, v in uest.udagcn.state_dict().items()}
+    loss, s_logits, t_logits = uest.forward_model(src, tgt, 0.04, 120)
+    uest.udagcn.zero_grad()
+    loss.backward()
+    out["udagcn"] = {
+        "source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
+        "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y},
+        "hparams": dict(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, ppmi=False, adv_dim=10, epoch=300),
+        "alpha": 0.04, "epoch": 120, "state": ustate, "loss": loss.detach().clone(),
+        "source_logits": s_logits.detach().clone(), "target_logits": t_logits.detach().clone(),
+        "grads": {k: p.grad.clone() for k, p in uest.udagcn.named_parameters() if p.grad is not None}}
+
+    # ---- GRADE.forward_model, disc = JS / MMD / C (models/grade.py:129-197) --------------------
+    for disc in ("JS", "MMD", "C"):
+        torch.manual_seed(31)
+        gest = ref.grade.GRADE(in_dim=24, hid_dim=16, num_classes=4, mode='node', num_layers=2, dropout=0.0,
+                               disc=disc, weight=0.5, device='cpu')
+        gest.grade = gest.init_model()
+        with torch.no_grad():
+            for p in gest.grade.parameters():
+                if p.dim() == 1:
+                    p.uniform_(-0.1, 0.1)
+        gest.grade.train()
+        gstate = {k: v.clone() for k, v in gest.grade.state_dict().items()}
+        torch.manual_seed(55)
+        loss, s_logits, t_logits = gest.forward_model(src, tgt, 0.3)
+        gest.grade.zero_grad()
+        loss.backward()
+        torch.manual_seed(55)
+        s_idx = torch.randint(50, (5, 1000))      # mind = min(60, 50) rows of each side (grade.py:177-182)
+        t_idx = torch.randint(50, (5, 1000))
+        out["grade_" + disc.lower()] = {
+            "source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
+            "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y},
+            "hparams": dict(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, disc=disc, weight=0.5),
+            "alpha": 0.3, "seed": 55, "state": gstate, "source_idx": s_idx, "target_idx": t_idx,
+            "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
+            "target_logits": t_logits.detach().clone(),
+            "grads": {k: p.grad.clone() for k, p in gest.grade.named_parameters() if p.grad is not None}}
+
     for name, blob in out.items():
         torch.save(blob, os.path.join(HERE, name + ".pt"))
         print("wrote", name + ".pt", os.path.getsize(os.path.join(HERE, name + ".pt")), "bytes")

@@ -53,7 +53,16 @@ def load_reference():
     pkg.nn.CachedGCNConv = ns.cached_gcn_conv.CachedGCNConv
     ns.attention = imp("pygda.nn.attention")
 
+    ns.ppmi_conv = imp("pygda.nn.ppmi_conv")
+    pkg.nn.PPMIConv = ns.ppmi_conv.PPMIConv
+    ns.udagcn_base = imp("pygda.nn.udagcn_base")
+    pkg.nn.UDAGCNBase = ns.udagcn_base.UDAGCNBase
+    ns.grade_base = imp("pygda.nn.grade_base")
+    pkg.nn.GRADEBase = ns.grade_base.GRADEBase
+
     ns.base = imp("pygda.models.base")
     pkg.models.BaseGDA = ns.base.BaseGDA
     ns.a2gnn = imp("pygda.models.a2gnn")
+    ns.udagcn = imp("pygda.models.udagcn")
+    ns.grade = imp("pygda.models.grade")
     return ns
