@@ -256,7 +256,8 @@ int gda_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, floa
   GDA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
   if (rows == 0) return GDA_OK;
   GDA_REQUIRE(x != nullptr, "gda_colsum_f32: NULL input");
-  const int64_t blocks = rows < 2 * kNumSMs ? rows : 2 * kNumSMs;
+  const int64_t want = ceil_div(rows, 64);                      // ~64 rows per block
+  const int64_t blocks = want < 16 * kNumSMs ? (want > 0 ? want : 1) : 16 * kNumSMs;
   const int64_t rpb = ceil_div(rows, blocks);
   const int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
   k_colsum<<<static_cast<unsigned>(ceil_div(rows, rpb)), threads, 0, st>>>(x, rows, static_cast<int>(cols), ldx, out, rpb);

@@ -23,7 +23,10 @@ extern "C" {
 int64_t gda_gemm_workspace_bytes(int transA, int transB, int64_t M, int64_t N, int64_t K) {
   int64_t a = gda::simt_workspace_bytes(M, N, K);
   int64_t b = gda::tc_workspace_bytes(transA, transB, M, N, K);
-  return a > b ? a : b;
+  // the skinny dW form is recognised by shape alone here (pointer alignment is checked at call time)
+  int64_t c = (transA && !transB && M <= 16) ? gda::skinny_workspace_bytes(3, M, N, K) : 0;
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
@@ -37,6 +40,10 @@ int gda_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, float 
   GDA_REQUIRE(ldc >= N, "gda_gemm_f32: ldc < N");
   GDA_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gda_gemm_f32: leading dimension too small");
   cudaStream_t st = as_stream(stream);
+  if (alpha == 1.f && beta == 0.f) {
+    const int kind = skinny_kind(transA, transB, M, N, K, lda, ldb, ldc, A, B, C);
+    if (kind) return gemm_skinny(kind, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
+  }
   if (tc_enabled() && tc_supported(transA, transB, M, N, K, lda, ldb, ldc, A, B, C))
     return gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);
   return gemm_simt(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, workspace, workspace_bytes, st);

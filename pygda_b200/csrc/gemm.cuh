@@ -24,3 +24,12 @@ int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const v
                 int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc, void* ws,
                 int64_t ws_bytes, cudaStream_t st);
 }  // namespace gda
+
+namespace gda {
+// skinny heads (gemm_skinny.cu): kind 0 = not applicable
+int skinny_kind(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                const float* A, const float* B, const float* C);
+int64_t skinny_workspace_bytes(int kind, int64_t M, int64_t N, int64_t K);
+int gemm_skinny(int kind, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float beta, float* C, int64_t ldc, void* ws, int64_t ws_bytes, cudaStream_t st);
+}  // namespace gda

@@ -14,7 +14,7 @@
 namespace gda {
 namespace {
 
-constexpr int TILE = 64, DK = 32, THREADS = 256;
+constexpr int TILE = 64, DK = 32, THREADS = 256, JSPLIT = 4;
 
 struct MmdWs {
   float* G;        // [times, n, n]
@@ -181,7 +181,10 @@ k_mmd_bwd(const float* __restrict__ src, int64_t lds, const float* __restrict__ 
   constexpr int JK = 16;
   __shared__ float Gs[JK][TILE + 1];          // G[i, j] stored [j][i]
   __shared__ float Xs[JK][TILE + 4];          // x_j[c]  stored [j][c]
-  const int n = 2 * b, t = blockIdx.z;
+  // blockIdx.z = sample * JSPLIT + slice of the j (reduction) range: 4x more CTAs than tiles
+  const int n = 2 * b, t = blockIdx.z / JSPLIT, js = blockIdx.z % JSPLIT;
+  const int jchunk = ((n + JSPLIT - 1) / JSPLIT + JK - 1) / JK * JK;
+  const int jbeg = js * jchunk, jend = min(n, jbeg + jchunk);
   const int i0 = blockIdx.y * TILE, c0 = blockIdx.x * TILE;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* G = ws.G + (int64_t)t * n * n;
@@ -191,20 +194,20 @@ k_mmd_bwd(const float* __restrict__ src, int64_t lds, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int j0 = 0; j0 < n; j0 += JK) {
+  for (int j0 = jbeg; j0 < jend; j0 += JK) {
 #pragma unroll
     for (int s = 0; s < TILE * JK / THREADS; ++s) {
       const int e = tid + s * THREADS;
       {   // G tile: j fastest in memory
         const int j = e % JK, i = e / JK;
         const int gi = i0 + i, gj = j0 + j;
-        Gs[j][i] = (gi < n && gj < n) ? G[(int64_t)gi * n + gj] : 0.f;
+        Gs[j][i] = (gi < n && gj < jend) ? G[(int64_t)gi * n + gj] : 0.f;
       }
       {   // X tile: c fastest in memory
         const int c = e % TILE, j = e / TILE;
         const int gj = j0 + j, gc = c0 + c;
         float v = 0.f;
-        if (gj < n && gc < d) v = __ldg(sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gj) + gc);
+        if (gj < jend && gc < d) v = __ldg(sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gj) + gc);
         Xs[j][c] = v;
       }
     }
@@ -229,7 +232,7 @@ k_mmd_bwd(const float* __restrict__ src, int64_t lds, const float* __restrict__ 
   for (int i = 0; i < 4; ++i) {
     const int gi = i0 + ty * 4 + i;
     if (gi >= n) continue;
-    const float rs = ws.rowsum[(int64_t)t * n + gi];
+    const float rs = (js == 0) ? ws.rowsum[(int64_t)t * n + gi] : 0.f;   // row-sum term added once
     const float* xi = sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gi);
     float* dst = (gi < b) ? gsrc + src_idx[(int64_t)t * b + gi] * ldgs
                           : gtgt + tgt_idx[(int64_t)t * b + (gi - b)] * ldgt;
@@ -289,7 +292,7 @@ int gda_mmd_bwd(const float* src, int64_t lds, const float* tgt, int64_t ldt, in
     return fail(GDA_E_WORKSPACE, "gda_mmd_bwd: workspace too small");
   const int n = 2 * b;
   MmdWs ws = carve(workspace, times, n);
-  dim3 grid(static_cast<unsigned>(ceil_div(d, TILE)), static_cast<unsigned>(ceil_div(n, TILE)), times);
+  dim3 grid(static_cast<unsigned>(ceil_div(d, TILE)), static_cast<unsigned>(ceil_div(n, TILE)), times * JSPLIT);
   k_mmd_bwd<<<grid, THREADS, 0, as_stream(stream)>>>(src, lds, tgt, ldt, d, src_idx, tgt_idx, b, times, grad_scale,
                                                     gsrc, ldgs, gtgt, ldgt, ws);
   GDA_LAUNCH_CHECK();

@@ -5,14 +5,21 @@
 // and its autograd backward (the same product with A_hat^T).
 //
 // Layout: CSR with int32 indices and fp32 weights (graph.cu); features row-major.
-// A group of LPR lanes owns one output row and walks its neighbour list: the group
-// loads LPR (colidx, weight) pairs with one coalesced access, broadcasts them with
-// shuffles and gathers the neighbour rows with 16-byte loads, U gathers in flight per
-// lane.  Accumulation is fp32, sequential in CSR (= COO) order, hence deterministic.
-// Rows longer than `seg` non-zeros are cut into segments handled by separate groups
-// that are scheduled FIRST; the last segment to finish reduces the partial sums in
-// segment order (still deterministic) -- no hub row is walked by a single warp.
+// A group of LPR lanes (a full warp at H = 128 fp32) owns a BLOCK of consecutive rows and
+// streams the contiguous run of their non-zeros: (colidx, weight) pairs are read LPR at a
+// time with one coalesced access and broadcast by shuffle; neighbour rows are gathered with
+// 16-byte loads, U gathers in flight per lane, batches running straight across row
+// boundaries so that the rowptr -> colidx -> gather latency chain is paid once per block,
+// not once per row (round-1 profile: the row-per-warp form was latency bound at 135 us,
+// DRAM 10 %, L2 18 %; see profiles/).  Accumulation is fp32, sequential in CSR (= COO) order,
+// hence deterministic and equal to a sequential scatter_add.
+// Rows longer than `seg` non-zeros are skipped by the row blocks and handled as `seg`-sized
+// segments by separate groups scheduled FIRST; the last segment to finish reduces the partial
+// sums in segment order (still deterministic) -- no hub row is walked by a single warp.
+// Optional fused epilogue on the output row: + bias, ReLU, dropout (hash mask).
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 
 #include "graph.cuh"
 
@@ -87,6 +94,9 @@ __device__ __forceinline__ void apply_epilogue(float (&acc)[VEC], const Epilogue
   }
 }
 
+// rows per group: the group keeps rowptr[row0 .. row0+RPG] in its lanes
+template <int LPR> struct RowsPerGroup { static constexpr int value = (LPR - 1) < 8 ? (LPR - 1) : 8; };
+
 template <typename T, int VEC, int LPR, int U>
 __global__ void __launch_bounds__(256)
 k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
@@ -95,27 +105,32 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
        const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int N, int H,
        Epilogue epi, float* __restrict__ partial) {
   constexpr int GPW = 32 / LPR;                         // groups per warp
+  constexpr int RPG = RowsPerGroup<LPR>::value;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   const int64_t warp = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t group = warp * GPW + sub;
-  if (group >= static_cast<int64_t>(num_segs) + N) return;
+  const int64_t row_groups = (static_cast<int64_t>(N) + RPG - 1) / RPG;
+  if (group >= static_cast<int64_t>(num_segs) + row_groups) return;
 
-  int row, start, end, L = -1;
-  if (group < num_segs) {                               // a segment of a long row
+  // ---- range of this group: lane i holds the boundary before its i-th row --------------------
+  int row0, nrows, L = -1, rp;
+  if (group < num_segs) {                               // one segment of a long row
     L = __ldg(seg_long + group);
-    row = __ldg(long_rows + L);
+    row0 = __ldg(long_rows + L);
+    nrows = 1;
     const int j = static_cast<int>(group) - __ldg(long_seg_ptr + L);
-    const int rs = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
-    start = rs + j * seg;
-    end = min(start + seg, re);
+    const int s = __ldg(rowptr + row0) + j * seg;
+    const int e = min(s + seg, __ldg(rowptr + row0 + 1));
+    rp = (l == 0) ? s : e;
   } else {
-    row = static_cast<int>(group - num_segs);
-    start = __ldg(rowptr + row);
-    end = __ldg(rowptr + row + 1);
-    if (end - start > seg) return;                      // covered by its segments
+    row0 = static_cast<int>((group - num_segs) * RPG);
+    nrows = min(RPG, N - row0);
+    rp = __ldg(rowptr + row0 + min(l, nrows));
   }
+  const int pos0 = __shfl_sync(gmask, rp, 0, LPR);
+  const int end = __shfl_sync(gmask, rp, nrows, LPR);
 
   for (int cb = 0; cb < H; cb += LPR * VEC) {
     const int c0 = cb + l * VEC;
@@ -124,44 +139,94 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
-    for (int base = start; base < end; base += LPR) {
-      const int idx = base + l;
-      int myc = 0;
-      float myv = 0.f;
-      if (idx < end) { myc = __ldg(colidx + idx); myv = __ldg(vals + idx); }
-      const int cnt = min(LPR, end - base);
-      for (int j = 0; j < cnt; j += U) {
-        float xv[U][VEC];
-        float wv[U];
+    auto flush = [&](int r) {                           // r: row index inside the block
+      if (!active) return;
+      if (L < 0) {
+        apply_epilogue<VEC>(acc, epi, row0 + r, c0, H);
+        VecIO<T, VEC>::store(Y + static_cast<int64_t>(row0 + r) * ldy + c0, acc);
+      } else {
+        float* dst = partial + static_cast<int64_t>(group) * H + c0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int cj = __shfl_sync(gmask, myc, j + u, LPR);
-          wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
-          const bool p = active && (j + u < cnt);
-          if (p) {
-            VecIO<T, VEC>::load(X + static_cast<int64_t>(cj) * ldx + c0, xv[u]);
-          } else {
-            wv[u] = 0.f;
+        for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+      }
+    };
+
+    int r = 0, rs = pos0, re = __shfl_sync(gmask, rp, 1, LPR);
+    int p = pos0;
+    int cbase = pos0 - LPR;                             // chunk currently staged in (myc, myv): none
+    int myc = 0;
+    float myv = 0.f;
+
+    while (true) {
+      // ---- settle: finish rows that end at p, skip long rows (their segments cover them) ----
+      bool moved = true;
+      while (moved && r < nrows) {
+        moved = false;
+        const bool lng = (L < 0) && (re - rs > seg);
+        if (lng) p = re;
+        if (p >= re) {
+          if (!lng) flush(r);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) xv[u][v] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+          for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+          ++r;
+          rs = re;
+          if (r < nrows) re = __shfl_sync(gmask, rp, r + 1, LPR);
+          moved = true;
         }
       }
-    }
+      if (r >= nrows) break;
 
-    if (!active) continue;
-    if (L < 0) {
-      apply_epilogue<VEC>(acc, epi, row, c0, H);
-      VecIO<T, VEC>::store(Y + static_cast<int64_t>(row) * ldy + c0, acc);
-    } else {
-      float* dst = partial + static_cast<int64_t>(group) * H + c0;
+      // ---- stage the next LPR (colidx, weight) pairs when p left the staged chunk ----
+      if (p >= cbase + LPR) {
+        cbase = p;
+        const int idx = cbase + l;
+        myc = 0; myv = 0.f;
+        if (idx < end) { myc = __ldg(colidx + idx); myv = __ldg(vals + idx); }
+      }
+      const int j = p - cbase;
+      const int nvalid = min(U, min(cbase + LPR, end) - p);
+
+      // ---- issue up to U gathers, regardless of row boundaries ----
+      float xv[U][VEC];
+      float wv[U];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(gmask, myc, j + u, LPR);
+        wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
+        if (active && u < nvalid) {
+          VecIO<T, VEC>::load(X + static_cast<int64_t>(cj) * ldx + c0, xv[u]);
+        } else {
+          wv[u] = 0.f;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) xv[u][v] = 0.f;
+        }
+      }
+
+      // ---- consume in order; rows may end (and empty / long rows begin) inside the batch ----
+      int consumed = nvalid;
+      bool stop = false;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < nvalid && !stop) {
+          const int e = p + u;
+          if (e >= re) {
+            do {
+              flush(r);
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+              ++r;
+              rs = re;
+              re = (r < nrows) ? __shfl_sync(gmask, rp, r + 1, LPR) : 0x7fffffff;
+            } while (r < nrows && e >= re);
+            if (r >= nrows || ((L < 0) && (re - rs > seg))) { stop = true; consumed = u; }
+          }
+          if (!stop) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+          }
+        }
+      }
+      p += consumed;
     }
   }
 
@@ -185,8 +250,8 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
 #pragma unroll
           for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(src + v);
         }
-        apply_epilogue<VEC>(acc, epi, row, c0, H);
-        VecIO<T, VEC>::store(Y + static_cast<int64_t>(row) * ldy + c0, acc);
+        apply_epilogue<VEC>(acc, epi, row0, c0, H);
+        VecIO<T, VEC>::store(Y + static_cast<int64_t>(row0) * ldy + c0, acc);
       }
       if (l == 0) counters[L] = 0;                      // ready for the next launch
     }
@@ -198,7 +263,8 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
            const Epilogue& epi, float* partial, cudaStream_t st) {
   constexpr int kBlock = 256;
   constexpr int groups_per_block = (kBlock / 32) * (32 / LPR);
-  const int64_t groups = static_cast<int64_t>(c.num_segs) + N;
+  constexpr int RPG = RowsPerGroup<LPR>::value;
+  const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
   if (groups == 0) return GDA_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(groups, groups_per_block));
   k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
