@@ -248,11 +248,13 @@ def run_gpu_arm(args, rank, world, local_rank):
     launches0 = lib.gda_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures the timed steps only
     ev0.record()
     for _ in range(args.steps):
         loss = one_step(s_batch, t_batch)
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = lib.gda_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)

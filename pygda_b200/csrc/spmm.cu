@@ -135,6 +135,8 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
   for (int cb = 0; cb < H; cb += LPR * VEC) {
     const int c0 = cb + l * VEC;
     const bool active = c0 < H;
+    const T* __restrict__ Xc = X + c0;
+    const unsigned ld32 = static_cast<unsigned>(ldx);   // N * ldx < 2^32 is checked on the host
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -187,46 +189,71 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
       const int nvalid = min(U, min(cbase + LPR, end) - p);
 
       // ---- issue up to U gathers, regardless of row boundaries ----
+      // (round-1 profile: the predicated zero-filling form of this loop cost ~320 warp
+      // instructions per batch; full batches now take a predicate-free path with 32-bit
+      // offset arithmetic)
       float xv[U][VEC];
       float wv[U];
+      if (nvalid == U) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int cj = __shfl_sync(gmask, myc, j + u, LPR);
-        wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
-        if (active && u < nvalid) {
-          VecIO<T, VEC>::load(X + static_cast<int64_t>(cj) * ldx + c0, xv[u]);
-        } else {
-          wv[u] = 0.f;
+        for (int u = 0; u < U; ++u) {
+          const unsigned cj = static_cast<unsigned>(__shfl_sync(gmask, myc, j + u, LPR));
+          wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
+          if (active) VecIO<T, VEC>::load(Xc + static_cast<size_t>(cj * ld32), xv[u]);
+        }
+      } else {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) xv[u][v] = 0.f;
+        for (int u = 0; u < U; ++u) {
+          const unsigned cj = static_cast<unsigned>(__shfl_sync(gmask, myc, j + u, LPR));
+          wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
+          if (active && u < nvalid) VecIO<T, VEC>::load(Xc + static_cast<size_t>(cj * ld32), xv[u]);
         }
       }
 
-      // ---- consume in order; rows may end (and empty / long rows begin) inside the batch ----
-      int consumed = nvalid;
-      bool stop = false;
+      // ---- consume in order ----
+      if (p + nvalid <= re) {                            // whole batch inside the current row
+        if (active) {
+          if (nvalid == U) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u < nvalid && !stop) {
-          const int e = p + u;
-          if (e >= re) {
-            do {
-              flush(r);
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-              ++r;
-              rs = re;
-              re = (r < nrows) ? __shfl_sync(gmask, rp, r + 1, LPR) : 0x7fffffff;
-            } while (r < nrows && e >= re);
-            if (r >= nrows || ((L < 0) && (re - rs > seg))) { stop = true; consumed = u; }
-          }
-          if (!stop) {
+              for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+          } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+            for (int u = 0; u < U; ++u)
+              if (u < nvalid) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+              }
           }
         }
+        p += nvalid;
+      } else {                                           // rows end (empty / long rows may begin) inside
+        int consumed = nvalid;
+        bool stop = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u < nvalid && !stop) {
+            const int e = p + u;
+            if (e >= re) {
+              do {
+                flush(r);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+                ++r;
+                rs = re;
+                re = (r < nrows) ? __shfl_sync(gmask, rp, r + 1, LPR) : 0x7fffffff;
+              } while (r < nrows && e >= re);
+              if (r >= nrows || ((L < 0) && (re - rs > seg))) { stop = true; consumed = u; }
+            }
+            if (!stop && active) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+            }
+          }
+        }
+        p += consumed;
       }
-      p += consumed;
     }
   }
 
@@ -301,6 +328,7 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   GDA_REQUIRE(X && Y, "gda_spmm: NULL feature pointer");
   GDA_REQUIRE(X != Y, "gda_spmm: X and Y must not alias");
   GDA_REQUIRE(ldx >= H && ldy >= H, "gda_spmm: leading dimension smaller than H");
+  GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32), "gda_spmm: N * ldx must be below 2^32 elements");
   GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm: dropout_p outside [0,1)");
   const Csr& c = transpose ? g->csr_t : g->csr;
   const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);

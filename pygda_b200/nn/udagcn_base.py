@@ -54,7 +54,10 @@ class UDAGCNBase(nn.Module):
             self.ppmi_encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, base_model=self.encoder,
                                     num_layers=num_layers, gnn_type='ppmi', path_len=10)
         self.cls_model = nn.Sequential(Linear(hid_dim, num_classes))
-        self.domain_model = nn.Sequential(Linear(hid_dim, adv_dim), ReLUDropout(0.1), Linear(adv_dim, 2))
+        # indices 0..3 as in the reference's Sequential(Linear, ReLU, Dropout(0.1), Linear) so that
+        # state_dict keys match (domain_model.0.*, domain_model.3.*); ReLU+Dropout run as one kernel
+        self.domain_model = nn.Sequential(Linear(hid_dim, adv_dim), ReLUDropout(0.1), nn.Identity(),
+                                          Linear(adv_dim, 2))
         self.att_model = Attention(hid_dim)
         self.models = [self.encoder, self.cls_model, self.domain_model]
         if self.ppmi:
