@@ -331,6 +331,7 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
     GDA_CUDA(cudaMemcpyAsync(g->csr_t.vals, raw_s, sizeof(float) * nnz, cudaMemcpyDeviceToDevice, st));
   }
 
+  g->csr.may_have_empty_rows = g->csr_t.may_have_empty_rows = !loops;   // a self loop in every row
   // 5. long-row segments for both orientations
   if ((rc = build_long_rows(g->csr, N, g->seg, sc, st))) return rc;
   if ((rc = build_long_rows(g->csr_t, N, g->seg, sc, st))) return rc;

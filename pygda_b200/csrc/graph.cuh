@@ -22,6 +22,7 @@ struct Csr {
   int32_t* long_seg_ptr = nullptr;  // [num_long+1] first segment of each long row
   int32_t* seg_long = nullptr;      // [num_segs] long-row index of each segment
   int32_t* counters = nullptr;      // [num_long] arrival counters, zero between launches
+  bool     may_have_empty_rows = true;   // false when every row holds a self loop
 };
 
 }  // namespace gda

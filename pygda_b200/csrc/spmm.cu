@@ -94,6 +94,11 @@ __device__ __forceinline__ void apply_epilogue(float (&acc)[VEC], const Epilogue
   }
 }
 
+inline bool generic_forced() {
+  static const bool on = [] { const char* e = std::getenv("GDA_SPMM_GENERIC"); return e && e[0] == '1'; }();
+  return on;
+}
+
 // rows per group: the group keeps rowptr[row0 .. row0+RPG] in its lanes
 template <int LPR> struct RowsPerGroup { static constexpr int value = (LPR - 1) < 8 ? (LPR - 1) : 8; };
 
@@ -285,6 +290,155 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Lean kernel for graphs in which every row has at least one non-zero (anything built with
+// self loops, i.e. every GCN-normalised graph).  Same decomposition as k_spmm, but the row
+// structure of each staged chunk of LPR non-zeros is turned into two bit masks up front
+// (end-of-row, belongs-to-a-split-long-row), so the inner loop is, per non-zero:
+// 2 SHFL + 2 address ops + 1 LDG.128 + VEC FFMA + 1 mask test -- no per-entry compares
+// against row bounds, no predicated register merging (profiles/r1_b_*: the generic kernel
+// executed 44 warp instructions per non-zero, this one ~12).
+template <typename T, int VEC, int LPR, int U, bool EPI>
+__global__ void __launch_bounds__(256)
+k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
+            int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
+            const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
+            const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int N, int H,
+            Epilogue epi, float* __restrict__ partial) {
+  static_assert(LPR % U == 0, "batches must tile a chunk");
+  constexpr int GPW = 32 / LPR;
+  constexpr int RPG = RowsPerGroup<LPR>::value;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int64_t warp = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t group = warp * GPW + sub;
+  const int64_t row_groups = (static_cast<int64_t>(N) + RPG - 1) / RPG;
+  if (group >= static_cast<int64_t>(num_segs) + row_groups) return;
+
+  int row0, nrows, L = -1, rp;
+  if (group < num_segs) {
+    L = __ldg(seg_long + group);
+    row0 = __ldg(long_rows + L);
+    nrows = 1;
+    const int j = static_cast<int>(group) - __ldg(long_seg_ptr + L);
+    const int s = __ldg(rowptr + row0) + j * seg;
+    const int e = min(s + seg, __ldg(rowptr + row0 + 1));
+    rp = (l == 0) ? s : e;
+  } else {
+    row0 = static_cast<int>((group - num_segs) * RPG);
+    nrows = min(RPG, N - row0);
+    rp = __ldg(rowptr + row0 + min(l, nrows));
+  }
+  // block boundaries, identical in every lane of the group (static shuffle indices)
+  int b[RPG + 1];
+#pragma unroll
+  for (int i = 0; i <= RPG; ++i) b[i] = __shfl_sync(gmask, rp, i < LPR ? i : LPR - 1, LPR);
+  const int end = b[RPG];
+  const unsigned ld32 = static_cast<unsigned>(ldx);
+  const unsigned ldy32 = static_cast<unsigned>(ldy);
+
+  for (int cb = 0; cb < H; cb += LPR * VEC) {
+    const int c0 = cb + l * VEC;
+    const bool active = c0 < H;
+    const T* __restrict__ Xc = X + c0;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    int r = 0;                                          // row (inside the block) being accumulated
+    int p = b[0];
+
+    while (p < end) {
+      // ---- stage LPR non-zeros and classify them ----
+      const int e = p + l;
+      const bool valid = e < end;
+      int myc = 0;
+      float myv = 0.f;
+      if (valid) { myc = __ldg(colidx + e); myv = __ldg(vals + e); }
+      int rid = 0, rid1 = 0, mylen = 0, myend = end;
+#pragma unroll
+      for (int i = 1; i <= RPG; ++i) {
+        rid += (e >= b[i]);
+        rid1 += (e + 1 >= b[i]);
+        if (e >= b[i - 1] && e < b[i]) { mylen = b[i] - b[i - 1]; myend = b[i]; }
+      }
+      const bool skip = valid && (L < 0) && (mylen > seg);
+      const bool isend = valid && !skip && (rid1 != rid);
+      const unsigned skipmask = (__ballot_sync(gmask, skip) >> (sub * LPR)) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
+      unsigned endmask = (__ballot_sync(gmask, isend) >> (sub * LPR)) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
+      if (skipmask & 1u) {                              // p sits in a split long row: jump over it
+        p = __shfl_sync(gmask, myend, 0, LPR);
+        r = __shfl_sync(gmask, rid, 0, LPR) + 1;
+        continue;
+      }
+      const int cnt = skipmask ? (__ffs(skipmask) - 1) : min(LPR, end - p);
+      if (l >= cnt) { myc = 0; myv = 0.f; }             // padding: weight 0, gathers row 0
+
+      for (int j = 0; j < cnt; j += U) {
+        float xv[U][VEC];
+        float wv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned cj = static_cast<unsigned>(__shfl_sync(gmask, myc, j + u, LPR));
+          wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
+          if (active) VecIO<T, VEC>::load(Xc + static_cast<size_t>(cj * ld32), xv[u]);
+        }
+        const unsigned em = endmask >> j;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (active) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+          }
+          if (em & (1u << u)) {                         // last non-zero of row r
+            if (active) {
+              if (L < 0) {
+                if (EPI) apply_epilogue<VEC>(acc, epi, row0 + r, c0, H);
+                VecIO<T, VEC>::store(Y + static_cast<size_t>(static_cast<unsigned>(row0 + r) * ldy32) + c0, acc);
+              } else {
+                float* dst = partial + static_cast<int64_t>(group) * H + c0;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+              }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+            ++r;
+          }
+        }
+      }
+      p += cnt;
+    }
+  }
+
+  if (L >= 0) {                                         // last segment to arrive reduces, in order
+    __threadfence();
+    __syncwarp(gmask);
+    int old = 0;
+    const int first = __ldg(long_seg_ptr + L), nseg = __ldg(long_seg_ptr + L + 1) - first;
+    if (l == 0) old = atomicAdd(counters + L, 1);
+    old = __shfl_sync(gmask, old, 0, LPR);
+    if (old == nseg - 1) {
+      __threadfence();
+      for (int cb = 0; cb < H; cb += LPR * VEC) {
+        const int c0 = cb + l * VEC;
+        if (c0 >= H) continue;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int s = 0; s < nseg; ++s) {
+          const float* src = partial + static_cast<int64_t>(first + s) * H + c0;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(src + v);
+        }
+        if (EPI) apply_epilogue<VEC>(acc, epi, row0, c0, H);
+        VecIO<T, VEC>::store(Y + static_cast<int64_t>(row0) * ldy + c0, acc);
+      }
+      if (l == 0) counters[L] = 0;
+    }
+  }
+}
+
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
            const Epilogue& epi, float* partial, cudaStream_t st) {
@@ -294,9 +448,19 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
   const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
   if (groups == 0) return GDA_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(groups, groups_per_block));
-  k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
-                                                 c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
-                                                 static_cast<int>(N), H, epi, partial);
+  constexpr int UF = U <= LPR ? U : LPR;               // batches must tile a chunk of LPR entries
+  const bool has_epi = epi.bias != nullptr || epi.flags != 0;
+  if (c.may_have_empty_rows || generic_forced()) {
+    k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
+                                                   c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
+                                                   static_cast<int>(N), H, epi, partial);
+  } else if (has_epi) {
+    k_spmm_fast<T, VEC, LPR, UF, true><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial);
+  } else {
+    k_spmm_fast<T, VEC, LPR, UF, false><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial);
+  }
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }
@@ -328,7 +492,8 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   GDA_REQUIRE(X && Y, "gda_spmm: NULL feature pointer");
   GDA_REQUIRE(X != Y, "gda_spmm: X and Y must not alias");
   GDA_REQUIRE(ldx >= H && ldy >= H, "gda_spmm: leading dimension smaller than H");
-  GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32), "gda_spmm: N * ldx must be below 2^32 elements");
+  GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32),
+              "gda_spmm: N * ld must be below 2^32 elements");
   GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm: dropout_p outside [0,1)");
   const Csr& c = transpose ? g->csr_t : g->csr;
   const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
