@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgda.so")
+LIB_PATH = os.environ.get("GDA_LIB_PATH") or os.path.join(_HERE, "libgda.so")   # override: kernel-variant experiments
 
 
 class GdaError(RuntimeError):

@@ -23,6 +23,16 @@
 
 #include "graph.cuh"
 
+#ifndef GDA_SPMM_MIN_CTAS
+#define GDA_SPMM_MIN_CTAS 12
+#endif
+#ifndef GDA_SPMM_BLOCK
+#define GDA_SPMM_BLOCK 64
+#endif
+#ifndef GDA_SPMM_U4
+#define GDA_SPMM_U4 8
+#endif
+
 namespace gda {
 namespace {
 
@@ -299,7 +309,7 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
 // against row bounds, no predicated register merging (profiles/r1_b_*: the generic kernel
 // executed 44 warp instructions per non-zero, this one ~12).
 template <typename T, int VEC, int LPR, int U, bool EPI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GDA_SPMM_BLOCK, GDA_SPMM_MIN_CTAS)
 k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
             int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
             const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
@@ -335,13 +345,14 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
 #pragma unroll
   for (int i = 0; i <= RPG; ++i) b[i] = __shfl_sync(gmask, rp, i < LPR ? i : LPR - 1, LPR);
   const int end = b[RPG];
-  const unsigned ld32 = static_cast<unsigned>(ldx);
-  const unsigned ldy32 = static_cast<unsigned>(ldy);
+  const unsigned ldxb = static_cast<unsigned>(ldx) * static_cast<unsigned>(sizeof(T));   // row pitch in bytes
+  const unsigned ldyb = static_cast<unsigned>(ldy) * static_cast<unsigned>(sizeof(T));
 
   for (int cb = 0; cb < H; cb += LPR * VEC) {
     const int c0 = cb + l * VEC;
     const bool active = c0 < H;
-    const T* __restrict__ Xc = X + c0;
+    const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
+    char* __restrict__ Yc = reinterpret_cast<char*>(Y + c0);
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -381,7 +392,8 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
         for (int u = 0; u < U; ++u) {
           const unsigned cj = static_cast<unsigned>(__shfl_sync(gmask, myc, j + u, LPR));
           wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
-          if (active) VecIO<T, VEC>::load(Xc + static_cast<size_t>(cj * ld32), xv[u]);
+          // one IMAD.WIDE.U32: base + col * pitch
+          if (active) VecIO<T, VEC>::load(reinterpret_cast<const T*>(Xc + static_cast<uint64_t>(cj) * ldxb), xv[u]);
         }
         const unsigned em = endmask >> j;
 #pragma unroll
@@ -394,7 +406,7 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
             if (active) {
               if (L < 0) {
                 if (EPI) apply_epilogue<VEC>(acc, epi, row0 + r, c0, H);
-                VecIO<T, VEC>::store(Y + static_cast<size_t>(static_cast<unsigned>(row0 + r) * ldy32) + c0, acc);
+                VecIO<T, VEC>::store(reinterpret_cast<T*>(Yc + static_cast<uint64_t>(static_cast<unsigned>(row0 + r)) * ldyb), acc);
               } else {
                 float* dst = partial + static_cast<int64_t>(group) * H + c0;
 #pragma unroll
@@ -442,15 +454,16 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
            const Epilogue& epi, float* partial, cudaStream_t st) {
-  constexpr int kBlock = 256;
-  constexpr int groups_per_block = (kBlock / 32) * (32 / LPR);
   constexpr int RPG = RowsPerGroup<LPR>::value;
   const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
+  const bool generic = c.may_have_empty_rows || generic_forced();
+  const int kBlock = generic ? 256 : GDA_SPMM_BLOCK;
+  const int groups_per_block = (kBlock / 32) * (32 / LPR);
   if (groups == 0) return GDA_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(groups, groups_per_block));
   constexpr int UF = U <= LPR ? U : LPR;               // batches must tile a chunk of LPR entries
   const bool has_epi = epi.bias != nullptr || epi.flags != 0;
-  if (c.may_have_empty_rows || generic_forced()) {
+  if (generic) {
     k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
                                                    c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
                                                    static_cast<int>(N), H, epi, partial);
@@ -473,7 +486,7 @@ int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t l
   int lanes = pow2_at_least(static_cast<int>(ceil_div(H, VEC)));
   if (lanes > 32) lanes = 32;
   if (lanes < 4) lanes = 4;
-  constexpr int U = (VEC * sizeof(T) >= 16) ? 8 : 4;
+  constexpr int U = (VEC == 4) ? GDA_SPMM_U4 : 4;               // 8 x float4 or 4 x (8 bf16) gathers in flight per lane
   switch (lanes) {
     case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
     case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
