@@ -25,10 +25,19 @@
 namespace gda {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, TC_THREADS = 192;
-constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB per operand half
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // Ah, Al, Bh, Bl
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64, TC_THREADS = 192;
+// Tile shapes: MT x 128 rows by BN columns per CTA.  (MT, BN) = (2, 128) halves the L2 re-reads of
+// the B operand for tall outputs (round-1 profile: with 128 x 128 tiles every one of 782 CTAs
+// re-read all of W through L2 -- L2 at 70 %, DRAM only 60 %); (1, 256) does the same for the A
+// operand of the weight-gradient GEMM; (1, 128) is the small-shape default.
+template <int MT, int BN_> struct TileCfg {
+  static constexpr int A_BYTES = MT * BM * BK * 2;      // one of (hi, lo)
+  static constexpr int B_BYTES = BN_ * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = MT * BN_;
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -101,17 +110,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
-         (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
+         (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(bn >> 3) << 17) |
          (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MT, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
               float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split, int64_t split_stride) {
+  using Cfg = TileCfg<MT, BN>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
+  static_assert(!(A_MN && MT != 1), "MN-major A uses one 128-row tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B wants 1024 B alignment
@@ -121,7 +134,7 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * (MT * BM), n0 = blockIdx.x * BN;
   const int nkb_total = (K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(nkb_total, kb_begin + kb_per_split);
@@ -133,7 +146,7 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -151,23 +164,25 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
         const uint32_t bar = full0 + 8 * stage;
         mbar_expect_tx(bar, STAGE_BYTES);
         const int k0 = (kb_begin + kb) * BK;
-        if (!A_MN) {
-          tma_load_2d(st, &mapAh, bar, k0, m0);
-          tma_load_2d(st + TILE_BYTES, &mapAl, bar, k0, m0);
-        } else {
-          tma_load_2d(st, &mapAh, bar, m0, k0);
-          tma_load_2d(st + TILE_BYTES / 2, &mapAh, bar, m0 + 64, k0);
-          tma_load_2d(st + TILE_BYTES, &mapAl, bar, m0, k0);
-          tma_load_2d(st + TILE_BYTES + TILE_BYTES / 2, &mapAl, bar, m0 + 64, k0);
+        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + 2 * A_BYTES, sBl = st + 2 * A_BYTES + B_BYTES;
+        if (!A_MN) {                                   // one box 64 x (MT*128)
+          tma_load_2d(sAh, &mapAh, bar, k0, m0);
+          tma_load_2d(sAl, &mapAl, bar, k0, m0);
+        } else {                                       // two boxes 64(m) x 64(k)
+          tma_load_2d(sAh, &mapAh, bar, m0, k0);
+          tma_load_2d(sAh + 8192, &mapAh, bar, m0 + 64, k0);
+          tma_load_2d(sAl, &mapAl, bar, m0, k0);
+          tma_load_2d(sAl + 8192, &mapAl, bar, m0 + 64, k0);
         }
-        if (!B_MN) {
-          tma_load_2d(st + 2 * TILE_BYTES, &mapBh, bar, k0, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &mapBl, bar, k0, n0);
-        } else {
-          tma_load_2d(st + 2 * TILE_BYTES, &mapBh, bar, n0, k0);
-          tma_load_2d(st + 2 * TILE_BYTES + TILE_BYTES / 2, &mapBh, bar, n0 + 64, k0);
-          tma_load_2d(st + 3 * TILE_BYTES, &mapBl, bar, n0, k0);
-          tma_load_2d(st + 3 * TILE_BYTES + TILE_BYTES / 2, &mapBl, bar, n0 + 64, k0);
+        if (!B_MN) {                                   // one box 64 x BN
+          tma_load_2d(sBh, &mapBh, bar, k0, n0);
+          tma_load_2d(sBl, &mapBl, bar, k0, n0);
+        } else {                                       // BN/64 boxes 64(n) x 64(k)
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) {
+            tma_load_2d(sBh + i * 8192, &mapBh, bar, n0 + 64 * i, k0);
+            tma_load_2d(sBl + i * 8192, &mapBl, bar, n0 + 64 * i, k0);
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -175,25 +190,30 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         const uint32_t st = tiles + stage * STAGE_BYTES;
+        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + 2 * A_BYTES, sBl = st + 2 * A_BYTES + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
           // K-major: +32 B per K=16 step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
           const uint32_t a_off = A_MN ? ks * 2048u : ks * 32u;
           const uint32_t b_off = B_MN ? ks * 2048u : ks * 32u;
-          const uint32_t a_lbo = A_MN ? TILE_BYTES / 2 : 16u, b_lbo = B_MN ? TILE_BYTES / 2 : 16u;
-          const uint64_t ah = make_desc(st + a_off, a_lbo, 1024u);
-          const uint64_t al = make_desc(st + TILE_BYTES + a_off, a_lbo, 1024u);
-          const uint64_t bh = make_desc(st + 2 * TILE_BYTES + b_off, b_lbo, 1024u);
-          const uint64_t bl = make_desc(st + 3 * TILE_BYTES + b_off, b_lbo, 1024u);
-          umma_bf16(tmem_base, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, ah, bl, idesc, 1u);
-          umma_bf16(tmem_base, al, bh, idesc, 1u);
+          const uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+          const uint64_t bh = make_desc(sBh + b_off, b_lbo, 1024u);
+          const uint64_t bl = make_desc(sBl + b_off, b_lbo, 1024u);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t ah = make_desc(sAh + mt * (BM * 128) + a_off, a_lbo, 1024u);   // 128 rows x 128 B
+            const uint64_t al = make_desc(sAl + mt * (BM * 128) + a_off, a_lbo, 1024u);
+            const uint32_t d = tmem_base + mt * BN;
+            umma_bf16(d, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(d, ah, bl, idesc, 1u);
+            umma_bf16(d, al, bh, idesc, 1u);
+          }
         }
         umma_commit(empty0 + 8 * stage);          // frees the smem stage once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -205,25 +225,28 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    float* crow = C + blockIdx.z * split_stride + static_cast<int64_t>(row) * ldc + n0;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0) && (ldc % 4 == 0);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      if (row < M) {
-        const int col0 = n0 + c * 32;
-        if (vec_ok && col0 + 32 <= N) {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = m0 + mt * BM + q * 32 + lane;
+      float* crow = C + blockIdx.z * split_stride + static_cast<int64_t>(row) * ldc + n0;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0) && (ldc % 4 == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + c * 32, r);
+        if (row < M) {
+          const int col0 = n0 + c * 32;
+          if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(crow + c * 32 + 4 * j) =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        } else {
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(crow + c * 32 + 4 * j) =
+                  make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) crow[c * 32 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) crow[c * 32 + j] = __uint_as_float(r[j]);
+          }
         }
       }
     }
@@ -233,7 +256,7 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
   }
 }
 
@@ -300,30 +323,39 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, in
   return GDA_OK;
 }
 
-int pick_splits(int64_t M, int64_t N, int64_t K) {
-  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+struct TcPlan { int mt, bn, splits; };
+
+TcPlan plan_for(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K) {
+  TcPlan p{1, 128, 1};
+  if (!a_mn && ceil_div(M, 256) * ceil_div(N, 128) >= kNumSMs) p.mt = 2;       // tall output: share B
+  else if (b_mn && N >= 256) p.bn = 256;                                        // wide output: share A
+  const int64_t tiles = ceil_div(M, p.mt * BM) * ceil_div(N, p.bn);
   const int64_t nkb = ceil_div(K, BK);
-  if (tiles >= kNumSMs) return 1;
-  int64_t s = (4 * kNumSMs + tiles / 2) / tiles;
-  const int64_t cap = nkb / 8 > 0 ? nkb / 8 : 1;
-  if (s > cap) s = cap;
-  return s < 1 ? 1 : static_cast<int>(s);
+  if (tiles < kNumSMs) {
+    int64_t s = (4 * kNumSMs + tiles / 2) / tiles;
+    const int64_t cap = nkb / 8 > 0 ? nkb / 8 : 1;
+    if (s > cap) s = cap;
+    p.splits = s < 1 ? 1 : static_cast<int>(s);
+  }
+  return p;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MT, int BN_>
 int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, int splits, int64_t split_stride, cudaStream_t st) {
+  using Cfg = TileCfg<MT, BN_>;
   static bool attr_set = false;
   if (!attr_set) {
-    GDA_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GDA_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<A_MN, B_MN, MT, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int nkb = static_cast<int>(ceil_div(K, BK));
   const int kbps = static_cast<int>(ceil_div(nkb, splits));
-  dim3 grid(static_cast<unsigned>(ceil_div(N, BN)), static_cast<unsigned>(ceil_div(M, BM)),
+  dim3 grid(static_cast<unsigned>(ceil_div(N, BN_)), static_cast<unsigned>(ceil_div(M, MT * BM)),
             static_cast<unsigned>(ceil_div(nkb, kbps)));
-  k_gemm_bf16x3<A_MN, B_MN><<<grid, TC_THREADS, SMEM_BYTES, st>>>(ah, al, bh, bl, C, ldc, (int)M, (int)N, (int)K, kbps,
-                                                                  split_stride);
+  k_gemm_bf16x3<A_MN, B_MN, MT, BN_><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, C, ldc, (int)M, (int)N,
+                                                                               (int)K, kbps, split_stride);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }
@@ -358,7 +390,10 @@ bool bf16x3_shape_ok(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb) 
 }
 
 int64_t bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  const int s = pick_splits(M, N, K);
+  // upper bound over the operand majors (the plan depends on them only through the tile shape)
+  int s = 1;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) { const int t = plan_for(a, b, M, N, K).splits; if (t > s) s = t; }
   return s > 1 ? static_cast<int64_t>(s) * M * N * sizeof(float) : 0;
 }
 
@@ -376,11 +411,13 @@ int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const v
   // inner = M, outer = K, box 64 x 64.  Same for B with N.
   const int64_t a_in = transA ? M : K, a_out = transA ? K : M;
   const int64_t b_in = transB ? K : N, b_out = transB ? N : K;
-  const int a_box = transA ? BK : BM, b_box = transB ? BN : BK;
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  const TcPlan plan = plan_for(a_mn, b_mn, M, N, K);
+  const int a_box = a_mn ? BK : plan.mt * BM, b_box = b_mn ? BK : plan.bn;
   if ((rc = make_map(&ah, a_hi, a_in, a_out, lda, a_box)) || (rc = make_map(&al, a_lo, a_in, a_out, lda, a_box)) ||
       (rc = make_map(&bh, b_hi, b_in, b_out, ldb, b_box)) || (rc = make_map(&bl, b_lo, b_in, b_out, ldb, b_box)))
     return rc;
-  const int splits = pick_splits(M, N, K);
+  const int splits = plan.splits;
   float* out = C;
   int64_t out_ld = ldc, stride = 0;
   if (splits > 1) {
@@ -388,11 +425,19 @@ int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const v
     if (!ws || ws_bytes < need) return fail(GDA_E_WORKSPACE, "gda_gemm_bf16x3: workspace too small");
     out = static_cast<float*>(ws); out_ld = N; stride = M * N;
   }
-  const bool a_mn = transA != 0, b_mn = transB == 0;
-  if (!a_mn && !b_mn) rc = launch_tc<false, false>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
-  else if (!a_mn && b_mn) rc = launch_tc<false, true>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
-  else if (a_mn && !b_mn) rc = launch_tc<true, false>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
-  else rc = launch_tc<true, true>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st);
+#define GDA_TC_LAUNCH(AM, BM_, MTV, BNV) \
+  rc = launch_tc<AM, BM_, MTV, BNV>(ah, al, bh, bl, out, out_ld, M, N, K, splits, stride, st)
+  if (plan.mt == 2) {
+    if (!b_mn) GDA_TC_LAUNCH(false, false, 2, 128); else GDA_TC_LAUNCH(false, true, 2, 128);
+  } else if (plan.bn == 256) {
+    if (!a_mn) GDA_TC_LAUNCH(false, true, 1, 256); else GDA_TC_LAUNCH(true, true, 1, 256);
+  } else {
+    if (!a_mn && !b_mn) GDA_TC_LAUNCH(false, false, 1, 128);
+    else if (!a_mn && b_mn) GDA_TC_LAUNCH(false, true, 1, 128);
+    else if (a_mn && !b_mn) GDA_TC_LAUNCH(true, false, 1, 128);
+    else GDA_TC_LAUNCH(true, true, 1, 128);
+  }
+#undef GDA_TC_LAUNCH
   if (rc) return rc;
   if (splits > 1) {
     const int nkb = static_cast<int>(ceil_div(K, BK));
