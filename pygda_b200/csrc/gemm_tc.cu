@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace gda {
@@ -328,7 +330,9 @@ struct TcPlan { int mt, bn, splits; };
 TcPlan plan_for(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K) {
   TcPlan p{1, 128, 1};
   if (!a_mn && ceil_div(M, 256) * ceil_div(N, 128) >= kNumSMs) p.mt = 2;       // tall output: share B
-  else if (b_mn && N >= 256) p.bn = 256;                                        // wide output: share A
+  // (1, 256) tiles (share A across a wide output) measured SLOWER on the B200 for dW = G^T X
+  // (581 vs 474 us): only 2 pipeline stages fit; kept compiled for experiments, not selected.
+  else if (b_mn && N >= 256 && std::getenv("GDA_TC_BN256")) p.bn = 256;
   const int64_t tiles = ceil_div(M, p.mt * BM) * ceil_div(N, p.bn);
   const int64_t nkb = ceil_div(K, BK);
   if (tiles < kNumSMs) {

@@ -31,6 +31,13 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         self.adv = adv
         self.weight = weight
         self.mode = mode
+        self.overlap_streams = True
+        self._side = None
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def init_model(self, **kwargs):
         return A2GNNBase(in_dim=self.in_dim, hid_dim=self.hid_dim, num_classes=self.num_classes,
@@ -39,23 +46,34 @@ class A2GNN(TwoDomainLoop, BaseGDA):
 
     def forward_model(self, source_data, target_data, alpha, mmd_indices=None):
         net = self.a2gnn
-        # Layer 1 of the bottleneck is evaluated twice per domain by the reference
-        # (a2gnn.py:181 & :192, :193 & :211) with identical inputs; it is computed once here
-        # and shared (same values -- dropout acts after it).
-        s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
-        t1 = net.first_conv(target_data.x, target_data.edge_index, self.t_pnums)
-
-        source_logits = net(source_data, self.s_pnums, first_layer=s1)                    # :181
-        train_loss = ops.softmax_cross_entropy(source_logits, source_data.y)              # :182
-
         if self.mode == 'node':
             source_batch = target_batch = None
         else:
             source_batch, target_batch = source_data.batch, target_data.batch
-        source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, source_batch,
-                                              self.s_pnums, first_layer=s1)               # :192
+
+        # The source branch (s_pnums is usually 0: dense GEMMs, DRAM-bound) and the target branch
+        # (k propagation steps, L2-latency-bound) are independent until the domain loss, so they
+        # are issued on two CUDA streams and overlap on the GPU; autograd replays each branch's
+        # backward on the stream its forward ran on.
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap_streams else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            # Layer 1 of the bottleneck is evaluated twice per domain by the reference
+            # (a2gnn.py:181 & :192, :193 & :211) with identical inputs; it is computed once here
+            # and shared (same values -- dropout acts after it).
+            s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
+            source_logits = net(source_data, self.s_pnums, first_layer=s1)                # :181
+            train_loss = ops.softmax_cross_entropy(source_logits, source_data.y)          # :182
+            source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, source_batch,
+                                                  self.s_pnums, first_layer=s1)           # :192
+        t1 = net.first_conv(target_data.x, target_data.edge_index, self.t_pnums)
         target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, target_batch,
                                               self.t_pnums, first_layer=t1)               # :193
+        if side is not main:
+            main.wait_stream(side)
+            for t in (source_logits, train_loss, source_features):
+                t.record_stream(main)
         if self.adv:                                                                      # :196-205
             source_dlogits = net.domain_classifier(source_features, alpha)
             target_dlogits = net.domain_classifier(target_features, alpha)
