@@ -136,15 +136,28 @@ def cpu_reference_sample(scale=20, mmd_times_full=5, threads=None):
     return full, t_step, t_mmd
 
 
+def calibrate_threads(scale, cores):
+    """torch's CPU scatter_add / index_select path does not scale to very wide hosts (128 threads
+    were 8x slower than 8 on the B200 box); give the reference its best thread count."""
+    import torch
+    best, best_t = cores, None
+    for n in sorted({min(cores, c) for c in (8, 16, 32, cores)}):
+        torch.set_num_threads(n)
+        cpu_reference_sample(scale)                  # warm-up at this setting
+        full, _, _ = cpu_reference_sample(scale)
+        if best_t is None or full < best_t:
+            best, best_t = n, full
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference_arm(args, rank, world):
     import torch
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     scale = 20
-    for _ in range(max(args.warmup, 0) and 1):       # one warm-up sample is enough on the CPU
-        cpu_reference_sample(scale)
+    cores = calibrate_threads(scale, cores)          # the thread count at which the reference is fastest
     fulls, steps, mmds = [], [], []
     t_begin = time.perf_counter()
     for _ in range(max(args.steps, 1)):
@@ -250,8 +263,10 @@ def run_gpu_arm(args, rank, world, local_rank):
     barrier()
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures the timed steps only
     ev0.record()
+    host_t0 = time.perf_counter()
     for _ in range(args.steps):
         loss = one_step(s_batch, t_batch)
+    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # CPU time to ISSUE a step
     ev1.record()
     barrier()
     torch.cuda.profiler.stop()
@@ -283,11 +298,19 @@ def run_gpu_arm(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = b_alg / (spmm_ms * 1e-3) / 1e9
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json")))
+    except Exception:
+        pass
     per_step_spmm = len(times) / max(min(args.steps, 5), 1)
     roofline = {"bound": "hbm", "kernel": "k_spmm<float,4,32,8> (A_hat x, H=128, N=100k, nnz=%d)" % nnz,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "alg_bytes_per_launch": b_alg, "us_per_launch": spmm_ms * 1e3,
+                "traffic": traffic["bytes_per_launch"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None,
+                "gather_bytes_per_launch": 4 * (n_nodes + 1) + 8 * nnz + 4 * nnz * H + 4 * n_nodes * H,
+                "alg_bytes_per_launch": b_alg, "us_per_launch": spmm_ms * 1e3,
                 "launches_per_step": per_step_spmm,
                 "share_of_step": per_step_spmm * spmm_ms / (ms_total / args.steps),
                 "how": "CUDA events around each gda_spmm_f32 launch in an instrumented repeat of the timed steps"}
@@ -296,7 +319,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_total / args.steps,
-                              "gpu_launches": int(launches), "roofline": roofline, "note": "profiling run"}), flush=True)
+                              "host_issue_ms_per_step": host_issue_ms, "gpu_launches": int(launches),
+                              "roofline": roofline, "note": "profiling run"}), flush=True)
         return
     src_h, tgt_h = src.to("cpu").pin_memory(), tgt.to("cpu").pin_memory()
     model._build_loaders(src_h, tgt_h)
@@ -335,11 +359,10 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+            "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "roofline": roofline,
+            "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cpu_reference_sample(20)
+        cores = calibrate_threads(20, os.cpu_count() or 1)
         full, t_step, t_mmd = cpu_reference_sample(20)
         line["cpu_baseline"] = {
             "value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",

@@ -96,6 +96,20 @@ def main():
                     if k in d:
                         md.append(f"  * {k}: {d[k]}")
             md.append("")
+    # per-launch DRAM traffic of the dominant aggregation kernel for bench.py's roofline.traffic
+    sp = os.path.join(SRC, "spmm_full.ncu-rep")
+    if os.path.exists(sp):
+        import json
+        for d in rep_metrics(sp):
+            if "k_spmm" in d["kernel"] and "float, (int)4, (int)32" in d["kernel"] or "float, 4, 32" in d["kernel"]:
+                def mb(v):
+                    num, unit = v.split()[:2]
+                    return float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                tot = mb(d["dram__bytes_read.sum"]) + mb(d["dram__bytes_write.sum"])
+                json.dump({"bytes_per_launch": tot, "source": f"profiles/{tag}/spmm_full.metrics.csv "
+                           "(dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"},
+                          open(os.path.join(ROOT, "profiles", "spmm_traffic.json"), "w"))
+                break
     open(os.path.join(dst, "summary.md"), "w").write("\n".join(md) + "\n")
     print("wrote", dst)
 
