@@ -108,6 +108,32 @@ int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ld
                   float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                   void* workspace, int64_t workspace_bytes, gda_stream_t stream);
 
+/* ---------------------------------------------------- multi-GPU (peer path) --
+ * 1-D node (row-block) partition over the GPUs of one NVSwitch box (the
+ * reference is single-device).  gda_graph_partition keeps rows [row_lo, row_hi) of a graph built
+ * with self loops and re-encodes columns as (owner rank << 28 | row inside the owner's block),
+ * owner = col / rows_per_rank.  gda_spmm_peer_f32 is gda_spmm_f32 on such a partition with the
+ * input matrix given as one pointer PER RANK (peer_x[q] = rank q's [rows_per_rank, H] block,
+ * CUDA-IPC mapped): neighbour rows owned by other GPUs are read over NVLink inside the kernel,
+ * so the exchange overlaps the gather/FMA work and only referenced rows cross the fabric.
+ * gda_sym_alloc / gda_sym_open give the IPC-shareable buffers; gda_peer_barrier is a device-side
+ * all-ranks barrier (flags in peer memory) that orders the k propagation steps across GPUs:
+ * peer_flags[q] = rank q's uint64[num_peers] flag array (zero-initialised), epoch strictly
+ * increasing; *error_flag (device int, may be NULL) is set if a peer does not arrive in ~10 s. */
+#define GDA_MAX_PEERS 8
+int gda_graph_partition(const gda_graph_t* g, int64_t row_lo, int64_t row_hi, int64_t rows_per_rank,
+                        gda_stream_t stream, gda_graph_t** out);
+int gda_spmm_peer_f32(const gda_graph_t* part, int transpose, const void* const* peer_x, int num_peers,
+                      int my_rank, int64_t ldx, float* Y, int64_t ldy, int H, const float* bias,
+                      int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                      void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
+int gda_sym_open(const unsigned char* handle /* 64 bytes */, void** ptr);
+int gda_sym_close(void* ptr);
+int gda_sym_free(void* ptr);
+int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t epoch, int* error_flag,
+                     gda_stream_t stream);
+
 /* ------------------------------------------------------------ dense GEMM --
  * C[M,N] = alpha * op(A) * op(B) + beta * C, fp32 row-major, op = transpose when
  * the flag is set (A is [M,K] or [K,M]; B is [K,N] or [N,K]).

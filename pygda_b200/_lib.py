@@ -33,6 +33,13 @@ SIGNATURES = {
     "gda_spmm_workspace_bytes": (i64, [vp, i32, i32]),
     "gda_spmm_f32": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_graph_partition": (i32, [vp, i64, i64, i64, vp, C.POINTER(vp)]),
+    "gda_spmm_peer_f32": (i32, [vp, i32, vp, i32, i32, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_sym_alloc": (i32, [i64, C.POINTER(vp), vp]),
+    "gda_sym_open": (i32, [vp, C.POINTER(vp)]),
+    "gda_sym_close": (i32, [vp]),
+    "gda_sym_free": (i32, [vp]),
+    "gda_peer_barrier": (i32, [vp, i32, i32, u64, vp, vp]),
     "gda_gemm_workspace_bytes": (i64, [i32, i32, i64, i64, i64]),
     "gda_gemm_f32": (i32, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, vp, i64, vp]),
     "gda_split_bf16": (i32, [vp, i64, i64, i64, vp, vp, i64, vp]),

@@ -52,4 +52,13 @@ int gda_graph_export_csr(const gda_graph_t* g, int transpose, int32_t* rowptr, i
   return gda::graph_export_csr(g, transpose, rowptr, colidx, vals, gda::as_stream(stream));
 }
 
+int gda_graph_partition(const gda_graph_t* g, int64_t row_lo, int64_t row_hi, int64_t rows_per_rank,
+                        gda_stream_t stream, gda_graph_t** out) {
+  try {
+    return gda::graph_partition(g, row_lo, row_hi, rows_per_rank, gda::as_stream(stream), out);
+  } catch (const std::exception& e) {
+    return gda::fail(GDA_E_CUDA, std::string("gda_graph_partition: ") + e.what());
+  }
+}
+
 }  // extern "C"

@@ -340,8 +340,68 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
   return GDA_OK;
 }
 
+namespace {
+__global__ void k_part_rowptr(const int* __restrict__ rowptr, int64_t lo, int64_t n, int base, int* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = rowptr[lo + i] - base;
+}
+__global__ void k_part_cols(const int* __restrict__ colidx, const float* __restrict__ vals, int64_t base, int64_t nnz,
+                            int rows_per_rank, int* __restrict__ col_out, float* __restrict__ val_out) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int c = colidx[base + e];
+  const int owner = c / rows_per_rank;
+  col_out[e] = (owner << 28) | (c - owner * rows_per_rank);
+  val_out[e] = vals[base + e];
+}
+}  // namespace
+
+// Row block [row_lo, row_hi) of a normalised graph, columns re-encoded as (owner rank, row inside
+// the owner's block) for the peer-memory aggregation kernel.
+int graph_partition(const gda_graph* g, int64_t row_lo, int64_t row_hi, int64_t rows_per_rank, cudaStream_t st,
+                    gda_graph** out) {
+  GDA_REQUIRE(g && out, "gda_graph_partition: NULL argument");
+  *out = nullptr;
+  GDA_REQUIRE(!g->peer_packed, "gda_graph_partition: already a partition");
+  GDA_REQUIRE(!g->csr.may_have_empty_rows, "gda_graph_partition: needs a graph built with self loops");
+  GDA_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= g->N, "gda_graph_partition: bad row range");
+  GDA_REQUIRE(rows_per_rank > 0 && rows_per_rank < (int64_t(1) << 28) &&
+              ceil_div(g->N, rows_per_rank) <= GDA_MAX_PEERS, "gda_graph_partition: bad rows_per_rank");
+  std::unique_ptr<gda_graph> p(new gda_graph());
+  const int64_t n = row_hi - row_lo;
+  p->N = n; p->E = 0; p->flags = g->flags; p->seg = g->seg; p->device = g->device;
+  p->peer_packed = true; p->rows_per_rank = rows_per_rank; p->global_N = g->N; p->row_lo = row_lo;
+  Scratch sc;
+  int rc;
+  for (int t = 0; t < 2; ++t) {
+    const Csr& s = t ? g->csr_t : g->csr;
+    Csr& d = t ? p->csr_t : p->csr;
+    int bounds[2] = {0, 0};
+    GDA_CUDA(cudaMemcpyAsync(&bounds[0], s.rowptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GDA_CUDA(cudaMemcpyAsync(&bounds[1], s.rowptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GDA_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnz = bounds[1] - bounds[0];
+    if (t == 0) p->nnz = nnz;
+    if ((rc = dev_alloc(&d.rowptr, n + 1)) || (rc = dev_alloc(&d.colidx, nnz)) || (rc = dev_alloc(&d.vals, nnz)))
+      return rc;
+    k_part_rowptr<<<blocks_for(n + 1), kThreads, 0, st>>>(s.rowptr, row_lo, n, bounds[0], d.rowptr);
+    GDA_LAUNCH_CHECK();
+    if (nnz > 0) {
+      k_part_cols<<<blocks_for(nnz), kThreads, 0, st>>>(s.colidx, s.vals, bounds[0], nnz, static_cast<int>(rows_per_rank),
+                                                        d.colidx, d.vals);
+      GDA_LAUNCH_CHECK();
+    }
+    d.may_have_empty_rows = false;
+    if ((rc = build_long_rows(d, n, p->seg, sc, st))) return rc;
+  }
+  GDA_CUDA(cudaStreamSynchronize(st));
+  *out = p.release();
+  return GDA_OK;
+}
+
 int graph_export_coo(const gda_graph* g, int64_t* ei_out, float* w_out, cudaStream_t st) {
   GDA_REQUIRE(g && (g->nnz == 0 || (ei_out && w_out)), "gda_graph_export_coo: NULL argument");
+  GDA_REQUIRE(!g->peer_packed, "gda_graph_export_coo: not available for a partition");
   if (g->nnz == 0) return GDA_OK;
   k_export_coo<<<blocks_for(g->nnz), kThreads, 0, st>>>(g->coo_src, g->coo_dst, g->nnz, ei_out);
   GDA_LAUNCH_CHECK();

@@ -37,6 +37,9 @@ struct gda_graph {
   float*   dinv = nullptr;     // [N] deg^-1/2
   gda::Csr csr;                // rows = targets: Y = A_hat X
   gda::Csr csr_t;              // rows = sources: Y = A_hat^T X
+  // row-block partition of a larger graph (peer path): colidx = owner << 28 | local row
+  bool    peer_packed = false;
+  int64_t rows_per_rank = 0, global_N = 0, row_lo = 0;
   ~gda_graph();
 };
 
@@ -46,4 +49,6 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
 int graph_export_coo(const gda_graph* g, int64_t* ei_out, float* w_out, cudaStream_t st);
 int graph_export_csr(const gda_graph* g, int transpose, int32_t* rowptr, int32_t* colidx, float* vals,
                      cudaStream_t st);
+int graph_partition(const gda_graph* g, int64_t row_lo, int64_t row_hi, int64_t rows_per_rank, cudaStream_t st,
+                    gda_graph** out);
 }  // namespace gda

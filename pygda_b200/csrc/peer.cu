@@ -1,0 +1,89 @@
+// Peer (NVLink) memory for the node-partitioned multi-GPU path.
+//
+// Each rank owns a row block of every [N, H] activation.  Instead of all-gathering the whole
+// matrix before every propagation step, the aggregation kernel reads the neighbour rows it
+// needs straight out of the owners' HBM over NVLink (P2P loads inside k_spmm_fast<PEER>), so the
+// transfer overlaps the gather/FMA work row by row and only rows that are actually referenced
+// cross the fabric.  This file provides the plumbing the reference never had (it is
+// single-device): CUDA-IPC symmetric buffers and a device-side
+// all-ranks barrier over flags in peer memory (one tiny kernel, no host round trip).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gda {
+namespace {
+
+struct FlagPtrs { uint64_t* p[GDA_MAX_PEERS]; };
+
+// thread q: tell rank q that `rank` reached `epoch`, then wait until rank q has told us.
+__global__ void k_peer_barrier(FlagPtrs flags, int rank, int num_peers, uint64_t epoch, int* error) {
+  const int q = threadIdx.x;
+  if (q >= num_peers) return;
+  uint64_t* theirs = flags.p[q] + rank;            // slot `rank` of rank q's flag array
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+  const uint64_t* mine = flags.p[rank] + q;
+  const long long t0 = clock64();
+  while (true) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 20000000000LL) {           // ~10 s: a peer died; fail instead of hanging the GPU
+      if (error) *error = 1;
+      break;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace gda
+
+using namespace gda;
+
+extern "C" {
+
+int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out) {
+  GDA_REQUIRE(bytes > 0 && ptr && handle_out, "gda_sym_alloc: bad arguments");
+  *ptr = nullptr;
+  GDA_CUDA(cudaMalloc(ptr, static_cast<size_t>(bytes)));
+  GDA_CUDA(cudaMemset(*ptr, 0, static_cast<size_t>(bytes)));
+  cudaIpcMemHandle_t h;
+  GDA_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  return GDA_OK;
+}
+
+int gda_sym_open(const unsigned char* handle, void** ptr) {
+  GDA_REQUIRE(handle && ptr, "gda_sym_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  GDA_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return GDA_OK;
+}
+
+int gda_sym_close(void* ptr) {
+  if (ptr) GDA_CUDA(cudaIpcCloseMemHandle(ptr));
+  return GDA_OK;
+}
+
+int gda_sym_free(void* ptr) {
+  if (ptr) GDA_CUDA(cudaFree(ptr));
+  return GDA_OK;
+}
+
+int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t epoch, int* error_flag,
+                     gda_stream_t stream) {
+  GDA_REQUIRE(peer_flags && num_peers >= 1 && num_peers <= GDA_MAX_PEERS && rank >= 0 && rank < num_peers,
+              "gda_peer_barrier: bad arguments");
+  FlagPtrs f;
+  for (int i = 0; i < num_peers; ++i) {
+    GDA_REQUIRE(peer_flags[i] != nullptr, "gda_peer_barrier: NULL flag array");
+    f.p[i] = peer_flags[i];
+  }
+  k_peer_barrier<<<1, 32, 0, as_stream(stream)>>>(f, rank, num_peers, epoch, error_flag);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+}  // extern "C"

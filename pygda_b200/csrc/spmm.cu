@@ -308,13 +308,15 @@ k_spmm(const int* __restrict__ rowptr, const int* __restrict__ colidx, const flo
 // 2 SHFL + 2 address ops + 1 LDG.128 + VEC FFMA + 1 mask test -- no per-entry compares
 // against row bounds, no predicated register merging (profiles/r1_b_*: the generic kernel
 // executed 44 warp instructions per non-zero, this one ~12).
-template <typename T, int VEC, int LPR, int U, bool EPI>
+struct PeerTable { const void* p[GDA_MAX_PEERS]; };
+
+template <typename T, int VEC, int LPR, int U, bool EPI, bool PEER>
 __global__ void __launch_bounds__(GDA_SPMM_BLOCK, GDA_SPMM_MIN_CTAS)
 k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
             int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
             const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
             const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy, int N, int H,
-            Epilogue epi, float* __restrict__ partial) {
+            Epilogue epi, float* __restrict__ partial, PeerTable peers, int pad_col) {
   static_assert(LPR % U == 0, "batches must tile a chunk");
   constexpr int GPW = 32 / LPR;
   constexpr int RPG = RowsPerGroup<LPR>::value;
@@ -383,7 +385,7 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
         continue;
       }
       const int cnt = skipmask ? (__ffs(skipmask) - 1) : min(LPR, end - p);
-      if (l >= cnt) { myc = 0; myv = 0.f; }             // padding: weight 0, gathers row 0
+      if (l >= cnt) { myc = pad_col; myv = 0.f; }       // padding: weight 0, gathers a local row
 
       for (int j = 0; j < cnt; j += U) {
         float xv[U][VEC];
@@ -392,8 +394,16 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
         for (int u = 0; u < U; ++u) {
           const unsigned cj = static_cast<unsigned>(__shfl_sync(gmask, myc, j + u, LPR));
           wv[u] = __shfl_sync(gmask, myv, j + u, LPR);
-          // one IMAD.WIDE.U32: base + col * pitch
-          if (active) VecIO<T, VEC>::load(reinterpret_cast<const T*>(Xc + static_cast<uint64_t>(cj) * ldxb), xv[u]);
+          if (PEER) {
+            // column = owner << 28 | row inside the owner's block: P2P load over NVLink when the
+            // owner is another GPU (the owners' blocks are CUDA-IPC mapped, peer.cu)
+            const char* base = static_cast<const char*>(peers.p[cj >> 28]) + c0 * sizeof(T);
+            if (active)
+              VecIO<T, VEC>::load(reinterpret_cast<const T*>(base + static_cast<uint64_t>(cj & 0x0FFFFFFFu) * ldxb), xv[u]);
+          } else {
+            // one IMAD.WIDE.U32: base + col * pitch
+            if (active) VecIO<T, VEC>::load(reinterpret_cast<const T*>(Xc + static_cast<uint64_t>(cj) * ldxb), xv[u]);
+          }
         }
         const unsigned em = endmask >> j;
 #pragma unroll
@@ -453,7 +463,7 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
 
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-           const Epilogue& epi, float* partial, cudaStream_t st) {
+           const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
   constexpr int RPG = RowsPerGroup<LPR>::value;
   const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
   const bool generic = c.may_have_empty_rows || generic_forced();
@@ -467,12 +477,23 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
     k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
                                                    c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
                                                    static_cast<int>(N), H, epi, partial);
+  } else if (peers) {
+    if (has_epi)
+      k_spmm_fast<T, VEC, LPR, UF, true, true><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+          c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial,
+          *peers, pad_col);
+    else
+      k_spmm_fast<T, VEC, LPR, UF, false, true><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+          c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial,
+          *peers, pad_col);
   } else if (has_epi) {
-    k_spmm_fast<T, VEC, LPR, UF, true><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
-        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial);
+    k_spmm_fast<T, VEC, LPR, UF, true, false><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial,
+        PeerTable{}, 0);
   } else {
-    k_spmm_fast<T, VEC, LPR, UF, false><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
-        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial);
+    k_spmm_fast<T, VEC, LPR, UF, false, false><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs,
+        c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy, static_cast<int>(N), H, epi, partial,
+        PeerTable{}, 0);
   }
   GDA_LAUNCH_CHECK();
   return GDA_OK;
@@ -482,27 +503,29 @@ inline int pow2_at_least(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <typename T, int VEC>
 int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-                 const Epilogue& epi, float* partial, cudaStream_t st) {
+                 const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
   int lanes = pow2_at_least(static_cast<int>(ceil_div(H, VEC)));
   if (lanes > 32) lanes = 32;
   if (lanes < 4) lanes = 4;
   constexpr int U = (VEC == 4) ? GDA_SPMM_U4 : 4;               // 8 x float4 or 4 x (8 bf16) gathers in flight per lane
   switch (lanes) {
-    case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
-    case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
-    case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
-    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st);
+    case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
   }
 }
 
 template <typename T, int WIDE>
 int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, int64_t ldy, int H,
              const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
-             void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+             void* workspace, int64_t workspace_bytes, cudaStream_t st, const PeerTable* peers = nullptr,
+             int my_rank = 0) {
   GDA_REQUIRE(g != nullptr, "gda_spmm: graph is NULL");
+  GDA_REQUIRE(g->peer_packed == (peers != nullptr), "gda_spmm: partitioned graphs need gda_spmm_peer_* (and only they)");
   GDA_REQUIRE(H > 0, "gda_spmm: H must be positive");
   if (g->N == 0) return GDA_OK;
-  GDA_REQUIRE(X && Y, "gda_spmm: NULL feature pointer");
+  GDA_REQUIRE((X || peers) && Y, "gda_spmm: NULL feature pointer");
   GDA_REQUIRE(X != Y, "gda_spmm: X and Y must not alias");
   GDA_REQUIRE(ldx >= H && ldy >= H, "gda_spmm: leading dimension smaller than H");
   GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32),
@@ -520,10 +543,13 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   epi.seed = seed;
   epi.seed_offset = seed_offset;
   float* partial = static_cast<float*>(workspace);
-  const bool wide_ok = (H % WIDE == 0) && (ldx % WIDE == 0) && (ldy % WIDE == 0) &&
-                       (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
-  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st);
-  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st);
+  bool wide_ok = (H % WIDE == 0) && (ldx % WIDE == 0) && (ldy % WIDE == 0) &&
+                 (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
+  const int pad_col = peers ? (my_rank << 28) : 0;
+  if (peers)
+    for (int i = 0; i < GDA_MAX_PEERS; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(peers->p[i]) % 16 == 0);
+  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
+  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
 }
 
 }  // namespace
@@ -550,6 +576,23 @@ int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ld
   return gda::spmm_any<__nv_bfloat16, 8>(g, transpose, static_cast<const __nv_bfloat16*>(X), ldx,
                                          static_cast<__nv_bfloat16*>(Y), ldy, H, bias, epi_flags, dropout_p,
                                          seed, seed_offset, workspace, workspace_bytes, gda::as_stream(stream));
+}
+
+int gda_spmm_peer_f32(const gda_graph_t* part, int transpose, const void* const* peer_x, int num_peers, int my_rank,
+                      int64_t ldx, float* Y, int64_t ldy, int H, const float* bias, int epi_flags, float dropout_p,
+                      uint64_t seed, const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
+                      gda_stream_t stream) {
+  GDA_REQUIRE(part && part->peer_packed, "gda_spmm_peer_f32: graph is not a partition (gda_graph_partition)");
+  GDA_REQUIRE(peer_x && num_peers >= 1 && num_peers <= GDA_MAX_PEERS && my_rank >= 0 && my_rank < num_peers,
+              "gda_spmm_peer_f32: bad peer arguments");
+  GDA_REQUIRE(gda::ceil_div(part->global_N, part->rows_per_rank) <= num_peers, "gda_spmm_peer_f32: too few peers");
+  gda::PeerTable t;
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) t.p[i] = peer_x[i < num_peers ? i : my_rank];
+  for (int i = 0; i < num_peers; ++i) GDA_REQUIRE(peer_x[i] != nullptr, "gda_spmm_peer_f32: NULL peer block");
+  GDA_REQUIRE(part->rows_per_rank * ldx < (int64_t(1) << 32), "gda_spmm_peer_f32: block too large");
+  return gda::spmm_any<float, 4>(part, transpose, static_cast<const float*>(peer_x[my_rank]), ldx, Y, ldy, H, bias,
+                                 epi_flags, dropout_p, seed, seed_offset, workspace, workspace_bytes,
+                                 gda::as_stream(stream), &t, my_rank);
 }
 
 }  // extern "C"

@@ -1,0 +1,257 @@
+"""Node-partitioned multi-GPU path (one process per GPU, NVLink peer memory + NCCL).
+
+SURVEY.md section 8e: the graph and every [N, .] activation are split into P contiguous row
+blocks.  Rank r keeps CSR rows of its block with columns encoded as (owner, local row); the
+aggregation kernel gathers neighbour rows directly from the owners' HBM over NVLink
+(``gda_spmm_peer_f32``), a device-side flag barrier (``gda_peer_barrier``) orders the k chained
+propagation steps, weight gradients are all-reduced with NCCL once per step, the cross-entropy
+mean becomes a scalar all-reduce and the MMD sample rows (5 x 1000 per domain) are exchanged
+with one small all-reduce.  The reference has no distributed code at all.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import gda, load
+from .data import Data
+from .graph import Graph, NORM_SYM_COL, SELF_LOOPS
+
+MAX_PEERS = 8
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _DevPtr:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class SymBuffer:
+    """A cudaMalloc'ed, CUDA-IPC-shared buffer: ``local`` tensor view + the same buffer of every rank."""
+
+    def __init__(self, group, nbytes):
+        self.group, self.nbytes = group, int(nbytes)
+        ptr = C.c_void_p(0)
+        handle = (C.c_ubyte * 64)()
+        gda.sym_alloc(self.nbytes, C.byref(ptr), handle)
+        self.ptr = ptr.value
+        handles = [None] * group.world
+        dist.all_gather_object(handles, bytes(handle), group=group.pg)
+        self.peer_ptrs, self._opened = [], []
+        for q, h in enumerate(handles):
+            if q == group.rank:
+                self.peer_ptrs.append(self.ptr)
+            else:
+                p = C.c_void_p(0)
+                gda.sym_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p))
+                self.peer_ptrs.append(p.value)
+                self._opened.append(p.value)
+        self.ptr_array = (C.c_void_p * group.world)(*self.peer_ptrs)
+        self.bytes_view = torch.as_tensor(_DevPtr(self.ptr, self.nbytes), device=group.device)
+
+    def view(self, dtype, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return self.bytes_view[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+    def close(self):
+        lib = load()
+        for p in self._opened:
+            lib.gda_sym_close(C.c_void_p(p))
+        self._opened = []
+        if self.ptr:
+            torch.cuda.synchronize()
+            lib.gda_sym_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+class PeerGroup:
+    """The ranks of one NVSwitch box that share a partitioned graph."""
+
+    def __init__(self, device=None, pg=None):
+        if not dist.is_initialized():
+            raise RuntimeError("init torch.distributed (backend 'nccl') before creating a PeerGroup")
+        self.pg = pg
+        self.rank, self.world = dist.get_rank(pg), dist.get_world_size(pg)
+        if self.world > MAX_PEERS:
+            raise ValueError(f"the peer path supports up to {MAX_PEERS} GPUs of one box")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.flags = SymBuffer(self, 8 * MAX_PEERS)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        dist.barrier(group=pg)
+
+    def barrier(self):
+        """Device-side all-ranks barrier on the current stream (no host sync)."""
+        self.epoch += 1
+        gda.peer_barrier(self.flags.ptr_array, self.rank, self.world, self.epoch,
+                         C.c_void_p(self.error.data_ptr()), _stream())
+
+    def check(self):
+        if int(self.error.item()):
+            raise RuntimeError("gda_peer_barrier timed out: a peer rank did not arrive")
+
+    def rows_per_rank(self, n):
+        return (n + self.world - 1) // self.world
+
+    def block(self, n):
+        rpr = self.rows_per_rank(n)
+        lo = min(n, self.rank * rpr)
+        return lo, min(n, lo + rpr)
+
+
+class PartitionedGraph:
+    """Rank-local row block of a normalised graph + the symmetric ping-pong feature buffers."""
+
+    def __init__(self, group, edge_index, num_nodes_global, flags=SELF_LOOPS | NORM_SYM_COL, edge_weight=None):
+        self.group = group
+        self.global_nodes = int(num_nodes_global)
+        self.rows_per_rank = group.rows_per_rank(self.global_nodes)
+        self.row_lo, self.row_hi = group.block(self.global_nodes)
+        self.num_nodes = self.row_hi - self.row_lo
+        full = Graph(edge_index, self.global_nodes, edge_weight, flags)      # normalisation needs global degrees
+        self._h = C.c_void_p(0)
+        gda.graph_partition(full.handle, self.row_lo, self.row_hi, self.rows_per_rank, _stream(), C.byref(self._h))
+        del full
+        self.device = group.device
+        self._ws, self._sym = {}, {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                load().gda_graph_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace(self, transpose, width):
+        key = (int(bool(transpose)), int(width))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = load().gda_spmm_workspace_bytes(self._h, key[0], key[1])
+            ws = self._ws[key] = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+        return ws
+
+    def _buffers(self, width):
+        s = self._sym.get(width)
+        if s is None:
+            nbytes = self.rows_per_rank * width * 4
+            s = self._sym[width] = (SymBuffer(self.group, nbytes), SymBuffer(self.group, nbytes))
+        return s
+
+    def spmm_k(self, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, seed_offset=None):
+        """A_hat^k x over the partition: x and the result are this rank's [n_local, H] blocks."""
+        x = ops._f32c(x)
+        n, h = x.shape
+        if n != self.num_nodes:
+            raise ValueError(f"x has {n} rows, this rank owns {self.num_nodes}")
+        g = self.group
+        bufs = self._buffers(h)
+        views = [b.view(torch.float32, (self.rows_per_rank, h)) for b in bufs]
+        ws = self.workspace(transpose, h)
+        g.barrier()                                   # every rank is done with the buffers of the last call
+        views[0][:n].copy_(x)
+        cur = None
+        for i in range(k):
+            last = i == k - 1
+            g.barrier()                               # step i-1 (or the copy-in) is complete on every rank
+            out = torch.empty(n, h, dtype=torch.float32, device=self.device) if last else views[(i + 1) & 1]
+            flags = ((ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)) if last else 0
+            gda.spmm_peer_f32(self._h, int(bool(transpose)), bufs[i & 1].ptr_array, g.world, g.rank, h,
+                              ops._p(out), h, h, ops._p(bias if last else None), flags,
+                              float(dropout_p if last else 0.0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                              ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
+            cur = out
+        return cur
+
+
+class _PartitionTag:
+    """Attached to a partitioned ``edge_index`` so that conv layers pick the peer path."""
+
+    def __init__(self, group, num_nodes_global):
+        self.group, self.num_nodes_global = group, num_nodes_global
+        self._graphs = {}
+
+    def graph(self, edge_index, flags, edge_weight=None):
+        g = self._graphs.get(flags)
+        if g is None:
+            g = self._graphs[flags] = PartitionedGraph(self.group, edge_index, self.num_nodes_global, flags,
+                                                       edge_weight)
+        return g
+
+
+def partition_data(data, group):
+    """Rank-local view of a full graph: x / y rows of this rank's block, the whole edge_index
+    (tagged), on the group's device."""
+    n = data.x.size(0)
+    lo, hi = group.block(n)
+    ei = data.edge_index.to(group.device)
+    ei._gda_partition = _PartitionTag(group, n)
+    out = Data(x=data.x[lo:hi].to(group.device), edge_index=ei, y=data.y[lo:hi].to(group.device))
+    out.num_nodes_global, out.row_lo, out.row_hi = n, lo, hi
+    return out
+
+
+# ------------------------------------------------------------------ collectives with autograd
+class AllReduceSum(torch.autograd.Function):
+    """sum over ranks of a (scaled) local term; backward is the identity on the local term."""
+
+    @staticmethod
+    def forward(ctx, t, pg):
+        out = t.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=pg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class GatherRows(torch.autograd.Function):
+    """rows ``idx`` (global ids) of a row-partitioned matrix, replicated on every rank: each rank
+    fills the rows it owns and one all-reduce completes them.  Backward: every rank keeps the
+    gradient of the rows it owns (scatter-add, indices repeat)."""
+
+    @staticmethod
+    def forward(ctx, feats, idx, row_lo, pg):
+        n = feats.size(0)
+        local = idx - row_lo
+        own = (local >= 0) & (local < n)
+        out = torch.zeros(idx.numel(), feats.size(1), dtype=feats.dtype, device=feats.device)
+        sel = own.nonzero(as_tuple=True)[0]
+        out[sel] = feats[local[sel]]
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=pg)
+        ctx.save_for_backward(sel, local[sel])
+        ctx.shape = feats.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sel, loc = ctx.saved_tensors
+        gx = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        gx.index_add_(0, loc, g[sel])
+        return gx, None, None, None
+
+
+def allreduce_grads(params, pg=None):
+    """Sum the weight gradients over ranks (one flat NCCL all-reduce)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

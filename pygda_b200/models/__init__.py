@@ -4,4 +4,4 @@ from .a2gnn import A2GNN
 from .udagcn import UDAGCN
 from .grade import GRADE
 
-__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE"]
+__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn

@@ -73,7 +73,11 @@ class PropGCNConv(nn.Module):
         if self.normalize:
             flags = NORM_SYM_COL | (SELF_LOOPS if self.add_self_loops else 0) | \
                 (IMPROVED if self.improved else 0)
-        g = graph_for(edge_index, x.size(0), edge_weight, flags)
+        part = getattr(edge_index, "_gda_partition", None)
+        if part is not None:               # row-partitioned multi-GPU graph (pygda_b200/dist.py)
+            g = part.graph(edge_index, flags, edge_weight)
+        else:
+            g = graph_for(edge_index, x.size(0), edge_weight, flags)
         if self.cached:
             self._cached_graph = g
         return g

@@ -74,6 +74,9 @@ def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, s
     """A_hat^k X with ping-pong buffers; the epilogue is applied on the last step."""
     if k == 0:
         raise ValueError("spmm_k needs k >= 1")
+    if hasattr(graph, "spmm_k"):          # row-partitioned graph: NVLink peer path (pygda_b200/dist.py)
+        return graph.spmm_k(x, k, transpose=transpose, bias=bias, relu=relu, dropout_p=dropout_p, seed=seed,
+                            seed_offset=seed_offset)
     cur, bufs = x, [None, None]
     for i in range(k):
         last = i == k - 1

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Multi-GPU parity: DistA2GNN over P ranks == A2GNN on the whole graph (same weights, dropout 0).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_check.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pygda_b200 import ops
+    from pygda_b200.dist import PartitionedGraph, PeerGroup, partition_data
+    from pygda_b200.graph import Graph
+    from pygda_b200.models import A2GNN
+    from pygda_b200.models.dist_a2gnn import DistA2GNN
+    from pygda_b200.optim import Adam
+    from pygda_b200.synthetic import domain_pair
+    from pygda_b200.utils import draw_indices
+    group = PeerGroup()
+    dev = group.device
+    ok = True
+
+    # ---- 1. peer aggregation == single-GPU aggregation on the owned rows -----------------------
+    n, h = 30011, 128                                       # not divisible by the world size
+    src, tgt = domain_pair(n, 300000, 64, 5, seed=3, target_nodes=n - 1000, target_edges=280000)
+    full = Graph(src.edge_index.to(dev), n)
+    part = PartitionedGraph(group, src.edge_index.to(dev), n)
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(1)).to(dev)
+    lo, hi = group.block(n)
+    for k, transpose in ((1, False), (3, False), (2, True)):
+        ref = ops.spmm_k(full, x, k, transpose=transpose)[lo:hi]
+        out = part.spmm_k(x[lo:hi].contiguous(), k, transpose=transpose)
+        e = rel(out, ref)
+        ok &= e < 1e-6
+        if rank == 0:
+            print(f"peer spmm k={k} T={transpose}: rel err {e:.2e}")
+    group.check()
+
+    # ---- 2. one training step: loss, logits, updated weights ------------------------------------
+    hp = dict(in_dim=64, hid_dim=32, num_classes=5, num_layers=2, dropout=0.0, s_pnums=0, t_pnums=4, weight=10,
+              weight_decay=0.005, lr=0.01, epoch=200, verbose=0)
+    torch.manual_seed(0)
+    single = A2GNN(device=str(dev), **hp)
+    single.a2gnn = single.init_model()
+    single.overlap_streams = False
+    multi = DistA2GNN(device=str(dev), group=group, **hp)
+    multi.a2gnn = multi.init_model()
+    multi.a2gnn.load_state_dict(single.a2gnn.state_dict())
+    for p in multi.a2gnn.parameters():
+        dist.broadcast(p.data, src=0)
+    single.a2gnn.load_state_dict(multi.a2gnn.state_dict())
+    torch.manual_seed(5)
+    idx = draw_indices(n, n - 1000)
+    idx = tuple(t.to(dev) for t in idx)
+    for t in idx:
+        dist.broadcast(t, src=0)
+    idx = tuple(t.cpu() for t in idx)
+    s_full, t_full = src.to(dev), tgt.to(dev)
+    s_part, t_part = partition_data(src, group), partition_data(tgt, group)
+    o1 = Adam(single.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    o2 = Adam(multi.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    for step in range(2):
+        l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=idx)
+        l2, sl2, tl2, _ = multi.train_step(s_part, t_part, 0.3, o2, mmd_indices=idx)
+        slo, shi = group.block(n)
+        tlo, thi = group.block(n - 1000)
+        errs = {"loss": rel(l2, l1), "source_logits": rel(sl2, sl1[slo:shi]), "target_logits": rel(tl2, tl1[tlo:thi])}
+        for (k, p), (_, q) in zip(multi.a2gnn.named_parameters(), single.a2gnn.named_parameters()):
+            errs["param " + k] = rel(p, q)
+        worst = max(errs.values())
+        ok &= worst < 2e-4
+        if rank == 0:
+            print(f"step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items() if not k.startswith("param")),
+                  f"max param err {max(v for k, v in errs.items() if k.startswith('param')):.1e}")
+    group.check()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if int(flag.item()) else "FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
