@@ -212,36 +212,41 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Each rank holds one source/target pair of the config-2 shape (weak scaling: per-GPU work
-    # fixed); ranks average weight gradients (see DESIGN.md section 6 for the node-partitioned path).
-    src, tgt = domain_pair(CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=10 * rank,
-                           device=dev)
+    hp = dict(in_dim=CFG["feats"], hid_dim=CFG["hid"], num_classes=CFG["classes"], mode="node",
+              num_layers=CFG["layers"], dropout=CFG["dropout"], s_pnums=CFG["s_pnums"], t_pnums=CFG["t_pnums"],
+              adv=False, weight=CFG["weight"], weight_decay=CFG["weight_decay"], lr=CFG["lr"],
+              epoch=CFG["epochs"], device=str(dev), verbose=0)
     torch.manual_seed(0)
-    model = A2GNN(in_dim=CFG["feats"], hid_dim=CFG["hid"], num_classes=CFG["classes"], mode="node",
-                  num_layers=CFG["layers"], dropout=CFG["dropout"], s_pnums=CFG["s_pnums"],
-                  t_pnums=CFG["t_pnums"], adv=False, weight=CFG["weight"], weight_decay=CFG["weight_decay"],
-                  lr=CFG["lr"], epoch=CFG["epochs"], device=str(dev), verbose=0)
-    model._build_loaders(src, tgt)
-    model.a2gnn = model.init_model()
+    if not distributed:
+        src, tgt = domain_pair(CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=0, device=dev)
+        model = A2GNN(**hp)
+        model._build_loaders(src, tgt)
+        model.a2gnn = model.init_model()
+        s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
+        parallelism = "single GPU"
+    else:
+        # Weak scaling over a 1-D node partition: the global source / target graphs
+        # are `world` citation-shaped communities of the config-2 size with a 5 % edge cut; rank r owns
+        # community r (rows, features, labels).  Neighbour rows owned by other GPUs are gathered over
+        # NVLink inside the aggregation kernel; weight gradients are all-reduced once per step.
+        from pygda_b200.dist import PeerGroup, attach_partition
+        from pygda_b200.models.dist_a2gnn import DistA2GNN
+        from pygda_b200.synthetic import community_block
+        group = PeerGroup(device=dev)
+        src = community_block(world, rank, CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=0,
+                              device=dev)
+        tgt = community_block(world, rank, CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=1,
+                              feature_shift=1.4, degree_offset=48.0, device=dev)
+        src, tgt = attach_partition(src, group), attach_partition(tgt, group)
+        model = DistA2GNN(group=group, **hp)
+        model.a2gnn = model.init_model()
+        s_batch, t_batch = src, tgt
+        parallelism = ("1-D node partition: %d communities of %dk nodes (one per GPU, 5%% cross-partition edges), "
+                       "NVLink peer gathers in the aggregation kernel, NCCL gradient all-reduce; value counts "
+                       "config-2-sized graph-epochs per second" % (world, CFG["nodes"] // 1000))
     params = list(model.a2gnn.parameters())
     opt = Adam(params, lr=CFG["lr"], weight_decay=CFG["weight_decay"])
-    s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
-
-    class SyncedAdam:
-        """Adam preceded by the weight-gradient all-reduce (mean) across ranks."""
-        def zero_grad(self):
-            opt.zero_grad()
-
-        def step(self):
-            if distributed:
-                flat = torch.cat([p.grad.reshape(-1) for p in params])
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-                off = 0
-                for p in params:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad)); off += p.numel()
-            opt.step()
-
-    sopt = SyncedAdam()
+    sopt = opt
     step_no = [0]
 
     def one_step(sb, tb):
@@ -286,8 +291,13 @@ def run_gpu_arm(args, rank, world, local_rank):
         one_step(s_batch, t_batch)
     torch.cuda.synchronize()
     recs, ops.PROFILE = ops.PROFILE, None
-    tg = graph_for(t_batch.edge_index, CFG["nodes"])
-    n_nodes, nnz, H = CFG["nodes"], tg.nnz, CFG["hid"]
+    if distributed:
+        tg = t_batch.edge_index._gda_partition.graph(t_batch.edge_index, 1 | 4)      # SELF_LOOPS | NORM_SYM_COL
+        nnz = tg.local_nnz
+    else:
+        tg = graph_for(t_batch.edge_index, CFG["nodes"])
+        nnz = tg.nnz
+    n_nodes, H = CFG["nodes"], CFG["hid"]
     b_alg = 4 * (n_nodes + 1) + 8 * nnz + 2 * 4 * n_nodes * H
     times = [a.elapsed_time(b) for (a, b, meta) in recs if meta == (n_nodes, H, "float32")]
     spmm_ms = statistics.mean(times) if times else float("nan")
@@ -323,9 +333,12 @@ def run_gpu_arm(args, rank, world, local_rank):
                               "roofline": roofline, "note": "profiling run"}), flush=True)
         return
     src_h, tgt_h = src.to("cpu").pin_memory(), tgt.to("cpu").pin_memory()
-    model._build_loaders(src_h, tgt_h)
-    sb_h, tb_h = next(iter(model.source_loader)), next(iter(model.target_loader))
-    sb_h, tb_h = sb_h.pin_memory(), tb_h.pin_memory()
+    if distributed:
+        sb_h, tb_h = src_h, tgt_h
+    else:
+        model._build_loaders(src_h, tgt_h)
+        sb_h, tb_h = next(iter(model.source_loader)), next(iter(model.target_loader))
+        sb_h, tb_h = sb_h.pin_memory(), tb_h.pin_memory()
     h2d = data_bytes(sb_h) + data_bytes(tb_h)
     del src, tgt, s_batch, t_batch
     torch.cuda.empty_cache()
@@ -353,7 +366,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "s_pnums": CFG["s_pnums"], "t_pnums": CFG["t_pnums"], "dropout": CFG["dropout"],
                        "mmd_weight": CFG["weight"], "optimizer": "Adam lr=0.01 wd=0.005",
                        "epoch_definition": "full-batch: 1 epoch = 1 optimiser step; F1/logging excluded",
-                       "parallelism": "1 graph pair per GPU, weight-gradient all-reduce" if world > 1 else "single GPU",
+                       "parallelism": parallelism,
                        "l2_policy": "inputs larger than L2 (x is 2.7 GB per domain, streamed every step); "
                                     "no explicit flush",
                        "final_loss": final_loss},

@@ -36,12 +36,20 @@ class Data:
             ei._gda_key = getattr(src, "_gda_key", None) or (
                 "src", src.data_ptr(), src._version, tuple(src.shape), str(src.device))
             ei._gda_keepalive = getattr(src, "_gda_keepalive", src)
+            part = getattr(src, "_gda_partition", None)      # row-partitioned multi-GPU graph tag
+            if part is not None:
+                ei._gda_partition = part
         return out
 
     def pin_memory(self):
-        out = Data.__new__(Data)
+        out = self.__class__.__new__(self.__class__)
         for k, v in self.__dict__.items():
             out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v
+        src, ei = self.edge_index, out.__dict__.get("edge_index")
+        if torch.is_tensor(ei) and ei is not src:
+            for attr in ("_gda_partition", "_gda_key", "_gda_keepalive"):
+                if hasattr(src, attr):
+                    setattr(ei, attr, getattr(src, attr))
         return out
 
     @property

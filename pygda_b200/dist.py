@@ -25,6 +25,23 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def rows_per_rank(n, world):
+    """Rows of a contiguous 1-D partition: ceil(n / world); the last rank may own fewer."""
+    return (n + world - 1) // world
+
+
+def block_range(n, world, rank):
+    rpr = rows_per_rank(n, world)
+    lo = min(n, rank * rpr)
+    return lo, min(n, lo + rpr)
+
+
+def pack_column(col, rpr):
+    """(owner << 28 | local row): the column encoding of a partition (gda_graph_partition)."""
+    owner = col // rpr
+    return (owner << 28) | (col - owner * rpr)
+
+
 class _DevPtr:
     """Exposes a raw device allocation to torch through __cuda_array_interface__."""
 
@@ -99,12 +116,10 @@ class PeerGroup:
             raise RuntimeError("gda_peer_barrier timed out: a peer rank did not arrive")
 
     def rows_per_rank(self, n):
-        return (n + self.world - 1) // self.world
+        return rows_per_rank(n, self.world)
 
     def block(self, n):
-        rpr = self.rows_per_rank(n)
-        lo = min(n, self.rank * rpr)
-        return lo, min(n, lo + rpr)
+        return block_range(n, self.world, self.rank)
 
 
 class PartitionedGraph:
@@ -119,6 +134,9 @@ class PartitionedGraph:
         full = Graph(edge_index, self.global_nodes, edge_weight, flags)      # normalisation needs global degrees
         self._h = C.c_void_p(0)
         gda.graph_partition(full.handle, self.row_lo, self.row_hi, self.rows_per_rank, _stream(), C.byref(self._h))
+        n_, nnz_, a_, b_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        gda.graph_info(self._h, C.byref(n_), C.byref(nnz_), C.byref(a_), C.byref(b_))
+        self.local_nnz = nnz_.value
         del full
         self.device = group.device
         self._ws, self._sym = {}, {}
@@ -168,10 +186,18 @@ class PartitionedGraph:
             g.barrier()                               # step i-1 (or the copy-in) is complete on every rank
             out = torch.empty(n, h, dtype=torch.float32, device=self.device) if last else views[(i + 1) & 1]
             flags = ((ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)) if last else 0
+            prof = ops.PROFILE
+            if prof is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             gda.spmm_peer_f32(self._h, int(bool(transpose)), bufs[i & 1].ptr_array, g.world, g.rank, h,
                               ops._p(out), h, h, ops._p(bias if last else None), flags,
                               float(dropout_p if last else 0.0), int(seed) & 0xFFFFFFFFFFFFFFFF,
                               ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
+            if prof is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                prof.append((e0, e1, (n, h, "float32")))
             cur = out
         return cur
 
@@ -189,6 +215,16 @@ class _PartitionTag:
             g = self._graphs[flags] = PartitionedGraph(self.group, edge_index, self.num_nodes_global, flags,
                                                        edge_weight)
         return g
+
+
+def attach_partition(data, group):
+    """Tag a rank-local ``Data`` (x / y rows of this rank's block + the GLOBAL edge_index, with
+    ``num_nodes_global`` / ``row_lo`` / ``row_hi`` set) so that conv layers take the peer path."""
+    lo, hi = group.block(data.num_nodes_global)
+    if (lo, hi) != (data.row_lo, data.row_hi):
+        raise ValueError("data block does not match this rank's row range")
+    data.edge_index._gda_partition = _PartitionTag(group, data.num_nodes_global)
+    return data
 
 
 def partition_data(data, group):

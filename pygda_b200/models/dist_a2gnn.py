@@ -69,6 +69,8 @@ class DistA2GNN(A2GNN):
 
     def train_step(self, source_data, target_data, alpha, optimizer, mmd_indices=None):
         self.a2gnn.train()
+        source_data = source_data.to(self.device)
+        target_data = target_data.to(self.device)
         loss, source_logits, target_logits = self.forward_model(source_data, target_data, alpha,
                                                                 mmd_indices=mmd_indices)
         optimizer.zero_grad()

@@ -97,3 +97,41 @@ def graph_dataset(num_graphs, mean_nodes, edges_per_node, num_features, num_clas
         y = torch.randint(num_classes, (1,), generator=g)
         out.append(Data(x=x, edge_index=ei, y=y))
     return out
+
+
+def community_edge_index(num_blocks, nodes_per_block, edges_per_block, cross_fraction=0.05, seed=0,
+                         degree_offset=32.0):
+    """Global edge_index of ``num_blocks`` citation-shaped communities (block b owns node ids
+    [b*nodes_per_block, (b+1)*nodes_per_block)) with ``edges_per_block`` directed edges each, of
+    which ``cross_fraction`` connect to other blocks -- the multi-GPU workload: a graph that
+    partitions naturally (one community per GPU, a 5 % edge cut by default).  Deterministic in
+    ``seed`` so that every rank can build the same global structure."""
+    cross = int(edges_per_block * cross_fraction) // 2 * 2
+    intra = edges_per_block - cross
+    parts = []
+    for b in range(num_blocks):
+        ei = powerlaw_edge_index(nodes_per_block, intra, seed=seed + 17 * b, offset=degree_offset)
+        parts.append(ei + b * nodes_per_block)
+    if num_blocks > 1 and cross > 0:
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + 99991)
+        m = num_blocks * cross // 2
+        ba = torch.randint(num_blocks, (m,), generator=g)
+        bb = (ba + 1 + torch.randint(num_blocks - 1, (m,), generator=g)) % num_blocks
+        u = ba * nodes_per_block + torch.randint(nodes_per_block, (m,), generator=g)
+        v = bb * nodes_per_block + torch.randint(nodes_per_block, (m,), generator=g)
+        parts.append(torch.stack([torch.cat([u, v]), torch.cat([v, u])]))
+    return torch.cat(parts, 1).contiguous()
+
+
+def community_block(num_blocks, block, nodes_per_block, edges_per_block, num_features, num_classes, seed=0,
+                    cross_fraction=0.05, feature_shift=1.5, degree_offset=32.0, device="cpu"):
+    """What one rank of the partitioned run holds: the GLOBAL edge_index and the feature / label
+    rows of its own block (as a ``Data`` with ``num_nodes_global``, ``row_lo``, ``row_hi``)."""
+    ei = community_edge_index(num_blocks, nodes_per_block, edges_per_block, cross_fraction, seed, degree_offset)
+    x = bow_features(nodes_per_block, num_features, seed=seed + 1000 + block, shift=feature_shift, device=device)
+    g = torch.Generator(device="cpu").manual_seed(int(seed) + 2000 + block)
+    y = torch.randint(num_classes, (nodes_per_block,), generator=g).to(device)
+    d = Data(x=x, edge_index=ei.to(device), y=y)
+    d.num_nodes_global = num_blocks * nodes_per_block
+    d.row_lo, d.row_hi = block * nodes_per_block, (block + 1) * nodes_per_block
+    return d
