@@ -102,6 +102,13 @@ int gda_spmm_f32(const gda_graph_t* g, int transpose, const float* X, int64_t ld
                  float* Y, int64_t ldy, int H, const float* bias, int epi_flags,
                  float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                  void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+/* A_hat^k X in one call (k launches): what `for i in range(prop_nums): out = self.propagate(...)`
+ * does at pygda/nn/prop_gcn_conv.py:208-210.  T0/T1: ping-pong scratch [N,H] (k>=2 / k>=3);
+ * the epilogue applies to the last step only. */
+int gda_spmm_k_f32(const gda_graph_t* g, int transpose, int k, const float* X, int64_t ldx, float* Y,
+                   int64_t ldy, float* T0, float* T1, int H, const float* bias, int epi_flags,
+                   float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                   int64_t workspace_bytes, gda_stream_t stream);
 /* bf16 features, fp32 edge weights and accumulation (BASELINE config 3) */
 int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ldx,
                   void* Y, int64_t ldy, int H, const float* bias, int epi_flags,
@@ -127,6 +134,13 @@ int gda_spmm_peer_f32(const gda_graph_t* part, int transpose, const void* const*
                       int my_rank, int64_t ldx, float* Y, int64_t ldy, int H, const float* bias,
                       int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                       void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+/* barrier, copy-in, then k x (barrier, gda_spmm_peer_f32) ping-ponging between the two symmetric
+ * buffers sym0/sym1 (per-rank pointer arrays); barrier epochs epoch0+1 .. epoch0+k+1 are used. */
+int gda_spmm_peer_k_f32(const gda_graph_t* part, int transpose, int k, const float* x_local,
+                        const void* const* sym0, const void* const* sym1, int num_peers, int my_rank,
+                        float* Y, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                        const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
+                        uint64_t* const* peer_flags, uint64_t epoch0, int* error_flag, gda_stream_t stream);
 int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
 int gda_sym_open(const unsigned char* handle /* 64 bytes */, void** ptr);
 int gda_sym_close(void* ptr);

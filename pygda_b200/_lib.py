@@ -32,6 +32,9 @@ SIGNATURES = {
     "gda_graph_export_csr": (i32, [vp, i32, vp, vp, vp, vp]),
     "gda_spmm_workspace_bytes": (i64, [vp, i32, i32]),
     "gda_spmm_f32": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_k_f32": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_peer_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
+                                  vp, u64, vp, vp]),
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_graph_partition": (i32, [vp, i64, i64, i64, vp, C.POINTER(vp)]),
     "gda_spmm_peer_f32": (i32, [vp, i32, vp, i32, i32, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),

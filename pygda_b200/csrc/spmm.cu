@@ -595,4 +595,60 @@ int gda_spmm_peer_f32(const gda_graph_t* part, int transpose, const void* const*
                                  gda::as_stream(stream), &t, my_rank);
 }
 
+// k chained steps in one call (host-side loop: k launches, one crossing of the ABI).
+// T0 / T1: ping-pong scratch [N, H] (needed for k >= 2 / k >= 3); the epilogue is applied on the last step.
+int gda_spmm_k_f32(const gda_graph_t* g, int transpose, int k, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                   float* T0, float* T1, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                   const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(k >= 1, "gda_spmm_k_f32: k must be >= 1");
+  GDA_REQUIRE(k < 2 || T0, "gda_spmm_k_f32: T0 scratch needed for k >= 2");
+  GDA_REQUIRE(k < 3 || T1, "gda_spmm_k_f32: T1 scratch needed for k >= 3");
+  const float* src = X;
+  int64_t ld_src = ldx;
+  for (int i = 0; i < k; ++i) {
+    const bool last = i == k - 1;
+    float* dst = last ? Y : ((i & 1) ? T1 : T0);
+    const int64_t ld_dst = last ? ldy : H;
+    int rc = gda_spmm_f32(g, transpose, src, ld_src, dst, ld_dst, H, last ? bias : nullptr, last ? epi_flags : 0,
+                          last ? dropout_p : 0.f, seed, seed_offset, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    src = dst;
+    ld_src = ld_dst;
+  }
+  return GDA_OK;
+}
+
+int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t epoch, int* error_flag,
+                     gda_stream_t stream);   // peer.cu
+
+// The partitioned form: barrier, copy x into the rank's symmetric buffer 0, then k x (barrier, peer
+// aggregation) ping-ponging between the symmetric buffers; the last step writes Y (plain memory).
+// sym0 / sym1: per-rank pointers of the two CUDA-IPC buffers ([rows_per_rank, H] each); uses barrier
+// epochs epoch0+1 .. epoch0+k+1 (the caller advances its counter by k+1).
+int gda_spmm_peer_k_f32(const gda_graph_t* part, int transpose, int k, const float* x_local,
+                        const void* const* sym0, const void* const* sym1, int num_peers, int my_rank, float* Y,
+                        int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                        const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
+                        uint64_t* const* peer_flags, uint64_t epoch0, int* error_flag, gda_stream_t stream) {
+  GDA_REQUIRE(part && part->peer_packed && k >= 1 && x_local && sym0 && sym1 && Y, "gda_spmm_peer_k_f32: bad arguments");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS && my_rank >= 0 && my_rank < num_peers,
+              "gda_spmm_peer_k_f32: bad peer arguments");
+  cudaStream_t st = gda::as_stream(stream);
+  int rc = gda_peer_barrier(peer_flags, my_rank, num_peers, ++epoch0, error_flag, stream);
+  if (rc) return rc;
+  GDA_CUDA(cudaMemcpyAsync(const_cast<void*>(sym0[my_rank]), x_local, sizeof(float) * part->N * H,
+                           cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < k; ++i) {
+    const bool last = i == k - 1;
+    if ((rc = gda_peer_barrier(peer_flags, my_rank, num_peers, ++epoch0, error_flag, stream))) return rc;
+    const void* const* src = (i & 1) ? sym1 : sym0;
+    float* dst = last ? Y : static_cast<float*>(const_cast<void*>(((i & 1) ? sym0 : sym1)[my_rank]));
+    rc = gda_spmm_peer_f32(part, transpose, src, num_peers, my_rank, H, dst, H, H, last ? bias : nullptr,
+                           last ? epi_flags : 0, last ? dropout_p : 0.f, seed, seed_offset, workspace,
+                           workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return GDA_OK;
+}
+
 }  // extern "C"

@@ -176,30 +176,35 @@ class PartitionedGraph:
             raise ValueError(f"x has {n} rows, this rank owns {self.num_nodes}")
         g = self.group
         bufs = self._buffers(h)
-        views = [b.view(torch.float32, (self.rows_per_rank, h)) for b in bufs]
         ws = self.workspace(transpose, h)
+        out = torch.empty(n, h, dtype=torch.float32, device=self.device)
+        flags = (ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)
+        if ops.PROFILE is None:
+            # barrier + copy-in + k x (barrier, peer aggregation) behind ONE call: k+2 fewer host round trips
+            gda.spmm_peer_k_f32(self._h, int(bool(transpose)), int(k), ops._p(x), bufs[0].ptr_array,
+                                bufs[1].ptr_array, g.world, g.rank, ops._p(out), h, ops._p(bias), flags,
+                                float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, ops._p(seed_offset), ops._p(ws),
+                                ws.numel(), g.flags.ptr_array, g.epoch, C.c_void_p(g.error.data_ptr()), _stream())
+            g.epoch += k + 1
+            return out
+        # bench.py instrumentation: one call per step so that each launch can be timed
+        views = [b.view(torch.float32, (self.rows_per_rank, h)) for b in bufs]
         g.barrier()                                   # every rank is done with the buffers of the last call
         views[0][:n].copy_(x)
-        cur = None
         for i in range(k):
             last = i == k - 1
             g.barrier()                               # step i-1 (or the copy-in) is complete on every rank
-            out = torch.empty(n, h, dtype=torch.float32, device=self.device) if last else views[(i + 1) & 1]
-            flags = ((ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)) if last else 0
-            prof = ops.PROFILE
-            if prof is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record()
+            dst = out if last else views[(i + 1) & 1]
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
             gda.spmm_peer_f32(self._h, int(bool(transpose)), bufs[i & 1].ptr_array, g.world, g.rank, h,
-                              ops._p(out), h, h, ops._p(bias if last else None), flags,
+                              ops._p(dst), h, h, ops._p(bias if last else None), flags if last else 0,
                               float(dropout_p if last else 0.0), int(seed) & 0xFFFFFFFFFFFFFFFF,
                               ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
-            if prof is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                prof.append((e0, e1, (n, h, "float32")))
-            cur = out
-        return cur
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ops.PROFILE.append((e0, e1, (n, h, "float32")))
+        return out
 
 
 class _PartitionTag:
