@@ -268,20 +268,19 @@ class GatherRows(torch.autograd.Function):
     def forward(ctx, feats, idx, row_lo, pg):
         n = feats.size(0)
         local = idx - row_lo
-        own = (local >= 0) & (local < n)
-        out = torch.zeros(idx.numel(), feats.size(1), dtype=feats.dtype, device=feats.device)
-        sel = own.nonzero(as_tuple=True)[0]
-        out[sel] = feats[local[sel]]
+        own = ((local >= 0) & (local < n)).to(feats.dtype).unsqueeze(1)
+        safe = local.clamp(0, max(n - 1, 0))          # no nonzero(): that would sync the host every step
+        out = feats.index_select(0, safe) * own
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=pg)
-        ctx.save_for_backward(sel, local[sel])
+        ctx.save_for_backward(safe, own)
         ctx.shape = feats.shape
         return out
 
     @staticmethod
     def backward(ctx, g):
-        sel, loc = ctx.saved_tensors
+        safe, own = ctx.saved_tensors
         gx = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
-        gx.index_add_(0, loc, g[sel])
+        gx.index_add_(0, safe, g * own)
         return gx, None, None, None
 
 
