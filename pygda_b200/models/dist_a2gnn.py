@@ -12,6 +12,7 @@ import torch.distributed as dist
 from .. import ops
 from ..dist import AllReduceSum, GatherRows, allreduce_grads
 from ..utils import draw_indices
+from ..utils.mmd import to_device_async
 from .a2gnn import A2GNN
 
 
@@ -39,7 +40,7 @@ class DistA2GNN(A2GNN):
         else:
             s_idx = t_idx = torch.empty(5, 1000, dtype=torch.int64)
         dev = self.group.device
-        s_idx, t_idx = s_idx.to(dev), t_idx.to(dev)
+        s_idx, t_idx = to_device_async(s_idx, dev), to_device_async(t_idx, dev)
         if given is None:
             dist.broadcast(s_idx, src=0, group=self.group.pg)
             dist.broadcast(t_idx, src=0, group=self.group.pg)

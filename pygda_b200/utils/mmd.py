@@ -17,14 +17,39 @@ def draw_indices(source_num, target_num, sampling_num=1000, times=5):
     return source_sample, target_sample
 
 
+_pinned = {}
+
+
+def to_device_async(idx, device):
+    """CPU index tensor -> device through a reusable pinned staging buffer: a pageable H2D copy
+    would block the host until the GPU drains everything queued before it."""
+    if idx.is_cuda:
+        return idx.contiguous()
+    key = (tuple(idx.shape), idx.dtype, str(device))
+    ring = _pinned.get(key)
+    if ring is None:
+        ring = _pinned[key] = [[torch.empty(idx.shape, dtype=idx.dtype).pin_memory() for _ in range(4)], 0, []]
+    bufs, pos, events = ring
+    if len(events) == len(bufs):                     # the buffer about to be reused must have been consumed
+        events.pop(0).synchronize()
+    buf = bufs[pos]
+    ring[1] = (pos + 1) % len(bufs)
+    buf.copy_(idx)
+    out = buf.to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    events.append(ev)
+    return out
+
+
 def MMD(source_feat, target_feat, sampling_num=1000, times=5, indices=None, kernel_mul=2.0,
         kernel_num=5):
     if indices is None:
         indices = draw_indices(source_feat.size(0), target_feat.size(0), sampling_num, times)
     s_idx, t_idx = indices
     dev = source_feat.device
-    s_idx = s_idx.to(dev, non_blocking=True).contiguous()
-    t_idx = t_idx.to(dev, non_blocking=True).contiguous()
+    s_idx = to_device_async(s_idx, dev)
+    t_idx = to_device_async(t_idx, dev)
     return ops.MMDFn.apply(source_feat, target_feat, s_idx, t_idx, kernel_mul, kernel_num)
 
 
