@@ -287,9 +287,11 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     # ---------------- roofline of the aggregation kernel (instrumented repeat) ----------------
     ops.PROFILE = []
+    overlap, model.overlap_streams = model.overlap_streams, False      # time the kernel alone, not co-scheduled
     for _ in range(min(args.steps, 5)):
         one_step(s_batch, t_batch)
     torch.cuda.synchronize()
+    model.overlap_streams = overlap
     recs, ops.PROFILE = ops.PROFILE, None
     if distributed:
         tg = t_batch.edge_index._gda_partition.graph(t_batch.edge_index, 1 | 4)      # SELF_LOOPS | NORM_SYM_COL
