@@ -163,3 +163,69 @@ class GRADE:
         loss.backward()
         self.optimizer.step()
         return val, s_logits, t_logits
+
+
+class AdaGCN:
+    """pygda/models/adagcn.py:67-454: forward_model :138-198 (10 critic iterations with WGAN-GP,
+    encoder graph kept as in the reference), critic :264-276, gradient_penalty :387-454."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, mode="node", num_layers=3, adv_dim=40, gp_weight=5,
+                 domain_weight=1, weight_decay=0., lr=4e-3, act=F.relu, **kwargs):
+        self.mode, self.gp_weight, self.domain_weight = mode, gp_weight, domain_weight
+        self.adagcn = ONN.AdaGCNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, act=act, mode=mode)
+        self.optimizer = torch.optim.Adam(self.adagcn.parameters(), lr=lr, weight_decay=weight_decay)
+        self.discriminator = torch.nn.Sequential(
+            torch.nn.Linear(hid_dim, adv_dim), torch.nn.ReLU(), torch.nn.Dropout(0.1),
+            torch.nn.Linear(adv_dim, 1), torch.nn.Sigmoid())
+        self.c_optimizer = torch.optim.Adam(self.discriminator.parameters(), lr=lr, weight_decay=weight_decay)
+
+    def gradient_penalty(self, es, et):
+        num_s, num_t = es.shape[0], et.shape[0]
+        if num_s < num_t:
+            hs = torch.cat((es, es), 0)
+            ht = torch.cat((et[0:num_s, ], et[-num_s:, ]), 0)
+            alpha = torch.rand((2 * num_s, 1))
+            inter = ht + alpha * (hs - ht)
+        elif num_s > num_t:
+            hs = torch.cat((es[0:num_t, ], es[-num_t:, ]), 0)
+            ht = torch.cat((et, et), 0)
+            alpha = torch.rand((2 * num_t, 1))
+            inter = ht + alpha * (hs - ht)
+        else:
+            alpha = torch.rand((num_t, 1))
+            inter = et + alpha * (es - et)
+        inputs = torch.cat((es, et, inter), 0)
+        scores = self.discriminator(inputs)
+        grad = torch.autograd.grad(inputs=inputs, outputs=scores, grad_outputs=torch.ones_like(scores),
+                                   create_graph=True, retain_graph=True, only_inputs=True)[0]
+        return torch.mean((grad.view(grad.shape[0], -1).norm(2, dim=1) - 1) ** 2)
+
+    def forward_model(self, source_data, target_data):
+        for _ in range(10):
+            es, et = self.adagcn(source_data), self.adagcn(target_data)
+            gp = self.gradient_penalty(es, et)
+            dis_loss = -torch.abs(torch.mean(self.discriminator(es).reshape(-1)) -
+                                  torch.mean(self.discriminator(et).reshape(-1)))
+            loss = dis_loss + self.gp_weight * gp
+            self.c_optimizer.zero_grad()
+            loss.backward()
+            self.c_optimizer.step()
+        es, et = self.adagcn(source_data), self.adagcn(target_data)
+        source_logits = self.adagcn.cls_model(es)
+        cls_loss = self.adagcn.loss_func(source_logits, source_data.y)
+        dis_loss = torch.abs(torch.mean(self.discriminator(es).reshape(-1)) -
+                             torch.mean(self.discriminator(et).reshape(-1)))
+        target_logits = self.adagcn.cls_model(et)
+        return cls_loss + dis_loss * self.domain_weight, source_logits, target_logits
+
+
+class GNN:
+    """pygda/models/gnn.py:59-268 over the gcn backbone (forward_model :120-150)."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0., act=F.relu, **kwargs):
+        self.gnn = ONN.GNNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, dropout=dropout, act=act)
+
+    def forward_model(self, source_data, target_data):
+        source_logits = self.gnn(source_data.x, source_data.edge_index)
+        target_logits = self.gnn(target_data.x, target_data.edge_index)
+        return F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y), source_logits, target_logits

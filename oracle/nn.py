@@ -254,3 +254,64 @@ class GRADEBase(nn.Module):
 
     def one_hot_embedding(self, labels):
         return torch.eye(self.num_classes)[labels]
+
+
+class AdaGCNEncoder(nn.Module):
+    """``GNN`` of pygda/nn/adagcn_base.py:9-59 (gcn type)."""
+
+    def __init__(self, in_dim, hid_dim, num_layers=3, act=F.relu, dropout=0.1):
+        super().__init__()
+        self.act = act
+        self.conv_layers = nn.ModuleList([GCNConv(in_dim, hid_dim)])
+        for _ in range(1, num_layers):
+            self.conv_layers.append(GCNConv(hid_dim, hid_dim))
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x, edge_index, batch, mode="node"):
+        for i, conv in enumerate(self.conv_layers):
+            x = conv(x, edge_index)
+            if i < len(self.conv_layers) - 1:
+                x = self.dropout(self.act(x))
+        if mode == "graph":
+            x = P.global_mean_pool(x, batch)
+        return x
+
+
+class AdaGCNBase(nn.Module):
+    """pygda/nn/adagcn_base.py:61-181."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0.1, act=F.relu,
+                 gnn_type="gcn", mode="node", **kwargs):
+        super().__init__()
+        self.encoder = AdaGCNEncoder(in_dim, hid_dim, num_layers=num_layers, act=act)
+        self.cls_model = nn.Sequential(nn.Linear(hid_dim, num_classes))
+        self.mode = mode
+        self.loss_func = nn.CrossEntropyLoss()
+
+    def forward(self, data):
+        batch = None if self.mode == "node" else data.batch
+        return self.encoder(data.x, data.edge_index, batch, mode=self.mode)
+
+
+class GNNBase(nn.Module):
+    """gcn branch of pygda/nn/gnn_base.py:8-205."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=1, dropout=0.1, act=F.relu,
+                 gnn="gcn", mode="node", **kwargs):
+        super().__init__()
+        assert gnn == "gcn"
+        self.dropout, self.act, self.mode = dropout, act, mode
+        self.convs = nn.ModuleList([GCNConv(in_dim, hid_dim)])
+        for _ in range(num_layers - 1):
+            self.convs.append(GCNConv(hid_dim, hid_dim))
+        self.cls = GCNConv(hid_dim, num_classes) if mode == "node" else nn.Linear(hid_dim, num_classes)
+
+    def forward(self, x, edge_index, edge_weight=None, batch=None):
+        for i, conv in enumerate(self.convs):
+            x = conv(x, edge_index, edge_weight)
+            if i < len(self.convs) - 1:
+                x = F.dropout(self.act(x), p=self.dropout, training=self.training)
+        if self.mode == "graph":
+            x = P.global_mean_pool(x, batch)
+        x = self.cls(x, edge_index, edge_weight) if self.mode == "node" else self.cls(x)
+        return F.log_softmax(x, dim=1)

@@ -3,5 +3,7 @@ from .base import BaseGDA
 from .a2gnn import A2GNN
 from .udagcn import UDAGCN
 from .grade import GRADE
+from .adagcn import AdaGCN
+from .gnn import GNN
 
-__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn
+__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE", "AdaGCN", "GNN"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn

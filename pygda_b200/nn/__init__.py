@@ -6,6 +6,8 @@ from .cached_gcn_conv import CachedGCNConv
 from .attention import Attention
 from .udagcn_base import UDAGCNBase
 from .grade_base import GRADEBase
+from .adagcn_base import AdaGCNBase
+from .gnn_base import GNNBase
 
 __all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "Attention",
-           "UDAGCNBase", "GRADEBase"]
+           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase"]

@@ -190,6 +190,65 @@ def main():
             "target_logits": t_logits.detach().clone(),
             "grads": {k: p.grad.clone() for k, p in gest.grade.named_parameters() if p.grad is not None}}
 
+    # ---- AdaGCN.forward_model (models/adagcn.py:138-198): 10 critic iterations with WGAN-GP, node and graph mode
+    from pygda_b200.synthetic import graph_dataset
+    from oracle.data import collate_graphs
+    gsrc = collate_graphs([Data(x=d.x, edge_index=d.edge_index, y=d.y) for d in graph_dataset(12, 9, 2.0, 6, 2, seed=1)])
+    gtgt = collate_graphs([Data(x=d.x, edge_index=d.edge_index, y=d.y) for d in graph_dataset(9, 11, 3.0, 6, 2, seed=2)])
+    for mode, (a, b), dims in (("node", (src, tgt), (24, 4)), ("graph", (gsrc, gtgt), (6, 2))):
+        torch.manual_seed(41)
+        aest = ref.adagcn.AdaGCN(in_dim=dims[0], hid_dim=16, num_classes=dims[1], mode=mode, num_layers=2, adv_dim=10,
+                                 gp_weight=5, domain_weight=0.5, lr=0.01, weight_decay=0.001, device='cpu')
+        aest.adagcn = aest.init_model()
+        aest.discriminator = torch.nn.Sequential(                      # as created inside fit (:264-270)
+            torch.nn.Linear(16, 10), torch.nn.ReLU(), torch.nn.Dropout(0.1), torch.nn.Linear(10, 1),
+            torch.nn.Sigmoid())
+        aest.c_optimizer = torch.optim.Adam(aest.discriminator.parameters(), lr=0.01, weight_decay=0.001)
+        with torch.no_grad():
+            for p in aest.adagcn.parameters():
+                if p.dim() == 1:
+                    p.uniform_(-0.1, 0.1)
+        aest.adagcn.eval()             # dropout off on both sides (RNG streams cannot match)
+        aest.discriminator.eval()
+        astate = {k: v.clone() for k, v in aest.adagcn.state_dict().items()}
+        dstate = {k: v.clone() for k, v in aest.discriminator.state_dict().items()}
+        torch.manual_seed(43)          # gradient_penalty draws torch.rand on the CPU generator (:405,:415,:421)
+        loss, s_logits, t_logits = aest.forward_model(a, b)
+        aest.adagcn.zero_grad()
+        loss.backward()
+        def pack(d):
+            return {k: getattr(d, k) for k in ("x", "edge_index", "y", "batch", "num_graphs") if getattr(d, k, None) is not None}
+        out["adagcn_" + mode] = {
+            "source": pack(a), "target": pack(b), "seed": 43,
+            "hparams": dict(in_dim=dims[0], hid_dim=16, num_classes=dims[1], mode=mode, num_layers=2, adv_dim=10,
+                            gp_weight=5, domain_weight=0.5, lr=0.01, weight_decay=0.001),
+            "state": astate, "critic_state": dstate,
+            "critic_state_after": {k: v.clone() for k, v in aest.discriminator.state_dict().items()},
+            "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
+            "target_logits": t_logits.detach().clone(),
+            "grads": {k: p.grad.clone() for k, p in aest.adagcn.named_parameters() if p.grad is not None}}
+
+    # ---- GNN (gcn backbone) forward_model (models/gnn.py:120-150) ---------------------------------
+    torch.manual_seed(51)
+    nest = ref.gnn.GNN(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn='gcn', device='cpu')
+    nest.gnn = nest.init_model()
+    with torch.no_grad():
+        for p in nest.gnn.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    nest.gnn.train()
+    loss, s_logits, t_logits = nest.forward_model(src, tgt)
+    nest.gnn.zero_grad()
+    loss.backward()
+    out["gnn_gcn"] = {
+        "source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
+        "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y},
+        "hparams": dict(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn='gcn'),
+        "state": {k: v.clone() for k, v in nest.gnn.state_dict().items()},
+        "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
+        "target_logits": t_logits.detach().clone(),
+        "grads": {k: p.grad.clone() for k, p in nest.gnn.named_parameters() if p.grad is not None}}
+
     for name, blob in out.items():
         torch.save(blob, os.path.join(HERE, name + ".pt"))
         print("wrote", name + ".pt", os.path.getsize(os.path.join(HERE, name + ".pt")), "bytes")

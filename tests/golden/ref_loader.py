@@ -60,9 +60,16 @@ def load_reference():
     ns.grade_base = imp("pygda.nn.grade_base")
     pkg.nn.GRADEBase = ns.grade_base.GRADEBase
 
+    ns.adagcn_base = imp("pygda.nn.adagcn_base")
+    pkg.nn.AdaGCNBase = ns.adagcn_base.AdaGCNBase
+
     ns.base = imp("pygda.models.base")
     pkg.models.BaseGDA = ns.base.BaseGDA
     ns.a2gnn = imp("pygda.models.a2gnn")
     ns.udagcn = imp("pygda.models.udagcn")
     ns.grade = imp("pygda.models.grade")
+    ns.adagcn = imp("pygda.models.adagcn")
+    ns.gnn_base = imp("pygda.nn.gnn_base")
+    pkg.nn.GNNBase = ns.gnn_base.GNNBase
+    ns.gnn = imp("pygda.models.gnn")
     return ns
