@@ -49,6 +49,7 @@ k_mmd_l2(const float* __restrict__ src, int64_t lds, const float* __restrict__ t
   __shared__ const float* rowA[TILE];
   __shared__ const float* rowB[TILE];
   const int n = 2 * b, t = blockIdx.z;
+  if (blockIdx.x < blockIdx.y) return;                  // L2 is symmetric: upper-triangular tiles only
   const int i0 = blockIdx.y * TILE, j0 = blockIdx.x * TILE;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   if (tid < TILE) {
@@ -108,6 +109,28 @@ k_mmd_l2(const float* __restrict__ src, int64_t lds, const float* __restrict__ t
       local += acc[i][j];
     }
   }
+  if (blockIdx.x != blockIdx.y) {                       // mirror tile: G[j, i] = G[i, j], written coalesced
+    local *= 2.0;
+    __syncthreads();                                    // As is free again: reuse it as a 64 x 64 staging tile
+    float (*T)[TILE + 1] = reinterpret_cast<float (*)[TILE + 1]>(&As[0][0]);   // DK * (TILE+1) >= 32 * 65 floats
+    for (int half = 0; half < 2; ++half) {              // 32 tile rows (i) at a time
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int li = ty * 4 + i;
+        if (li / 32 == half) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) T[li % 32][tx * 4 + j] = acc[i][j];
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < 32 * TILE; e += THREADS) {
+        const int li = e % 32, lj = e / 32;             // consecutive threads -> consecutive i (contiguous in row j)
+        const int gi = i0 + half * 32 + li, gj = j0 + lj;
+        if (gi < n && gj < n) G[(int64_t)gj * n + gi] = T[li][lj];
+      }
+      __syncthreads();
+    }
+  }
   // block reduction in double
   __shared__ double red[THREADS / 32];
 #pragma unroll
@@ -131,18 +154,29 @@ k_mmd_kernel(int b, float kernel_mul, int kernel_num, MmdWs ws) {
   const float sum_l2 = static_cast<float>(ws.sums[2 * t]);
   float bw = (sum_l2 + 1e-6f) / static_cast<float>((int64_t)n * n - n);
   bw = bw / powf(kernel_mul, static_cast<float>(kernel_num / 2));
-  float bwq[kMaxKernels];
-  for (int q = 0; q < kernel_num; ++q) bwq[q] = bw * powf(kernel_mul, static_cast<float>(q));
+  float inv_bwq[kMaxKernels];
+  for (int q = 0; q < kernel_num; ++q) inv_bwq[q] = 1.0f / (bw * powf(kernel_mul, static_cast<float>(q)));
+  const bool pow2_chain = (kernel_mul == 2.0f);
   float* G = ws.G + ((int64_t)t * n + i) * n;
   const float inv_bb = 1.f / (static_cast<float>(b) * static_cast<float>(b));
   float loss = 0.f, rs = 0.f;
   for (int j = tid; j < n; j += THREADS) {
     const float l2 = G[j];
     float k = 0.f, dk = 0.f;
-    for (int q = 0; q < kernel_num; ++q) {
-      const float e = expf(-l2 / bwq[q]);
-      k += e;
-      dk -= e / bwq[q];
+    if (pow2_chain) {
+      // bandwidths are a factor 2 apart: exp(-l2/bw_q) = exp(-l2/bw_{q+1})^2 -- one expf, then squarings
+      float e = expf(-l2 * inv_bwq[kernel_num - 1]);
+      for (int q = kernel_num - 1; q >= 0; --q) {
+        k += e;
+        dk -= e * inv_bwq[q];
+        e *= e;
+      }
+    } else {
+      for (int q = 0; q < kernel_num; ++q) {
+        const float e = expf(-l2 * inv_bwq[q]);
+        k += e;
+        dk -= e * inv_bwq[q];
+      }
     }
     const float sign = ((i < b) == (j < b)) ? 1.f : -1.f;
     loss += sign * k;
