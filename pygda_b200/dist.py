@@ -140,6 +140,10 @@ class PartitionedGraph:
         del full
         self.device = group.device
         self._ws, self._sym = {}, {}
+        # every partitioned graph has its own barrier channel (flag array + epoch counter): graphs used
+        # on different streams (source / target branch) then never wait on each other's epochs
+        self.flags = SymBuffer(group, 8 * MAX_PEERS)
+        self.epoch = 0
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -168,6 +172,11 @@ class PartitionedGraph:
             s = self._sym[width] = (SymBuffer(self.group, nbytes), SymBuffer(self.group, nbytes))
         return s
 
+    def _barrier(self):
+        self.epoch += 1
+        gda.peer_barrier(self.flags.ptr_array, self.group.rank, self.group.world, self.epoch,
+                         C.c_void_p(self.group.error.data_ptr()), _stream())
+
     def spmm_k(self, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, seed_offset=None):
         """A_hat^k x over the partition: x and the result are this rank's [n_local, H] blocks."""
         x = ops._f32c(x)
@@ -184,16 +193,17 @@ class PartitionedGraph:
             gda.spmm_peer_k_f32(self._h, int(bool(transpose)), int(k), ops._p(x), bufs[0].ptr_array,
                                 bufs[1].ptr_array, g.world, g.rank, ops._p(out), h, ops._p(bias), flags,
                                 float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, ops._p(seed_offset), ops._p(ws),
-                                ws.numel(), g.flags.ptr_array, g.epoch, C.c_void_p(g.error.data_ptr()), _stream())
-            g.epoch += k + 1
+                                ws.numel(), self.flags.ptr_array, self.epoch, C.c_void_p(g.error.data_ptr()),
+                                _stream())
+            self.epoch += k + 1
             return out
         # bench.py instrumentation: one call per step so that each launch can be timed
         views = [b.view(torch.float32, (self.rows_per_rank, h)) for b in bufs]
-        g.barrier()                                   # every rank is done with the buffers of the last call
+        self._barrier()                               # every rank is done with the buffers of the last call
         views[0][:n].copy_(x)
         for i in range(k):
             last = i == k - 1
-            g.barrier()                               # step i-1 (or the copy-in) is complete on every rank
+            self._barrier()                           # step i-1 (or the copy-in) is complete on every rank
             dst = out if last else views[(i + 1) & 1]
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()

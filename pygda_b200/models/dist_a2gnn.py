@@ -24,7 +24,7 @@ class DistA2GNN(A2GNN):
         if self.mode != 'node' or self.adv:
             raise NotImplementedError("the partitioned path covers node-level A2GNN with the MMD loss")
         self.group = group
-        self.overlap_streams = False
+        self.overlap_streams = True
 
     def init_model(self, **kwargs):
         net = super().init_model(**kwargs)
@@ -48,16 +48,27 @@ class DistA2GNN(A2GNN):
 
     def forward_model(self, source_data, target_data, alpha, mmd_indices=None):
         net, pg = self.a2gnn, self.group.pg
-        s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
+        # source branch (dense, no propagation steps but the classifier's) on a side stream, target
+        # branch (k peer-memory propagation steps per conv) on the current one -- as in A2GNN.forward_model;
+        # each partitioned graph has its own barrier channel, so the two streams never interlock
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if self.overlap_streams else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
+            source_logits = net(source_data, self.s_pnums, first_layer=s1)
+            ce_local = ops.softmax_cross_entropy(source_logits, source_data.y)
+            frac = source_data.x.shape[0] / float(source_data.num_nodes_global)
+            train_loss = AllReduceSum.apply(ops.combine([(ce_local, frac)]), pg)   # global mean CE
+            source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, None, self.s_pnums,
+                                                  first_layer=s1)
         t1 = net.first_conv(target_data.x, target_data.edge_index, self.t_pnums)
-        source_logits = net(source_data, self.s_pnums, first_layer=s1)
-        ce_local = ops.softmax_cross_entropy(source_logits, source_data.y)
-        frac = source_data.x.shape[0] / float(source_data.num_nodes_global)
-        train_loss = AllReduceSum.apply(ops.combine([(ce_local, frac)]), pg)       # global mean CE
-        source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, None, self.s_pnums,
-                                              first_layer=s1)
         target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, None, self.t_pnums,
                                               first_layer=t1)
+        if side is not main:
+            main.wait_stream(side)
+            for t in (source_logits, train_loss, source_features):
+                t.record_stream(main)
         s_idx, t_idx = self._mmd_indices(source_data.num_nodes_global, target_data.num_nodes_global, mmd_indices)
         times, b = s_idx.shape
         s_rows = GatherRows.apply(source_features, s_idx.reshape(-1), source_data.row_lo, pg)
