@@ -368,24 +368,6 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
       int myc = 0;
       float myv = 0.f;
       if (valid) { myc = __ldg(colidx + e); myv = __ldg(vals + e); }
-      if (PEER) {
-        // Rows owned by other GPUs arrive over NVLink (~2 us, L2-bypassing, L1-cacheable): start
-        // fetching the remote rows of the NEXT chunk into L1 now, a whole chunk of work ahead.
-        const int en = e + LPR;
-        const int nxt = (en < end) ? __ldg(colidx + en) : pad_col;
-        unsigned remote = (__ballot_sync(gmask, (nxt >> 28) != (pad_col >> 28)) >> (sub * LPR)) &
-                          ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
-        while (remote) {
-          const int bit = __ffs(remote) - 1;
-          remote &= remote - 1;
-          const unsigned cn = static_cast<unsigned>(__shfl_sync(gmask, nxt, bit, LPR));
-          if (active) {
-            const char* addr = static_cast<const char*>(peers.p[cn >> 28]) + c0 * sizeof(T) +
-                               static_cast<uint64_t>(cn & 0x0FFFFFFFu) * ldxb;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
-          }
-        }
-      }
       int rid = 0, rid1 = 0, mylen = 0, myend = end;
 #pragma unroll
       for (int i = 1; i <= RPG; ++i) {
