@@ -32,6 +32,12 @@
 #ifndef GDA_SPMM_U4
 #define GDA_SPMM_U4 8
 #endif
+#ifndef GDA_ROWS_BLOCK
+#define GDA_ROWS_BLOCK 128
+#endif
+#ifndef GDA_ROWS_MIN_CTAS
+#define GDA_ROWS_MIN_CTAS 12
+#endif
 
 namespace gda {
 namespace {
@@ -102,6 +108,11 @@ __device__ __forceinline__ void apply_epilogue(float (&acc)[VEC], const Epilogue
       y = dropout_keep(seed, static_cast<uint64_t>(row) * H + c0 + v, epi.thresh) ? y * epi.scale : 0.f;
     acc[v] = y;
   }
+}
+
+inline bool fast_forced() {     // experiments: keep the row-block streaming kernel for the common width too
+  static const bool on = [] { const char* e = std::getenv("GDA_SPMM_STREAM"); return e && e[0] == '1'; }();
+  return on;
 }
 
 inline bool generic_forced() {
@@ -461,6 +472,112 @@ k_spmm_fast(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-per-warp kernel for the common width (one 16-byte slice per lane: H = 128 fp32 / 256 bf16).
+// The probes in profiles/probes/ show what bounds a gather on this GPU: with ~48-64 resident
+// warps per SM and only 4 independent 512-byte row gathers in flight per warp, plain LDG.128
+// reaches 16.5 TB/s of gathered rows under the aggregation's own read/write pattern (19.5 TB/s
+// read-only) -- occupancy, not per-warp depth, hides the L2/HBM latency, and cp.async staging is
+// slower (16.8 TB/s best).  So: minimal state per warp (~40 registers), (colidx, weight) read
+// with warp-uniform loads (one L1 transaction, no shuffles), the next batch's indices fetched
+// while the current batch's rows are in flight, grid-stride over rows.  Long rows are again
+// handled as `seg`-sized segments (work items < num_segs) with an ordered reduction.
+template <typename T, int VEC, bool EPI, bool PEER>
+__global__ void __launch_bounds__(GDA_ROWS_BLOCK, GDA_ROWS_MIN_CTAS)
+k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ vals,
+            int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
+            const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
+            const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int N, int H,
+            Epilogue epi, float* __restrict__ partial, PeerTable peers) {
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * VEC;
+  const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
+  const int total = num_segs + N;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
+    int row, p, e, L = -1;
+    if (item < num_segs) {
+      L = __ldg(seg_long + item);
+      row = __ldg(long_rows + L);
+      p = __ldg(rowptr + row) + (item - __ldg(long_seg_ptr + L)) * seg;
+      e = min(p + seg, __ldg(rowptr + row + 1));
+    } else {
+      row = item - num_segs;
+      p = __ldg(rowptr + row);
+      e = __ldg(rowptr + row + 1);
+      if (e - p > seg) continue;                        // covered by its segments
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    int cn[U];
+    float wn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                       // indices of the first batch
+      const bool ok = p + u < e;
+      cn[u] = ok ? __ldg(colidx + p + u) : 0;
+      wn[u] = ok ? __ldg(vals + p + u) : 0.f;
+    }
+    while (p < e) {
+      float xv[U][VEC];
+      float wv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        wv[u] = wn[u];
+        if (p + u < e) {
+          const unsigned cj = static_cast<unsigned>(cn[u]);
+          const char* src = PEER ? static_cast<const char*>(peers.p[cj >> 28]) + c0 * sizeof(T) +
+                                       static_cast<uint64_t>(cj & 0x0FFFFFFFu) * ldxb
+                                 : Xc + static_cast<uint64_t>(cj) * ldxb;
+          VecIO<T, VEC>::load(reinterpret_cast<const T*>(src), xv[u]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) xv[u][v] = 0.f;
+        }
+      }
+      p += U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {                     // next batch's indices while the rows are in flight
+        const bool ok = p + u < e;
+        cn[u] = ok ? __ldg(colidx + p + u) : 0;
+        wn[u] = ok ? __ldg(vals + p + u) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+    }
+    if (L < 0) {
+      if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
+      VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
+    } else {
+      float* dst = partial + static_cast<int64_t>(item) * H + c0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+      __threadfence();
+      __syncwarp();
+      int old = 0;
+      const int first = __ldg(long_seg_ptr + L), nseg = __ldg(long_seg_ptr + L + 1) - first;
+      if (lane == 0) old = atomicAdd(counters + L, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == nseg - 1) {                            // last segment to arrive reduces, in order
+        __threadfence();
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          const float* srcp = partial + static_cast<int64_t>(first + sgi) * H + c0;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(srcp + v);
+        }
+        if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
+        VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
+        if (lane == 0) counters[L] = 0;
+      }
+    }
+  }
+}
+
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
            const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
@@ -473,6 +590,24 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
   const unsigned grid = static_cast<unsigned>(ceil_div(groups, groups_per_block));
   constexpr int UF = U <= LPR ? U : LPR;               // batches must tile a chunk of LPR entries
   const bool has_epi = epi.bias != nullptr || epi.flags != 0;
+  if (LPR == 32 && H == 32 * VEC && VEC * sizeof(T) == 16 && !generic && !fast_forced()) {
+    // one 16-byte slice per lane: row-per-warp kernel, grid-stride over rows
+    const unsigned ldxb = static_cast<unsigned>(ldx * sizeof(T)), ldyb = static_cast<unsigned>(ldy * sizeof(T));
+    const int64_t items = static_cast<int64_t>(c.num_segs) + N;
+    int64_t blocks = ceil_div(items, GDA_ROWS_BLOCK / 32);
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * GDA_ROWS_MIN_CTAS;
+    if (blocks > cap) blocks = cap;
+    const PeerTable pt = peers ? *peers : PeerTable{};
+#define GDA_ROWS_LAUNCH(E, P)                                                                              \
+    k_spmm_rows<T, VEC, E, P><<<static_cast<unsigned>(blocks), GDA_ROWS_BLOCK, 0, st>>>(                  \
+        c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, \
+        X, ldxb, Y, ldyb, static_cast<int>(N), H, epi, partial, pt)
+    if (peers) { if (has_epi) GDA_ROWS_LAUNCH(true, true); else GDA_ROWS_LAUNCH(false, true); }
+    else { if (has_epi) GDA_ROWS_LAUNCH(true, false); else GDA_ROWS_LAUNCH(false, false); }
+#undef GDA_ROWS_LAUNCH
+    GDA_LAUNCH_CHECK();
+    return GDA_OK;
+  }
   if (generic) {
     k_spmm<T, VEC, LPR, U><<<grid, kBlock, 0, st>>>(c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows,
                                                    c.long_seg_ptr, c.seg_long, c.counters, seg, X, ldx, Y, ldy,
