@@ -332,7 +332,6 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
   }
 
   g->csr.may_have_empty_rows = g->csr_t.may_have_empty_rows = !loops;   // a self loop in every row
-  g->csr.nnz = g->csr_t.nnz = nnz;
   // 5. long-row segments for both orientations
   if ((rc = build_long_rows(g->csr, N, g->seg, sc, st))) return rc;
   if ((rc = build_long_rows(g->csr_t, N, g->seg, sc, st))) return rc;
@@ -393,7 +392,6 @@ int graph_partition(const gda_graph* g, int64_t row_lo, int64_t row_hi, int64_t 
       GDA_LAUNCH_CHECK();
     }
     d.may_have_empty_rows = false;
-    d.nnz = nnz;
     if ((rc = build_long_rows(d, n, p->seg, sc, st))) return rc;
   }
   GDA_CUDA(cudaStreamSynchronize(st));

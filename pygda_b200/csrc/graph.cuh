@@ -23,7 +23,6 @@ struct Csr {
   int32_t* seg_long = nullptr;      // [num_segs] long-row index of each segment
   int32_t* counters = nullptr;      // [num_long] arrival counters, zero between launches
   bool     may_have_empty_rows = true;   // false when every row holds a self loop
-  int64_t  nnz = 0;                      // rowptr[N]
 };
 
 }  // namespace gda

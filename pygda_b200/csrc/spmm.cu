@@ -32,12 +32,6 @@
 #ifndef GDA_SPMM_U4
 #define GDA_SPMM_U4 8
 #endif
-#ifndef GDA_ROWS_U
-#define GDA_ROWS_U 4
-#endif
-#ifndef GDA_ROWS_QUOTA
-#define GDA_ROWS_QUOTA 64
-#endif
 #ifndef GDA_ROWS_BLOCK
 #define GDA_ROWS_BLOCK 128
 #endif
@@ -494,42 +488,25 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
             int num_segs, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
             const int* __restrict__ seg_long, int* __restrict__ counters, int seg,
             const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int N, int H,
-            Epilogue epi, float* __restrict__ partial, PeerTable peers, int pad_col, int nnz, int quota) {
-  constexpr int U = GDA_ROWS_U;
+            Epilogue epi, float* __restrict__ partial, PeerTable peers, int pad_col) {
+  constexpr int U = 4;
   const int lane = threadIdx.x & 31;
   const int c0 = lane * VEC;
   const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
-  // Work items of (nearly) equal size, one warp each, scheduled dynamically by the hardware:
-  // warps [0, num_segs) take one segment of a split long row; every following warp takes the rows
-  // that START inside its slice of `quota` consecutive non-zeros (found by one binary search over
-  // rowptr).  A grid-stride split by row COUNT left the power-law degree tail on single warps
-  // (55.7 us vs 37 us for the same gathers with equal-length rows, profiles/probes).
-  const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int row, p, L = -1, stop;
-  if (item < num_segs) {
-    L = __ldg(seg_long + item);
-    row = __ldg(long_rows + L);
-    p = __ldg(rowptr + row) + (item - __ldg(long_seg_ptr + L)) * seg;
-    stop = p + 1;
-  } else {
-    const int a = (item - num_segs) * quota;
-    if (a >= nnz) return;
-    stop = min(nnz, a + quota);
-    int lo = 0, hi = N;                                 // first row with rowptr[row] >= a
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(rowptr + mid) < a) lo = mid + 1; else hi = mid;
-    }
-    row = lo;
-    p = (row < N) ? __ldg(rowptr + row) : nnz;
-  }
-  for (; p < stop; ++row) {
-    int e;
-    if (L >= 0) {
+  const int total = num_segs + N;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
+    int row, p, e, L = -1;
+    if (item < num_segs) {
+      L = __ldg(seg_long + item);
+      row = __ldg(long_rows + L);
+      p = __ldg(rowptr + row) + (item - __ldg(long_seg_ptr + L)) * seg;
       e = min(p + seg, __ldg(rowptr + row + 1));
     } else {
+      row = item - num_segs;
+      p = __ldg(rowptr + row);
       e = __ldg(rowptr + row + 1);
-      if (e - p > seg) { p = e; continue; }             // long row: covered by its segments
+      if (e - p > seg) continue;                        // covered by its segments
     }
     float acc[VEC];
 #pragma unroll
@@ -540,7 +517,6 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
     const int* __restrict__ ci = colidx + p;
     const float* __restrict__ cw = vals + p;
     int left = e - p;
-    const int item_slot = item;
     for (; left >= U; left -= U, ci += U, cw += U) {
       unsigned cj[U];
       float wv[U];
@@ -585,7 +561,7 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
       if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
       VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
     } else {
-      float* dst = partial + static_cast<int64_t>(item_slot) * H + c0;
+      float* dst = partial + static_cast<int64_t>(item) * H + c0;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
       __threadfence();
@@ -608,14 +584,12 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
         if (lane == 0) counters[L] = 0;
       }
     }
-    p = e;
   }
 }
 
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-           const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0,
-           int64_t nnz = 0) {
+           const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
   constexpr int RPG = RowsPerGroup<LPR>::value;
   const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
   const bool generic = c.may_have_empty_rows || generic_forced();
@@ -628,14 +602,15 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
   if (LPR == 32 && H == 32 * VEC && VEC * sizeof(T) == 16 && !generic && !fast_forced()) {
     // one 16-byte slice per lane: row-per-warp kernel, grid-stride over rows
     const unsigned ldxb = static_cast<unsigned>(ldx * sizeof(T)), ldyb = static_cast<unsigned>(ldy * sizeof(T));
-    const int quota = GDA_ROWS_QUOTA;                      // non-zeros per warp (~ one segment)
-    const int64_t items = static_cast<int64_t>(c.num_segs) + ceil_div(nnz, quota);
-    const int64_t blocks = ceil_div(items, GDA_ROWS_BLOCK / 32);
+    const int64_t items = static_cast<int64_t>(c.num_segs) + N;
+    int64_t blocks = ceil_div(items, GDA_ROWS_BLOCK / 32);
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * GDA_ROWS_MIN_CTAS;
+    if (blocks > cap) blocks = cap;
     const PeerTable pt = peers ? *peers : PeerTable{};
 #define GDA_ROWS_LAUNCH(E, P)                                                                              \
     k_spmm_rows<T, VEC, E, P><<<static_cast<unsigned>(blocks), GDA_ROWS_BLOCK, 0, st>>>(                  \
         c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, \
-        X, ldxb, Y, ldyb, static_cast<int>(N), H, epi, partial, pt, pad_col, static_cast<int>(nnz), quota)
+        X, ldxb, Y, ldyb, static_cast<int>(N), H, epi, partial, pt, pad_col)
     if (peers) { if (has_epi) GDA_ROWS_LAUNCH(true, true); else GDA_ROWS_LAUNCH(false, true); }
     else { if (has_epi) GDA_ROWS_LAUNCH(true, false); else GDA_ROWS_LAUNCH(false, false); }
 #undef GDA_ROWS_LAUNCH
@@ -672,17 +647,16 @@ inline int pow2_at_least(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <typename T, int VEC>
 int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-                 const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0,
-                 int64_t nnz = 0) {
+                 const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
   int lanes = pow2_at_least(static_cast<int>(ceil_div(H, VEC)));
   if (lanes > 32) lanes = 32;
   if (lanes < 4) lanes = 4;
   constexpr int U = (VEC == 4) ? GDA_SPMM_U4 : 4;               // 8 x float4 or 4 x (8 bf16) gathers in flight per lane
   switch (lanes) {
-    case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col, nnz);
-    case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col, nnz);
-    case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col, nnz);
-    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col, nnz);
+    case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
   }
 }
 
@@ -718,8 +692,8 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   const int pad_col = peers ? (my_rank << 28) : 0;
   if (peers)
     for (int i = 0; i < GDA_MAX_PEERS; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(peers->p[i]) % 16 == 0);
-  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col, c.nnz);
-  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col, c.nnz);
+  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
+  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
 }
 
 }  // namespace
