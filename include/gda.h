@@ -234,6 +234,18 @@ int gda_mmd_bwd(const float* src, int64_t lds, const float* tgt, int64_t ldt, in
                 float* gtgt, int64_t ldgt, void* workspace, int64_t workspace_bytes,
                 gda_stream_t stream);
 
+/* ------------------------------------------------------------------- GAT --
+ * Edge-softmax aggregation of the stock PyG GATConv(heads=1, concat=False) used by
+ * pygda/nn/gnn_base.py:81-87: e_ij = leaky_relu(a_src[j] + a_dst[i]), alpha = softmax over the
+ * in-edges of i (+1e-16), out_i = sum_j alpha_ij h_j.  g: graph built with GDA_SELF_LOOPS and no
+ * normalisation.  alpha: float [nnz] (CSR order) written by the forward and read by the backward;
+ * scratch: float [nnz].  The backward OVERWRITES dh [N,C], da_src [N], da_dst [N]. */
+int gda_gat_fwd(const gda_graph_t* g, const float* h, int C, const float* a_src, const float* a_dst,
+                float negative_slope, float* out, float* alpha, gda_stream_t stream);
+int gda_gat_bwd(const gda_graph_t* g, const float* h, int C, const float* a_src, const float* a_dst,
+                float negative_slope, const float* alpha, const float* gout, float* dh, float* da_src,
+                float* da_dst, float* scratch, gda_stream_t stream);
+
 /* ---------------------------------------------------------------- pooling --
  * global_mean_pool over a sorted `batch` vector given as CSR-style ptr
  * (int64 [G+1]).  Call sites: a2gnn_base.py:141, adagcn_base.py:94,

@@ -222,8 +222,9 @@ class AdaGCN:
 class GNN:
     """pygda/models/gnn.py:59-268 over the gcn backbone (forward_model :120-150)."""
 
-    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0., act=F.relu, **kwargs):
-        self.gnn = ONN.GNNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, dropout=dropout, act=act)
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0., act=F.relu, gnn="gcn", **kwargs):
+        self.gnn = ONN.GNNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, dropout=dropout, act=act,
+                               gnn=gnn)
 
     def forward_model(self, source_data, target_data):
         source_logits = self.gnn(source_data.x, source_data.edge_index)

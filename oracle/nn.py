@@ -299,12 +299,13 @@ class GNNBase(nn.Module):
     def __init__(self, in_dim, hid_dim, num_classes, num_layers=1, dropout=0.1, act=F.relu,
                  gnn="gcn", mode="node", **kwargs):
         super().__init__()
-        assert gnn == "gcn"
+        assert gnn in ("gcn", "gat")
+        conv = GCNConv if gnn == "gcn" else (lambda i, o: GATConv(i, o, heads=1, concat=False))
         self.dropout, self.act, self.mode = dropout, act, mode
-        self.convs = nn.ModuleList([GCNConv(in_dim, hid_dim)])
+        self.convs = nn.ModuleList([conv(in_dim, hid_dim)])
         for _ in range(num_layers - 1):
-            self.convs.append(GCNConv(hid_dim, hid_dim))
-        self.cls = GCNConv(hid_dim, num_classes) if mode == "node" else nn.Linear(hid_dim, num_classes)
+            self.convs.append(conv(hid_dim, hid_dim))
+        self.cls = conv(hid_dim, num_classes) if mode == "node" else nn.Linear(hid_dim, num_classes)
 
     def forward(self, x, edge_index, edge_weight=None, batch=None):
         for i, conv in enumerate(self.convs):
@@ -315,3 +316,36 @@ class GNNBase(nn.Module):
             x = P.global_mean_pool(x, batch)
         x = self.cls(x, edge_index, edge_weight) if self.mode == "node" else self.cls(x)
         return F.log_softmax(x, dim=1)
+
+
+class GATConv(nn.Module):
+    """Stock PyG ``GATConv(in, out, heads=1, concat=False)`` (call site
+    pygda/nn/gnn_base.py:81-87).  "parity unpinned" upstream restatement: lin_src shared for
+    source/target, att_src/att_dst [1,1,out] glorot, negative_slope 0.2, remove + add self loops,
+    softmax over the in-edges of each target (max-subtracted, +1e-16), mean over the single head, + bias."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=False, negative_slope=0.2, **kwargs):
+        super().__init__()
+        assert heads == 1 and not concat
+        self.out_channels, self.negative_slope = out_channels, negative_slope
+        self.lin_src = P.Linear(in_channels, out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, 1, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        P.glorot_(self.att_src)
+        P.glorot_(self.att_dst)
+
+    def forward(self, x, edge_index, edge_weight=None):
+        n, c = x.size(0), self.out_channels
+        h = self.lin_src(x).view(n, 1, c)
+        a_s = (h * self.att_src).sum(-1)
+        a_d = (h * self.att_dst).sum(-1)
+        ei, _ = P.remove_self_loops(edge_index)
+        ei = P.add_self_loops(ei, n)
+        e = F.leaky_relu(a_s[ei[0]] + a_d[ei[1]], self.negative_slope)          # [E, 1]
+        m = torch.full((n, 1), float("-inf")).scatter_reduce(0, ei[1].view(-1, 1), e, "amax", include_self=True)
+        ex = (e - m[ei[1]]).exp()
+        den = P.scatter_add(ex, ei[1], 0, n) + 1e-16
+        alpha = ex / den[ei[1]]
+        out = P.scatter_add(alpha.unsqueeze(-1) * h[ei[0]], ei[1], 0, n)        # [N, 1, C]
+        return out.mean(dim=1) + self.bias

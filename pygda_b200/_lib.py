@@ -57,6 +57,8 @@ SIGNATURES = {
     "gda_mmd_workspace_bytes": (i64, [i32, i32, i32]),
     "gda_mmd_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp, i32, i32, f32, i32, vp, vp, i64, vp]),
     "gda_mmd_bwd": (i32, [vp, i64, vp, i64, i32, vp, vp, i32, i32, vp, vp, i64, vp, i64, vp, i64, vp]),
+    "gda_gat_fwd": (i32, [vp, vp, i32, vp, vp, f32, vp, vp, vp]),
+    "gda_gat_bwd": (i32, [vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "gda_segment_mean_bwd": (i32, [vp, vp, i64, i32, vp, i64, vp]),
     "gda_adam_step": (i32, [i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp]),

@@ -8,6 +8,7 @@ from .udagcn_base import UDAGCNBase
 from .grade_base import GRADEBase
 from .adagcn_base import AdaGCNBase
 from .gnn_base import GNNBase
+from .gat_conv import GATConv
 
 __all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "Attention",
-           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase"]
+           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv"]

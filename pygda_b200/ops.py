@@ -361,6 +361,21 @@ def act_dropout(x, act, p, training):
     return x
 
 
+class BiasAddFn(torch.autograd.Function):
+    """x + bias (broadcast over rows) on libgda; backward = (g, column sums of g)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        gda.bias_act_dropout_fwd(_p(x), _p(bias), _p(y), x.shape[0], x.shape[1], 0, 0.0, 0, _NULL, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, colsum(g)
+
+
 class GradReverse(torch.autograd.Function):
     """pygda/nn/reverse_layer.py:4-66: identity forward, -alpha * g backward."""
 

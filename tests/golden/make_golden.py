@@ -228,26 +228,27 @@ def main():
             "target_logits": t_logits.detach().clone(),
             "grads": {k: p.grad.clone() for k, p in aest.adagcn.named_parameters() if p.grad is not None}}
 
-    # ---- GNN (gcn backbone) forward_model (models/gnn.py:120-150) ---------------------------------
-    torch.manual_seed(51)
-    nest = ref.gnn.GNN(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn='gcn', device='cpu')
-    nest.gnn = nest.init_model()
-    with torch.no_grad():
-        for p in nest.gnn.parameters():
-            if p.dim() == 1:
-                p.uniform_(-0.1, 0.1)
-    nest.gnn.train()
-    loss, s_logits, t_logits = nest.forward_model(src, tgt)
-    nest.gnn.zero_grad()
-    loss.backward()
-    out["gnn_gcn"] = {
-        "source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
-        "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y},
-        "hparams": dict(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn='gcn'),
-        "state": {k: v.clone() for k, v in nest.gnn.state_dict().items()},
-        "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
-        "target_logits": t_logits.detach().clone(),
-        "grads": {k: p.grad.clone() for k, p in nest.gnn.named_parameters() if p.grad is not None}}
+    # ---- GNN (gcn / gat backbone) forward_model (models/gnn.py:120-150) ----------------------------
+    for backbone in ("gcn", "gat"):
+        torch.manual_seed(51)
+        nest = ref.gnn.GNN(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn=backbone, device='cpu')
+        nest.gnn = nest.init_model()
+        with torch.no_grad():
+            for p in nest.gnn.parameters():
+                if p.dim() == 1:
+                    p.uniform_(-0.1, 0.1)
+        nest.gnn.train()
+        loss, s_logits, t_logits = nest.forward_model(src, tgt)
+        nest.gnn.zero_grad()
+        loss.backward()
+        out["gnn_" + backbone] = {
+            "source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
+            "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y},
+            "hparams": dict(in_dim=24, hid_dim=16, num_classes=4, num_layers=2, dropout=0.0, gnn=backbone),
+            "state": {k: v.clone() for k, v in nest.gnn.state_dict().items()},
+            "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
+            "target_logits": t_logits.detach().clone(),
+            "grads": {k: p.grad.clone() for k, p in nest.gnn.named_parameters() if p.grad is not None}}
 
     for name, blob in out.items():
         torch.save(blob, os.path.join(HERE, name + ".pt"))
