@@ -343,7 +343,7 @@ class GATConv(nn.Module):
         ei, _ = P.remove_self_loops(edge_index)
         ei = P.add_self_loops(ei, n)
         e = F.leaky_relu(a_s[ei[0]] + a_d[ei[1]], self.negative_slope)          # [E, 1]
-        m = torch.full((n, 1), float("-inf")).scatter_reduce(0, ei[1].view(-1, 1), e, "amax", include_self=True)
+        m = torch.full((n, 1), float("-inf"), dtype=e.dtype).scatter_reduce(0, ei[1].view(-1, 1), e, "amax", include_self=True)
         ex = (e - m[ei[1]]).exp()
         den = P.scatter_add(ex, ei[1], 0, n) + 1e-16
         alpha = ex / den[ei[1]]
