@@ -316,7 +316,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     except Exception:
         pass
     per_step_spmm = len(times) / max(min(args.steps, 5), 1)
-    roofline = {"bound": "hbm", "kernel": "k_spmm<float,4,32,8> (A_hat x, H=128, N=100k, nnz=%d)" % nnz,
+    roofline = {"bound": "hbm", "kernel": "k_spmm_rows<float,4,4,false> (A_hat x, H=128, N=100k, nnz=%d)" % nnz,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "traffic": traffic["bytes_per_launch"] if traffic else None,
