@@ -101,7 +101,7 @@ def main():
     if os.path.exists(sp):
         import json
         for d in rep_metrics(sp):
-            if "k_spmm" in d["kernel"] and "float, (int)4, (int)32" in d["kernel"] or "float, 4, 32" in d["kernel"]:
+            if "k_spmm_rows<float, 4" in d["kernel"] or "k_spmm_fast<float, 4, 32" in d["kernel"]:
                 def mb(v):
                     num, unit = v.split()[:2]
                     return float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
