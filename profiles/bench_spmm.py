@@ -11,7 +11,11 @@ from pygda_b200.graph import Graph                            # noqa: E402
 from pygda_b200.synthetic import powerlaw_edge_index          # noqa: E402
 
 n = int(os.environ.get("N", 100_000)); e = int(os.environ.get("E", 1_000_000))
-for h, dt in ((128, torch.float32), (5, torch.float32), (256, torch.bfloat16), (64, torch.float32)):
+cases = ((128, torch.float32), (5, torch.float32), (256, torch.bfloat16), (64, torch.float32))
+if os.environ.get("WIDE_ONLY"):                                # the one-16-byte-slice-per-lane widths only
+    cases = ((128, torch.float32), (256, torch.bfloat16))
+print("GDA_SPMM_TASKS =", os.environ.get("GDA_SPMM_TASKS", "(default 4)"))
+for h, dt in cases:
     ei = powerlaw_edge_index(n, e, seed=2, offset=48.0).cuda()
     g = Graph(ei, n)
     x = torch.randn(n, h, device="cuda").to(dt)

@@ -142,6 +142,34 @@ __global__ void k_long_fill(const int* __restrict__ is_long, const int* __restri
   for (int j = 0; j < nsegs[i]; ++j) seg_long[seg_pos[i] + j] = L;
 }
 
+// Work items of k_spmm_tasks: item < num_segs is a segment of a long row, item - num_segs a row.
+// Rows covered by segments (and empty rows) get length 0 and sort to the end of the list.
+__global__ void k_task_make(const int* __restrict__ rowptr, int64_t N, int num_segs, int seg,
+                            const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
+                            const int* __restrict__ seg_long, unsigned* __restrict__ keys,
+                            unsigned long long* __restrict__ descs) {
+  int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (item >= num_segs + N) return;
+  int p, len;
+  unsigned y;
+  if (item < num_segs) {
+    const int L = seg_long[item];
+    const int row = long_rows[L];
+    p = rowptr[row] + (static_cast<int>(item) - long_seg_ptr[L]) * seg;
+    len = min(seg, rowptr[row + 1] - p);
+    y = 0x80000000u | static_cast<unsigned>(item);
+  } else {
+    const int row = static_cast<int>(item - num_segs);
+    p = rowptr[row];
+    len = rowptr[row + 1] - p;
+    if (len > seg) len = 0;
+    y = static_cast<unsigned>(row);
+  }
+  keys[item] = static_cast<unsigned>(seg - len);                      // ascending key = descending length
+  y |= static_cast<unsigned>(len > 0 ? len - 1 : 0) << 25;
+  descs[item] = (static_cast<unsigned long long>(y) << 32) | static_cast<unsigned>(p);
+}
+
 __global__ void k_export_coo(const int* __restrict__ src, const int* __restrict__ dst, int64_t nnz,
                              int64_t* __restrict__ out) {
   int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -195,6 +223,35 @@ int sort_by_key(const int* keys_in, int* keys_out, int* perm_out, int64_t nnz, i
   return GDA_OK;
 }
 
+// Length-sorted work list (graph.cuh: Csr::tasks).  Only for graphs whose rows are all non-empty
+// (a self loop in every row): then exactly the num_long covered rows have length 0 and are cut off.
+int build_tasks(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
+  c.tasks = nullptr;
+  c.num_tasks = 0;
+  const int64_t total = static_cast<int64_t>(c.num_segs) + N;
+  if (c.may_have_empty_rows || total == 0 || N >= (int64_t(1) << 25) || c.num_segs >= (1 << 25) || seg > 64)
+    return GDA_OK;
+  unsigned *keys, *keys_sorted;
+  unsigned long long *descs, *sorted;
+  int rc;
+  if ((rc = sc.get(&keys, total)) || (rc = sc.get(&keys_sorted, total)) || (rc = sc.get(&descs, total))) return rc;
+  if ((rc = dev_alloc(&sorted, total))) return rc;
+  c.tasks = reinterpret_cast<uint2*>(sorted);
+  k_task_make<<<blocks_for(total), kThreads, 0, st>>>(c.rowptr, N, c.num_segs, seg, c.long_rows, c.long_seg_ptr,
+                                                      c.seg_long, keys, descs);
+  GDA_LAUNCH_CHECK();
+  size_t bytes = 0;
+  GDA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_sorted, descs, sorted,
+                                           static_cast<int>(total), 0, 8, st));
+  void* tmp;
+  if ((rc = sc.get(reinterpret_cast<char**>(&tmp), static_cast<int64_t>(bytes)))) return rc;
+  GDA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, keys_sorted, descs, sorted,
+                                           static_cast<int>(total), 0, 8, st));
+  GDA_CUDA(cudaStreamSynchronize(st));
+  c.num_tasks = static_cast<int32_t>(total - c.num_long);
+  return GDA_OK;
+}
+
 int build_long_rows(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
   int *is_long, *nsegs, *long_pos, *seg_pos;
   int rc;
@@ -223,12 +280,13 @@ int build_long_rows(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
   GDA_CUDA(cudaMemcpyAsync(c.long_seg_ptr + c.num_long, &c.num_segs, sizeof(int),
                            cudaMemcpyHostToDevice, st));
   GDA_CUDA(cudaStreamSynchronize(st));   // &c.num_segs must outlive the copy
-  return GDA_OK;
+  return build_tasks(c, N, seg, sc, st);
 }
 
 void free_csr(Csr& c) {
   cudaFree(c.rowptr); cudaFree(c.colidx); cudaFree(c.vals);
   cudaFree(c.long_rows); cudaFree(c.long_seg_ptr); cudaFree(c.seg_long); cudaFree(c.counters);
+  cudaFree(c.tasks);
   c = Csr{};
 }
 

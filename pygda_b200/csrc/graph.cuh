@@ -22,6 +22,11 @@ struct Csr {
   int32_t* long_seg_ptr = nullptr;  // [num_long+1] first segment of each long row
   int32_t* seg_long = nullptr;      // [num_segs] long-row index of each segment
   int32_t* counters = nullptr;      // [num_long] arrival counters, zero between launches
+  // work list for k_spmm_tasks (spmm.cu): one entry per short row and per long-row segment, sorted by
+  // descending length so that a grid-stride walk hands every warp the same mix of lengths.
+  //   x = first non-zero;  y = segment flag << 31 | (len - 1) << 25 | row id (or global segment index)
+  uint2*   tasks = nullptr;         // [num_tasks]; null when not built (empty rows possible, ids >= 2^25)
+  int32_t  num_tasks = 0;
   bool     may_have_empty_rows = true;   // false when every row holds a self loop
 };
 

@@ -38,6 +38,12 @@
 #ifndef GDA_ROWS_MIN_CTAS
 #define GDA_ROWS_MIN_CTAS 12
 #endif
+#ifndef GDA_TASKS_MIN_CTAS
+#define GDA_TASKS_MIN_CTAS 10
+#endif
+#ifndef GDA_TASKS_MIN_CTAS_WIDE
+#define GDA_TASKS_MIN_CTAS_WIDE 8
+#endif
 
 namespace gda {
 namespace {
@@ -587,6 +593,156 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Work-list kernel for the common width (one 16-byte slice per lane), the default when the graph
+// carries a length-sorted task list (graph.cu: build_tasks).  What the ncu capture of k_spmm_rows
+// showed (profiles/r1_d_rows_kernel): DRAM traffic = B_alg, but only 58 % of the resident warps
+// active on average and 5 serial L2 latencies per average row (rowptr -> colidx -> gather, then
+// colidx -> gather per further batch).  Two changes, both in the schedule, none in the arithmetic:
+//  * static balance: tasks (short rows and 64-nnz segments of long rows) are sorted by descending
+//    length at graph build; a grid-stride walk over that list gives every warp one task from each
+//    length stratum, so all warps finish together (longest-processing-time-first scheduling);
+//  * software pipeline over tasks: while the gathers of task t are in flight the warp has already
+//    loaded the descriptor of task t+2 and the (colidx, weight) pairs of task t+1 (one coalesced
+//    load, lane l holds pair l), so a task costs ceil(len / U) dependent L2 round trips, not
+//    2 + ceil(len / U).  Indices and weights reach the lanes by shuffle.
+// The summation order inside a row is unchanged (sequential in CSR = COO order, segments reduced
+// in segment order), so results are bit-identical to k_spmm_rows.
+template <typename T, int VEC, int K, bool PEER>
+__device__ __forceinline__ void gather_batch(float (&acc)[VEC], int myc, float myv, int j, const char* __restrict__ Xc,
+                                             unsigned ldxb, int c0, const PeerTable& peers) {
+  unsigned cj[K];
+  float wv[K];
+  float xv[K][VEC];
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    cj[u] = static_cast<unsigned>(__shfl_sync(0xffffffffu, myc, j + u));
+    wv[u] = __shfl_sync(0xffffffffu, myv, j + u);
+  }
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    const char* src = PEER ? static_cast<const char*>(peers.p[cj[u] >> 28]) + c0 * sizeof(T) +
+                                 static_cast<uint64_t>(cj[u] & 0x0FFFFFFFu) * ldxb
+                           : Xc + static_cast<uint64_t>(cj[u]) * ldxb;
+    VecIO<T, VEC>::load(reinterpret_cast<const T*>(src), xv[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < K; ++u)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+}
+
+template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER>
+__global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
+k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
+             const float* __restrict__ vals, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
+             const int* __restrict__ seg_long, int* __restrict__ counters,
+             const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int H,
+             Epilogue epi, float* __restrict__ partial, PeerTable peers) {
+  static_assert(U == 4 || U == 8, "batch depth");
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * VEC;
+  const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= num_tasks) return;
+
+  uint2 cur = __ldg(tasks + i);
+  bool has_next = i + nwarps < num_tasks;
+  uint2 nxt = make_uint2(0u, 0u);
+  if (has_next) nxt = __ldg(tasks + i + nwarps);
+  int myc = 0;
+  float myv = 0.f;
+  if (lane <= static_cast<int>((cur.y >> 25) & 63u)) {
+    myc = __ldg(colidx + cur.x + lane);
+    myv = __ldg(vals + cur.x + lane);
+  }
+
+  while (true) {
+    // ---- prefetch: pairs of the next task, descriptor of the one after ----
+    int nc = 0;
+    float nv = 0.f;
+    uint2 nn = make_uint2(0u, 0u);
+    const bool has_nn = i + 2 * nwarps < num_tasks;
+    if (has_next && lane <= static_cast<int>((nxt.y >> 25) & 63u)) {
+      nc = __ldg(colidx + nxt.x + lane);
+      nv = __ldg(vals + nxt.x + lane);
+    }
+    if (has_nn) nn = __ldg(tasks + i + 2 * nwarps);
+
+    // ---- the task: len non-zeros starting at cur.x, first min(len, 32) pairs staged in (myc, myv) ----
+    const int len = static_cast<int>((cur.y >> 25) & 63u) + 1;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    int base = 0;
+    while (true) {
+      const int n = min(len - base, 32);
+      int j = 0;
+      for (; j + U <= n; j += U) gather_batch<T, VEC, U, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers);
+      switch (n - j) {                                   // warp-uniform: exact tails, no padding gathers
+        case 1: gather_batch<T, VEC, 1, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 2: gather_batch<T, VEC, 2, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 3: gather_batch<T, VEC, 3, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 4: if (U > 4) gather_batch<T, VEC, 4, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 5: if (U > 4) gather_batch<T, VEC, 5, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 6: if (U > 4) gather_batch<T, VEC, 6, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 7: if (U > 4) gather_batch<T, VEC, 7, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        default: break;
+      }
+      base += 32;
+      if (base >= len) break;
+      myc = 0; myv = 0.f;                                // tasks of 33..64 non-zeros: second chunk
+      if (base + lane < len) {
+        myc = __ldg(colidx + cur.x + base + lane);
+        myv = __ldg(vals + cur.x + base + lane);
+      }
+    }
+
+    if (!(cur.y & 0x80000000u)) {
+      const unsigned row = cur.y & 0x01FFFFFFu;
+      if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
+      VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
+    } else {                                             // segment of a long row: ordered reduction by the last arrival
+      const int sgid = static_cast<int>(cur.y & 0x01FFFFFFu);
+      const int L = __ldg(seg_long + sgid);
+      float* dst = partial + static_cast<int64_t>(sgid) * H + c0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+      __threadfence();
+      __syncwarp();
+      int old = 0;
+      const int first = __ldg(long_seg_ptr + L), nseg = __ldg(long_seg_ptr + L + 1) - first;
+      if (lane == 0) old = atomicAdd(counters + L, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == nseg - 1) {
+        __threadfence();
+        const int row = __ldg(long_rows + L);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          const float* srcp = partial + static_cast<int64_t>(first + sgi) * H + c0;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(srcp + v);
+        }
+        if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
+        VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
+        if (lane == 0) counters[L] = 0;
+      }
+    }
+
+    if (!has_next) break;
+    cur = nxt; myc = nc; myv = nv;
+    nxt = nn; has_next = has_nn;
+    i += nwarps;
+  }
+}
+
+inline int tasks_mode() {       // experiments: GDA_SPMM_TASKS=0 keeps k_spmm_rows, =8 the 8-deep variant, =12 12 CTAs/SM
+  static const int m = [] { const char* e = std::getenv("GDA_SPMM_TASKS"); return e ? std::atoi(e) : 4; }();
+  return m;
+}
+
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
            const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
@@ -607,6 +763,28 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
     const int64_t cap = static_cast<int64_t>(kNumSMs) * GDA_ROWS_MIN_CTAS;
     if (blocks > cap) blocks = cap;
     const PeerTable pt = peers ? *peers : PeerTable{};
+    const int tm = tasks_mode();
+    if (c.tasks != nullptr && c.num_tasks > 0 && tm != 0) {
+      const int per_sm = tm == 8 ? GDA_TASKS_MIN_CTAS_WIDE : (tm == 12 ? 12 : GDA_TASKS_MIN_CTAS);
+      int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
+      if (tb > static_cast<int64_t>(kNumSMs) * per_sm) tb = static_cast<int64_t>(kNumSMs) * per_sm;
+#define GDA_TASKS_LAUNCH(UU, CC, E, P)                                                                     \
+      k_spmm_tasks<T, VEC, UU, CC, E, P><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(            \
+          c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters,      \
+          X, ldxb, Y, ldyb, H, epi, partial, pt)
+#define GDA_TASKS_LAUNCH_EP(UU, CC)                                                                        \
+      do {                                                                                                 \
+        if (peers) { if (has_epi) GDA_TASKS_LAUNCH(UU, CC, true, true); else GDA_TASKS_LAUNCH(UU, CC, false, true); } \
+        else { if (has_epi) GDA_TASKS_LAUNCH(UU, CC, true, false); else GDA_TASKS_LAUNCH(UU, CC, false, false); }   \
+      } while (0)
+      if (tm == 8) GDA_TASKS_LAUNCH_EP(8, GDA_TASKS_MIN_CTAS_WIDE);
+      else if (tm == 12) GDA_TASKS_LAUNCH_EP(4, 12);
+      else GDA_TASKS_LAUNCH_EP(4, GDA_TASKS_MIN_CTAS);
+#undef GDA_TASKS_LAUNCH_EP
+#undef GDA_TASKS_LAUNCH
+      GDA_LAUNCH_CHECK();
+      return GDA_OK;
+    }
 #define GDA_ROWS_LAUNCH(E, P)                                                                              \
     k_spmm_rows<T, VEC, E, P><<<static_cast<unsigned>(blocks), GDA_ROWS_BLOCK, 0, st>>>(                  \
         c.rowptr, c.colidx, c.vals, c.num_segs, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, seg, \

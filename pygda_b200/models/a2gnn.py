@@ -33,6 +33,8 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         self.mode = mode
         self.overlap_streams = True
         self._side = None
+        # opt-in: capture the full-batch node-level step as a CUDA graph (models/graphed.py)
+        self.cuda_graph = False
 
     def _side_stream(self):
         if self._side is None:
@@ -115,6 +117,8 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         self.a2gnn = self.init_model(**self.kwargs)
         optimizer = Adam(self.a2gnn.parameters(), lr=self.lr, weight_decay=self.weight_decay)
         self.optimizer = optimizer
+        if self.cuda_graph and self.mode == 'node' and self.epoch > 1:
+            return self._fit_graphed(optimizer)
 
         def step(epoch, sampled_source_data, sampled_target_data):
             alpha = self.alpha_at(epoch, self.epoch)
@@ -123,6 +127,31 @@ class A2GNN(TwoDomainLoop, BaseGDA):
             return loss, source_logits, sampled_source_data
 
         self._fit_loop(step)
+
+    def _fit_graphed(self, optimizer):
+        """fit() with the loop body replayed from a CUDA graph: epoch 0 runs eagerly (and warms the
+        caches), epochs 1.. are replays.  Logging as in _fit_loop."""
+        import time
+        from ..metrics import eval_micro_f1
+        from ..utils import logger
+        from .graphed import GraphedStep
+        start_time = time.time()
+        source_batch = next(iter(self.source_loader))
+        target_batch = next(iter(self.target_loader))
+        step = GraphedStep(self, source_batch, target_batch, optimizer, warmup=1,
+                           alpha_fn=lambda i: self.alpha_at(i, self.epoch))
+        self.graphed_step = step
+        for epoch in range(self.epoch):
+            if epoch == 0:
+                loss, source_logits, _ = step.warmup_results[0]
+            else:
+                loss, source_logits, _ = step(self.alpha_at(epoch, self.epoch))
+            epoch_loss = loss.item()
+            micro_f1_score = None
+            if self.verbose > 1:
+                micro_f1_score = eval_micro_f1(step.src.y, source_logits.argmax(dim=1))
+            logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
+                   time=time.time() - start_time, verbose=self.verbose, train=True)
 
     def process_graph(self, data):
         pass

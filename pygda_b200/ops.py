@@ -386,6 +386,11 @@ class GradReverse(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if torch.is_tensor(ctx.alpha):          # device scalar: a captured CUDA graph reads the current value
+            g = _f32c(g)
+            out = torch.empty_like(g)
+            gda.scale_dev_f32(_p(out), _p(g), g.numel(), -1.0, _p(ctx.alpha), _stream())
+            return out, None
         return scale(g, -float(ctx.alpha)), None
 
 

@@ -42,6 +42,26 @@ def to_device_async(idx, device):
     return out
 
 
+def stage_into(dst, idx):
+    """Copy a CPU index tensor into the pre-allocated device tensor ``dst`` through the pinned ring
+    (used by the CUDA-graph step, whose kernels read the indices from a fixed address)."""
+    key = (tuple(idx.shape), idx.dtype, str(dst.device))
+    ring = _pinned.get(key)
+    if ring is None:
+        ring = _pinned[key] = [[torch.empty(idx.shape, dtype=idx.dtype).pin_memory() for _ in range(4)], 0, []]
+    bufs, pos, events = ring
+    if len(events) == len(bufs):
+        events.pop(0).synchronize()
+    buf = bufs[pos]
+    ring[1] = (pos + 1) % len(bufs)
+    buf.copy_(idx)
+    dst.copy_(buf, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    events.append(ev)
+    return dst
+
+
 def MMD(source_feat, target_feat, sampling_num=1000, times=5, indices=None, kernel_mul=2.0,
         kernel_num=5):
     if indices is None:
