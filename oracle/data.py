@@ -40,8 +40,11 @@ class FullBatchNeighborLoader:
         self.data = data
         ei = data.edge_index
         order = torch.argsort(ei[1], stable=True)
+        # attributes PyG classifies as neither node- nor edge-level (e.g. TDSS's edge_index_smooth,
+        # pygda/models/tdss.py:503) are copied through unchanged by NeighborLoader's filter_data
+        extra = {k: v for k, v in data.__dict__.items() if k not in ("x", "edge_index", "y", "batch", "num_graphs")}
         self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
-                           batch=getattr(data, "batch", None))
+                           batch=getattr(data, "batch", None), **extra)
 
     def __iter__(self):
         yield self._batch

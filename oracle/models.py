@@ -74,6 +74,72 @@ class A2GNN:
             return self.a2gnn(data, self.s_pnums if source else self.t_pnums), data.y
 
 
+class TDSS(A2GNN):
+    """pygda/models/tdss.py:93-312 (ctor :168-214, forward_model :241-312, smoothness :314-383,
+    compute_laplacian_loss :385-449, TwoHopNeighbor :21-90).  SURVEY.md section 8(f) row 1."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, mode="node", smooth_mode="RW", num_layers=2, dropout=0.,
+                 act=F.relu, s_pnums=0, t_pnums=30, k=2, rw_len=4, alpha=0.001, beta=1e-4, weight_decay=0.005,
+                 adv=False, lr=0.01, epoch=200, device="cpu", **kwargs):
+        assert mode == "node", "TDSS only supports node-level tasks"                      # :205
+        assert adv == False, "TDSS does not support adversarial training"  # noqa: E712   # :206
+        super().__init__(in_dim, hid_dim, num_classes, mode=mode, num_layers=num_layers, dropout=dropout, act=act,
+                         s_pnums=s_pnums, t_pnums=t_pnums, adv=adv, weight=alpha, weight_decay=weight_decay, lr=lr,
+                         epoch=epoch, device=device, **kwargs)
+        self.smooth_mode, self.k, self.rw_len, self.alpha, self.beta = smooth_mode, k, rw_len, alpha, beta
+        self.rw_generator = None
+
+    @staticmethod
+    def two_hop(edge_index, num_nodes):
+        """TwoHopNeighbor.__call__ (:66-90) for ``edge_attr is None``."""
+        value = edge_index.new_ones((edge_index.size(1),), dtype=torch.float)
+        index, value = P.spspmm(edge_index, value, edge_index, value, num_nodes, num_nodes, num_nodes, True)   # :73
+        value.fill_(0)
+        index, value = P.remove_self_loops(index, value)                                  # :75
+        edge_index = torch.cat([edge_index, index], dim=1)                                # :77
+        out, _ = P.coalesce(edge_index, None, num_nodes)                                  # :79
+        return out
+
+    def smoothness(self, edge_index, edge_attr, num_nodes):                               # :314-383
+        if self.smooth_mode == "RW":
+            row, col = edge_index
+            start = torch.arange(num_nodes)
+            walk = P.random_walk(row, col, start, self.rw_len, generator=self.rw_generator)    # :370
+            adj = torch.zeros((num_nodes, num_nodes), dtype=torch.float)
+            adj[walk[start], start.unsqueeze(1)] = 1.0                                    # :372
+            return P.dense_to_sparse(adj)                                                 # :373
+        if self.k == 1:
+            return P.add_remaining_self_loops(edge_index, edge_attr)                      # :376
+        assert edge_attr is None, "oracle restates the edge_attr=None branch"
+        hop = edge_index
+        for _ in range(self.k - 1):                                                       # :381-382
+            hop = self.two_hop(hop, num_nodes)
+        return P.add_remaining_self_loops(hop, None, num_nodes=num_nodes)                 # :385
+
+    @staticmethod
+    def compute_laplacian_loss(features, edge_index):                                     # :385-449
+        edge_weight = torch.ones(edge_index.size(1))
+        row, col = edge_index
+        deg = torch.zeros(features.size(0)).scatter_add_(0, row, edge_weight)
+        dinv = deg.pow(-0.5)
+        dinv[torch.isinf(dinv)] = 0
+        diff = features[row] * dinv[row].view(-1, 1) - features[col] * dinv[col].view(-1, 1)
+        return ((diff).pow(2).sum(dim=1) * edge_weight).sum() / 2.
+
+    def forward_model(self, source_data, target_data, alpha):                             # :241-312
+        net = self.a2gnn
+        source_logits = net(source_data, self.s_pnums)
+        loss = F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y)
+        source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, None, self.s_pnums)
+        target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, None, self.t_pnums)
+        mmd_loss = M.MMD(source_features, target_features, indices=self.mmd_indices, sqdist=self.mmd_sqdist)
+        loss = loss + self.alpha * mmd_loss                                               # :300
+        laplacian_loss = self.compute_laplacian_loss(target_features, target_data.edge_index_smooth)   # :303
+        loss = loss + self.beta * laplacian_loss                                          # :304
+        target_logits = net(target_data, self.t_pnums)                                    # :306
+        return loss, source_logits, target_logits
+
+
 class UDAGCN:
     """pygda/models/udagcn.py:64-308 with ``ppmi=False`` (forward_model :131-201, loop body
     :277-293).  Note the encoder's dropout layers are always active (oracle/nn.py)."""

@@ -151,3 +151,69 @@ def dense_adj(edge_index, edge_weight, num_nodes, dtype=torch.float64):
     a = torch.zeros(num_nodes, num_nodes, dtype=dtype)
     a.index_put_((edge_index[1], edge_index[0]), edge_weight.to(dtype), accumulate=True)
     return a
+
+
+# ---------------------------------------------------------------------------------------------
+# Upstream ops behind TDSS's smoothness graph (pygda/models/tdss.py:66-90, 367-383); SURVEY 8(f).1
+def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce="sum"):
+    """PyG ``utils.coalesce`` (2.4): sort by (row, col), drop duplicate pairs (attributes summed).
+    Call sites: tdss.py:79, :84 -- called as ``coalesce(edge_index, None, N, N)``, i.e. with
+    ``reduce=N`` positionally, which upstream never reads when ``edge_attr`` is None."""
+    n = maybe_num_nodes(edge_index, num_nodes)
+    key = edge_index[0] * n + edge_index[1]
+    key_sorted, perm = torch.sort(key, stable=True)
+    uniq, inverse = torch.unique_consecutive(key_sorted, return_inverse=True)
+    out_index = torch.stack([uniq // n, uniq % n])
+    if edge_attr is None:
+        return out_index, None
+    attr = edge_attr[perm]
+    out_attr = torch.zeros((uniq.numel(),) + tuple(attr.shape[1:]), dtype=attr.dtype)
+    out_attr.index_add_(0, inverse, attr)
+    return out_index, out_attr
+
+
+def spspmm(index_a, value_a, index_b, value_b, m, k, n, coalesced=False):
+    """``torch_sparse.spspmm``: sparse (m x k) @ sparse (k x n) -> (index [2, nnz] sorted by (row, col),
+    value [nnz]).  Call site: tdss.py:73 (A @ A on the unit-weight adjacency; only the PATTERN of the
+    result is used -- the values are overwritten with zeros at :74)."""
+    import numpy as np
+    import scipy.sparse as sp
+    a = sp.csr_matrix((value_a.double().numpy(), (index_a[0].numpy(), index_a[1].numpy())), shape=(m, k))
+    b = sp.csr_matrix((value_b.double().numpy(), (index_b[0].numpy(), index_b[1].numpy())), shape=(k, n))
+    c = (a @ b).tocsr()
+    c.sum_duplicates()
+    c.sort_indices()
+    c = c.tocoo()
+    index = torch.from_numpy(np.stack([c.row, c.col]).astype(np.int64))
+    return index, torch.from_numpy(c.data).to(value_a.dtype)
+
+
+def dense_to_sparse(adj):
+    """PyG ``dense_to_sparse``: non-zero entries in row-major order.  Call site: tdss.py:373."""
+    index = adj.nonzero().t().contiguous()
+    return index, adj[index[0], index[1]]
+
+
+def random_walk(row, col, start, walk_length, generator=None):
+    """``torch_cluster.random_walk``: [len(start), walk_length + 1] node ids, each step moving to a
+    uniformly chosen out-neighbour (edges row -> col), staying put at nodes without one.
+    Call site: tdss.py:370.  The random stream of the upstream C++/CUDA sampler cannot be
+    reproduced; parity for the 'RW' smoothing mode is by construction rules only."""
+    n = int(max(int(row.max()) if row.numel() else -1, int(col.max()) if col.numel() else -1,
+                int(start.max()) if start.numel() else -1)) + 1
+    order = torch.argsort(row, stable=True)
+    col_sorted = col[order]
+    deg = torch.bincount(row, minlength=n)
+    ptr = torch.zeros(n + 1, dtype=torch.long)
+    ptr[1:] = torch.cumsum(deg, 0)
+    walk = [start.clone()]
+    cur = start.clone()
+    for _ in range(walk_length):
+        d = deg[cur]
+        r = torch.rand(cur.numel(), generator=generator)
+        pick = (r * d.clamp(min=1)).long().clamp(max=(d - 1).clamp(min=0))
+        nxt = torch.where(d > 0, col_sorted[(ptr[cur] + pick).clamp(max=max(col_sorted.numel() - 1, 0))], cur) \
+            if col_sorted.numel() else cur
+        walk.append(nxt)
+        cur = nxt
+    return torch.stack(walk, dim=1)

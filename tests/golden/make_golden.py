@@ -250,7 +250,63 @@ def main():
             "target_logits": t_logits.detach().clone(),
             "grads": {k: p.grad.clone() for k, p in nest.gnn.named_parameters() if p.grad is not None}}
 
+    # ---- TDSS (pygda/models/tdss.py): TwoHopNeighbor :21-90, smoothness :314-383, ---------------
+    # ---- compute_laplacian_loss :385-449, forward_model :241-312 ------------------------------
+    tsrc = small_graph(60, 200, 24, 4, seed=11)
+    ttgt = small_graph(50, 150, 24, 4, seed=12)
+    tblob = {"source": {"x": tsrc.x, "edge_index": tsrc.edge_index, "y": tsrc.y},
+             "target": {"x": ttgt.x, "edge_index": ttgt.edge_index, "y": ttgt.y}}
+    hop_in = ref.tdss.Data(edge_index=ttgt.edge_index, edge_attr=None)
+    hop_in.num_nodes = 50
+    tblob["two_hop"] = ref.tdss.TwoHopNeighbor()(hop_in).edge_index.clone()
+    smooth = {}
+    for kk in (1, 2, 3):
+        e = ref.tdss.TDSS(in_dim=24, hid_dim=16, num_classes=4, smooth_mode='K-hop', k=kk, device='cpu')
+        ei_s, _ = e.smoothness(ttgt.edge_index, None, 50)
+        smooth[kk] = ei_s.clone()
+    tblob["smooth_khop"] = smooth
+    torch.manual_seed(31)
+    e = ref.tdss.TDSS(in_dim=24, hid_dim=16, num_classes=4, smooth_mode='RW', rw_len=4, device='cpu')
+    torch.manual_seed(32)
+    walk = __import__("oracle.pyg_ops", fromlist=["random_walk"]).random_walk(
+        ttgt.edge_index[0], ttgt.edge_index[1], torch.arange(50), 4)
+    torch.manual_seed(32)
+    ei_rw, _ = e.smoothness(ttgt.edge_index, None, 50)
+    tblob["smooth_rw"] = {"walk": walk, "edge_index": ei_rw.clone(), "seed": 32}
+    feats = torch.randn(50, 16, requires_grad=True)
+    lap = e.compute_laplacian_loss(feats, smooth[2])
+    lap.backward()
+    tblob["laplacian"] = {"features": feats.detach().clone(), "edge_index": smooth[2], "loss": lap.detach().clone(),
+                          "grad": feats.grad.clone()}
+    torch.manual_seed(41)
+    hp = dict(in_dim=24, hid_dim=16, num_classes=4, mode='node', smooth_mode='K-hop', num_layers=2, dropout=0.0,
+              s_pnums=0, t_pnums=3, k=2, alpha=0.5, beta=0.05)
+    test_ = ref.tdss.TDSS(device='cpu', **hp)
+    test_.a2gnn = test_.init_model()
+    with torch.no_grad():
+        for p in test_.a2gnn.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    test_.a2gnn.train()
+    ttgt.edge_index_smooth = smooth[2]
+    state = {k: v.clone() for k, v in test_.a2gnn.state_dict().items()}
+    torch.manual_seed(78)
+    loss, s_logits, t_logits = test_.forward_model(tsrc, ttgt, 0.3)
+    test_.a2gnn.zero_grad()
+    loss.backward()
+    torch.manual_seed(78)
+    s_idx = torch.randint(60, (5, 1000))
+    t_idx = torch.randint(50, (5, 1000))
+    tblob.update({"hparams": hp, "alpha_grl": 0.3, "seed": 78, "state": state, "source_idx": s_idx, "target_idx": t_idx,
+                  "loss": loss.detach().clone(), "source_logits": s_logits.detach().clone(),
+                  "target_logits": t_logits.detach().clone(),
+                  "grads": {k: p.grad.clone() for k, p in test_.a2gnn.named_parameters()}})
+    out["tdss"] = tblob
+
+    only = sys.argv[1:]
     for name, blob in out.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
         torch.save(blob, os.path.join(HERE, name + ".pt"))
         print("wrote", name + ".pt", os.path.getsize(os.path.join(HERE, name + ".pt")), "bytes")
 

@@ -72,4 +72,5 @@ def load_reference():
     ns.gnn_base = imp("pygda.nn.gnn_base")
     pkg.nn.GNNBase = ns.gnn_base.GNNBase
     ns.gnn = imp("pygda.models.gnn")
+    ns.tdss = imp("pygda.models.tdss")
     return ns
