@@ -42,6 +42,7 @@ extern "C" {
 
 typedef void* gda_stream_t;      /* cudaStream_t */
 typedef struct gda_graph gda_graph_t;
+typedef struct gda_edges gda_edges_t;   /* device edge list produced by the library (TDSS smoothing graph) */
 
 int         gda_version(void);
 int         gda_sm_arch(void);   /* 100: built for sm_100a only */
@@ -245,6 +246,42 @@ int gda_gat_fwd(const gda_graph_t* g, const float* h, int C, const float* a_src,
 int gda_gat_bwd(const gda_graph_t* g, const float* h, int C, const float* a_src, const float* a_dst,
                 float negative_slope, const float* alpha, const float* gout, float* dh, float* da_src,
                 float* da_dst, float* scratch, gda_stream_t stream);
+
+/* ------------------------------------------------- TDSS smoothness --
+ * The smoothing graph `edge_index_smooth` that TDSS.fit builds once per target graph
+ * (pygda/models/tdss.py:503) and the Laplacian regulariser evaluated on it every step.
+ *
+ * gda_khop_create: TDSS.smoothness(smooth_mode='K-hop') (tdss.py:374-385) = (k-1) applications
+ *   of TwoHopNeighbor (tdss.py:66-90: spspmm(A, A) pattern, remove_self_loops, cat with the
+ *   input, coalesce) then add_remaining_self_loops.  Bit-exact: sorted distinct non-loop pairs,
+ *   then loops 0..N-1 (k = 1: the input's non-loop edges in their order, then the loops).
+ * gda_rw_create: smooth_mode='RW' (tdss.py:367-373): edge (v, i) for every node v on a uniform
+ *   random walk of `walk_length` steps from i (walks stay put at nodes without out-edges), in
+ *   row-major order, duplicates removed.  Own counter-based random stream (`seed`).
+ * The result is an opaque device edge list; its size is only known after the build, so the
+ * caller asks for it, allocates int64 [2, E] and exports.  Errors: GDA_E_INDEX for ids outside
+ * [0, N); GDA_E_INVALID when the number of 2-paths exceeds 2^31. */
+int gda_khop_create(const int64_t* edge_index, int64_t E, int64_t N, int k, gda_stream_t stream, gda_edges_t** out);
+int gda_rw_create(const int64_t* edge_index, int64_t E, int64_t N, int walk_length, uint64_t seed,
+                  gda_stream_t stream, gda_edges_t** out);
+int64_t gda_edges_size(const gda_edges_t* edges);
+int gda_edges_export(const gda_edges_t* edges, int64_t* edge_index_out /* [2, E] */, gda_stream_t stream);
+int gda_edges_destroy(gda_edges_t* edges);
+
+/* compute_laplacian_loss (tdss.py:385-449):  loss = 1/2 sum_e |f[row] d[row]^-1/2 - f[col] d[col]^-1/2|^2,
+ * d = scatter_add(ones, row).  Evaluated without the [E, H] edge tensors as
+ *   g = D^-1/2 f (gda_row_scale_rsqrt_f32),  u_in = A g, u_out = A^T g (gda_spmm_f32 on a graph built
+ *   with flags = 0 from edge_index_smooth),  r = (d_out + d_in) g - u_in - u_out,
+ *   loss = 1/2 sum_i g_i . r_i,  d loss / d f = D^-1/2 r   (gda_laplacian_finish_f32; fp64 reduction,
+ *   fixed order).  gda_graph_degrees: edge counts per node as floats (out = by source = the
+ *   reference's `deg`, in = by target). */
+int gda_graph_degrees(const gda_graph_t* g, float* out_deg, float* in_deg, gda_stream_t stream);
+int gda_row_scale_rsqrt_f32(const float* x, int64_t ldx, const float* deg, float* y, int64_t N, int H,
+                            gda_stream_t stream);
+int64_t gda_laplacian_workspace_bytes(void);
+int gda_laplacian_finish_f32(const float* g, const float* u_in, const float* u_out, const float* out_deg,
+                             const float* in_deg, int64_t N, int H, float* loss, float* df, void* workspace,
+                             int64_t workspace_bytes, gda_stream_t stream);
 
 /* ---------------------------------------------------------------- pooling --
  * global_mean_pool over a sorted `batch` vector given as CSR-style ptr

@@ -59,6 +59,15 @@ SIGNATURES = {
     "gda_mmd_bwd": (i32, [vp, i64, vp, i64, i32, vp, vp, i32, i32, vp, vp, i64, vp, i64, vp, i64, vp]),
     "gda_gat_fwd": (i32, [vp, vp, i32, vp, vp, f32, vp, vp, vp]),
     "gda_gat_bwd": (i32, [vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "gda_khop_create": (i32, [vp, i64, i64, i32, vp, C.POINTER(vp)]),
+    "gda_rw_create": (i32, [vp, i64, i64, i32, u64, vp, C.POINTER(vp)]),
+    "gda_edges_size": (i64, [vp]),
+    "gda_edges_export": (i32, [vp, vp, vp]),
+    "gda_edges_destroy": (i32, [vp]),
+    "gda_graph_degrees": (i32, [vp, vp, vp, vp]),
+    "gda_row_scale_rsqrt_f32": (i32, [vp, i64, vp, vp, i64, i32, vp]),
+    "gda_laplacian_workspace_bytes": (i64, []),
+    "gda_laplacian_finish_f32": (i32, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "gda_segment_mean_bwd": (i32, [vp, vp, i64, i32, vp, i64, vp]),
     "gda_adam_step": (i32, [i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp]),

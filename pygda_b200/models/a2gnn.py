@@ -90,10 +90,15 @@ class A2GNN(TwoDomainLoop, BaseGDA):
             loss = ops.combine([(train_loss, 1.0), (domain_loss, float(self.weight))])
         else:                                                                             # :207-209
             mmd_loss = MMD(source_features, target_features, indices=mmd_indices)
-            loss = ops.combine([(train_loss, 1.0), (mmd_loss, float(self.weight))])
+            loss = ops.combine([(train_loss, 1.0), (mmd_loss, float(self.weight))] +
+                               self._extra_loss_terms(target_features, target_data))
 
         target_logits = net(target_data, self.t_pnums, first_layer=t1)                    # :211
         return loss, source_logits, target_logits
+
+    def _extra_loss_terms(self, target_features, target_data):
+        """[(scalar tensor, weight), ...] added to the MMD objective by subclasses (TDSS)."""
+        return []
 
     @staticmethod
     def alpha_at(epoch, total):
