@@ -120,6 +120,14 @@ __global__ void k_norm_coo(const int* __restrict__ src, const int* __restrict__ 
   w[p] = (dinv[src[p]] * w[p]) * dinv[dst[p]];
 }
 
+// smallest row length of a CSR: rows are all non-empty iff it is >= 1
+__global__ void k_min_degree(const int* __restrict__ rowptr, int64_t N, int* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int d = rowptr[i + 1] - rowptr[i];
+  if (d == 0) atomicMin(out, 0);
+}
+
 __global__ void k_long_flags(const int* __restrict__ rowptr, int64_t N, int seg, int* __restrict__ is_long,
                              int* __restrict__ nsegs) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -390,6 +398,22 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
   }
 
   g->csr.may_have_empty_rows = g->csr_t.may_have_empty_rows = !loops;   // a self loop in every row
+  if (!loops && N > 0) {
+    // graphs given with their loops already in place (TDSS's smoothing graph, tdss.py:376-385) have no empty
+    // row either: look, so that they take the lean aggregation kernels as well
+    int* mins; if ((rc = sc.get(&mins, 2))) return rc;
+    int ones[2] = {1, 1};
+    GDA_CUDA(cudaMemcpyAsync(mins, ones, sizeof(ones), cudaMemcpyHostToDevice, st));
+    k_min_degree<<<blocks_for(N), kThreads, 0, st>>>(g->csr.rowptr, N, mins);
+    GDA_LAUNCH_CHECK();
+    k_min_degree<<<blocks_for(N), kThreads, 0, st>>>(g->csr_t.rowptr, N, mins + 1);
+    GDA_LAUNCH_CHECK();
+    int h_min[2] = {0, 0};
+    GDA_CUDA(cudaMemcpyAsync(h_min, mins, sizeof(h_min), cudaMemcpyDeviceToHost, st));
+    GDA_CUDA(cudaStreamSynchronize(st));
+    g->csr.may_have_empty_rows = h_min[0] == 0;
+    g->csr_t.may_have_empty_rows = h_min[1] == 0;
+  }
   // 5. long-row segments for both orientations
   if ((rc = build_long_rows(g->csr, N, g->seg, sc, st))) return rc;
   if ((rc = build_long_rows(g->csr_t, N, g->seg, sc, st))) return rc;
