@@ -110,6 +110,20 @@ int gda_spmm_k_f32(const gda_graph_t* g, int transpose, int k, const float* X, i
                    int64_t ldy, float* T0, float* T1, int H, const float* bias, int epi_flags,
                    float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
                    int64_t workspace_bytes, gda_stream_t stream);
+/* The same over nb feature matrices that share the graph: matrix b is X + b*x_batch_stride ->
+ * Y + b*y_batch_stride (elements).  Used for the repeated bottleneck evaluations of one domain per
+ * step (pygda/models/a2gnn.py:192-193 and :181/:211 run feat_bottleneck twice on the same graph with
+ * fresh dropout masks): one (colidx, weight) read and one dependency chain per row serve nb gathers.
+ * The dropout mask of matrix b is that of rows [b*N, (b+1)*N) of the stacked [nb*N, H] matrix;
+ * workspace: gda_spmm_workspace_bytes(g, transpose, H * nb). */
+int gda_spmm_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* X, int64_t ldx,
+                    int64_t x_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int H,
+                    const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                    const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+int gda_spmm_k_nb_f32(const gda_graph_t* g, int transpose, int k, int nb, const float* X, int64_t ldx,
+                      int64_t x_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, float* T0, float* T1,
+                      int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                      const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream);
 /* bf16 features, fp32 edge weights and accumulation (BASELINE config 3) */
 int gda_spmm_bf16(const gda_graph_t* g, int transpose, const void* X, int64_t ldx,
                   void* Y, int64_t ldy, int H, const float* bias, int epi_flags,
@@ -193,6 +207,17 @@ int gda_bias_act_dropout_fwd(const float* x, const float* bias, float* y, int64_
 int gda_bias_act_dropout_bwd(const float* gy, const float* y, float* gx, float* gbias,
                              int64_t rows, int64_t cols, int act, float dropout_p,
                              uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream);
+/* `rep` independent dropout masks over ONE input: y [rep*rows, cols] stacked, copy r = dropout_r(act(x + bias)),
+ * mask index r*rows*cols + element.  The reference evaluates feat_bottleneck twice per domain and step on the same
+ * graph (a2gnn.py:181/192, 193/211); layer 1 is shared (dropout acts after it, a2gnn_base.py:136-138) and fans
+ * out here.  Backward: gy0 / gy1 = gradient of copy 0 / 1 (NULL: none arrived), y = the stacked forward output;
+ * sum = 1: gx [rows, cols] = sum of the masked copies; sum = 0: gx [rep*rows, cols] stacked (gbias over all rows). */
+int gda_bias_act_dropout_rep_fwd(const float* x, const float* bias, float* y, int64_t rows, int64_t cols, int rep,
+                                 int act, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                                 gda_stream_t stream);
+int gda_bias_act_dropout_rep_bwd(const float* gy0, const float* gy1, const float* y, float* gx, float* gbias,
+                                 int64_t rows, int64_t cols, int rep, int sum, int act, float dropout_p,
+                                 uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream);
 /* column sums: out[cols] = sum_r x[r, :]   (bias gradients) */
 int gda_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out,
                    gda_stream_t stream);

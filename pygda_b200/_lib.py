@@ -33,6 +33,9 @@ SIGNATURES = {
     "gda_spmm_workspace_bytes": (i64, [vp, i32, i32]),
     "gda_spmm_f32": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_k_f32": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_nb_f32": (i32, [vp, i32, i32, vp, i64, i64, vp, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_k_nb_f32": (i32, [vp, i32, i32, i32, vp, i64, i64, vp, i64, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp,
+                                i64, vp]),
     "gda_spmm_peer_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
                                   vp, u64, vp, vp]),
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
@@ -51,6 +54,8 @@ SIGNATURES = {
     "gda_gemm_bf16x3": (i32, [i32, i32, i64, i64, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
     "gda_bias_act_dropout_fwd": (i32, [vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_bwd": (i32, [vp, vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
+    "gda_bias_act_dropout_rep_fwd": (i32, [vp, vp, vp, i64, i64, i32, i32, f32, u64, vp, vp]),
+    "gda_bias_act_dropout_rep_bwd": (i32, [vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, f32, u64, vp, vp]),
     "gda_colsum_f32": (i32, [vp, i64, i64, i64, vp, vp]),
     "gda_softmax_ce_fwd_bwd": (i32, [vp, i64, i32, i64, vp, i64, vp, vp, vp]),
     "gda_softmax_entropy_fwd_bwd": (i32, [vp, i64, i32, i64, vp, vp, vp]),

@@ -16,31 +16,101 @@ inline unsigned grid_for(int64_t n, int per_thread = 1) {
   return static_cast<unsigned>(b < cap ? b : cap);
 }
 
-__global__ void k_bias_act_dropout_fwd(const float* __restrict__ x, const float* __restrict__ bias,
-                                       float* __restrict__ y, int64_t n, int cols, int act, uint32_t thresh,
-                                       float scale, uint64_t seed, const uint64_t* __restrict__ seed_offset,
-                                       int do_drop) {
+// y_r = dropout_r(act(x + bias)) for r < rep: x [n_in] is read once, y is the stacked [rep * n_in] output and the
+// keep mask of element e of copy r is hash(seed, r * n_in + e) -- `rep` independent masks over one input
+// (the two bottleneck evaluations per domain share layer 1: pygda/models/a2gnn.py:181/192, 193/211).
+// V = 4: 16-byte accesses (cols % 4 == 0, aligned pointers); V = 1: any shape.
+template <int V>
+__global__ void k_bias_act_dropout_fwd(const float* x /* may alias y when rep == 1 */, const float* __restrict__ bias,
+                                       float* y, int64_t n_in, int cols, int rep, int act,
+                                       uint32_t thresh, float scale, uint64_t seed,
+                                       const uint64_t* __restrict__ seed_offset, int do_drop) {
   if (do_drop && seed_offset) seed += __ldg(seed_offset);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = x[i];
-    if (bias) v += __ldg(bias + (i % cols));
-    if (act == 1) v = fmaxf(v, 0.f);
-    if (do_drop) v = dropout_keep(seed, static_cast<uint64_t>(i), thresh) ? v * scale : 0.f;
-    y[i] = v;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V;
+  unsigned col = static_cast<unsigned>(i % cols);
+  const unsigned step = static_cast<unsigned>(stride % cols);
+  for (; i < n_in; i += stride) {
+    float v[V];
+    if (V == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(x + i);
+      v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+    } else {
+      v[0] = x[i];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (bias) v[j] += __ldg(bias + col + j);
+      if (act == 1) v[j] = fmaxf(v[j], 0.f);
+    }
+    for (int r = 0; r < rep; ++r) {
+      const int64_t o = r * n_in + i;
+      float w[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        w[j] = do_drop ? (dropout_keep(seed, static_cast<uint64_t>(o + j), thresh) ? v[j] * scale : 0.f) : v[j];
+      if (V == 4) *reinterpret_cast<float4*>(y + o) = make_float4(w[0], w[1 % V], w[2 % V], w[3 % V]);
+      else y[o] = w[0];
+    }
+    col += step;
+    if (col >= static_cast<unsigned>(cols)) col -= cols;
   }
 }
 
-__global__ void k_bias_act_dropout_bwd(const float* __restrict__ gy, const float* __restrict__ y,
-                                       float* __restrict__ gx, int64_t n, int act, uint32_t thresh, float scale,
-                                       uint64_t seed, const uint64_t* __restrict__ seed_offset, int do_drop) {
+// backward of the above.  gy_r = gy0 / gy1 (NULL = no gradient reached that copy); y is the stacked output.
+// sum = 1: gx [n_in] = sum_r mask_r(gy_r) (one input, rep outputs); sum = 0: gx stacked [rep * n_in].
+template <int V>
+__global__ void k_bias_act_dropout_bwd(const float* __restrict__ gy0, const float* __restrict__ gy1,
+                                       const float* __restrict__ y, float* __restrict__ gx, int64_t n_in, int rep,
+                                       int sum, int act, uint32_t thresh, float scale, uint64_t seed,
+                                       const uint64_t* __restrict__ seed_offset, int do_drop) {
   if (do_drop && seed_offset) seed += __ldg(seed_offset);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float g = gy[i];
-    if (do_drop) g = dropout_keep(seed, static_cast<uint64_t>(i), thresh) ? g * scale : 0.f;
-    if (act == 1 && !(y[i] > 0.f)) g = 0.f;      // relu'(0) = 0, like torch
-    gx[i] = g;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * V;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * V; i < n_in; i += stride) {
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int r = 0; r < rep; ++r) {
+      const float* __restrict__ gy = r == 0 ? gy0 : gy1;
+      const int64_t o = r * n_in + i;
+      float g[V], yo[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { g[j] = 0.f; yo[j] = 1.f; }
+      if (gy) {
+        if (V == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(gy + i);
+          g[0] = t.x; g[1 % V] = t.y; g[2 % V] = t.z; g[3 % V] = t.w;
+          if (act == 1) {
+            const float4 u = *reinterpret_cast<const float4*>(y + o);
+            yo[0] = u.x; yo[1 % V] = u.y; yo[2 % V] = u.z; yo[3 % V] = u.w;
+          }
+        } else {
+          g[0] = gy[i];
+          if (act == 1) yo[0] = y[o];
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (do_drop) g[j] = dropout_keep(seed, static_cast<uint64_t>(o + j), thresh) ? g[j] * scale : 0.f;
+          if (act == 1 && !(yo[j] > 0.f)) g[j] = 0.f;      // relu'(0) = 0, like torch
+        }
+      }
+      if (sum) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += g[j];
+      } else if (V == 4) {
+        *reinterpret_cast<float4*>(gx + o) = make_float4(g[0], g[1 % V], g[2 % V], g[3 % V]);
+      } else {
+        gx[o] = g[0];
+      }
+    }
+    if (sum) {
+      if (V == 4) *reinterpret_cast<float4*>(gx + i) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+      else gx[i] = acc[0];
+    }
   }
 }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // out[c] += sum over this block's row range; out pre-zeroed
 __global__ void k_colsum(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, float* __restrict__ out,
@@ -233,19 +303,34 @@ using namespace gda;
 
 extern "C" {
 
-int gda_bias_act_dropout_fwd(const float* x, const float* bias, float* y, int64_t rows, int64_t cols, int act,
-                             float dropout_p, uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream) {
+int gda_bias_act_dropout_rep_fwd(const float* x, const float* bias, float* y, int64_t rows, int64_t cols, int rep,
+                                 int act, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                                 gda_stream_t stream) {
   GDA_REQUIRE(rows >= 0 && cols >= 0, "gda_bias_act_dropout_fwd: negative size");
+  GDA_REQUIRE(rep >= 1, "gda_bias_act_dropout_fwd: rep must be >= 1");
   const int64_t n = rows * cols;
   if (n == 0) return GDA_OK;
   GDA_REQUIRE(x && y, "gda_bias_act_dropout_fwd: NULL pointer");
+  GDA_REQUIRE(cols < (int64_t(1) << 31), "gda_bias_act_dropout_fwd: too many columns");
+  GDA_REQUIRE(rep == 1 || x != y, "gda_bias_act_dropout_fwd: in-place needs rep == 1");
   GDA_REQUIRE(act == 0 || act == 1, "gda_bias_act_dropout_fwd: act must be 0 (none) or 1 (relu)");
   GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_bias_act_dropout_fwd: dropout_p outside [0,1)");
-  k_bias_act_dropout_fwd<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(
-      x, bias, y, n, static_cast<int>(cols), act, dropout_threshold(dropout_p), 1.f / (1.f - dropout_p), seed,
-      seed_offset, dropout_p > 0.f ? 1 : 0);
+  const uint32_t th = dropout_threshold(dropout_p);
+  const float sc = 1.f / (1.f - dropout_p);
+  const int drop = dropout_p > 0.f ? 1 : 0;
+  if (cols % 4 == 0 && aligned16(x) && aligned16(y))
+    k_bias_act_dropout_fwd<4><<<grid_for(n, 8), kThreads, 0, as_stream(stream)>>>(
+        x, bias, y, n, static_cast<int>(cols), rep, act, th, sc, seed, seed_offset, drop);
+  else
+    k_bias_act_dropout_fwd<1><<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(
+        x, bias, y, n, static_cast<int>(cols), rep, act, th, sc, seed, seed_offset, drop);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
+}
+
+int gda_bias_act_dropout_fwd(const float* x, const float* bias, float* y, int64_t rows, int64_t cols, int act,
+                             float dropout_p, uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream) {
+  return gda_bias_act_dropout_rep_fwd(x, bias, y, rows, cols, 1, act, dropout_p, seed, seed_offset, stream);
 }
 
 int gda_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* out, gda_stream_t stream) {
@@ -265,21 +350,35 @@ int gda_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ldx, floa
   return GDA_OK;
 }
 
+int gda_bias_act_dropout_rep_bwd(const float* gy0, const float* gy1, const float* y, float* gx, float* gbias,
+                                 int64_t rows, int64_t cols, int rep, int sum, int act, float dropout_p, uint64_t seed,
+                                 const uint64_t* seed_offset, gda_stream_t stream) {
+  GDA_REQUIRE(rows >= 0 && cols >= 0, "gda_bias_act_dropout_bwd: negative size");
+  GDA_REQUIRE(rep == 1 || rep == 2, "gda_bias_act_dropout_bwd: rep must be 1 or 2");
+  const int64_t n = rows * cols;
+  if (n > 0) {
+    GDA_REQUIRE((gy0 || (rep == 2 && gy1)) && gx, "gda_bias_act_dropout_bwd: NULL pointer");
+    GDA_REQUIRE(act == 0 || (act == 1 && y), "gda_bias_act_dropout_bwd: act must be 0 or 1 (1 needs y)");
+    const uint32_t th = dropout_threshold(dropout_p);
+    const float sc = 1.f / (1.f - dropout_p);
+    const int drop = dropout_p > 0.f ? 1 : 0;
+    if (cols % 4 == 0 && aligned16(gy0) && aligned16(gy1) && aligned16(y) && aligned16(gx))
+      k_bias_act_dropout_bwd<4><<<grid_for(n, 8), kThreads, 0, as_stream(stream)>>>(gy0, gy1, y, gx, n, rep, sum, act, th,
+                                                                                    sc, seed, seed_offset, drop);
+    else
+      k_bias_act_dropout_bwd<1><<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(gy0, gy1, y, gx, n, rep, sum, act, th,
+                                                                                    sc, seed, seed_offset, drop);
+    GDA_LAUNCH_CHECK();
+  }
+  if (gbias) return gda_colsum_f32(gx, (sum ? 1 : rep) * rows, cols, cols, gbias, stream);
+  return GDA_OK;
+}
+
 int gda_bias_act_dropout_bwd(const float* gy, const float* y, float* gx, float* gbias, int64_t rows, int64_t cols,
                              int act, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                              gda_stream_t stream) {
-  GDA_REQUIRE(rows >= 0 && cols >= 0, "gda_bias_act_dropout_bwd: negative size");
-  const int64_t n = rows * cols;
-  if (n > 0) {
-    GDA_REQUIRE(gy && y && gx, "gda_bias_act_dropout_bwd: NULL pointer");
-    GDA_REQUIRE(act == 0 || act == 1, "gda_bias_act_dropout_bwd: act must be 0 or 1");
-    k_bias_act_dropout_bwd<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(
-        gy, y, gx, n, act, dropout_threshold(dropout_p), 1.f / (1.f - dropout_p), seed, seed_offset,
-        dropout_p > 0.f ? 1 : 0);
-    GDA_LAUNCH_CHECK();
-  }
-  if (gbias) return gda_colsum_f32(gx, rows, cols, cols, gbias, stream);
-  return GDA_OK;
+  return gda_bias_act_dropout_rep_bwd(gy, nullptr, y, gx, gbias, rows, cols, 1, 0, act, dropout_p, seed, seed_offset,
+                                      stream);
 }
 
 int gda_softmax_ce_fwd_bwd(const float* logits, int64_t rows, int C, int64_t ld, const int64_t* labels,

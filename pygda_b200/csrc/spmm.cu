@@ -608,12 +608,12 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
 //    2 + ceil(len / U).  Indices and weights reach the lanes by shuffle.
 // The summation order inside a row is unchanged (sequential in CSR = COO order, segments reduced
 // in segment order), so results are bit-identical to k_spmm_rows.
-template <typename T, int VEC, int K, bool PEER>
-__device__ __forceinline__ void gather_batch(float (&acc)[VEC], int myc, float myv, int j, const char* __restrict__ Xc,
-                                             unsigned ldxb, int c0, const PeerTable& peers) {
+template <typename T, int VEC, int K, bool PEER, int NB>
+__device__ __forceinline__ void gather_batch(float (&acc)[NB][VEC], int myc, float myv, int j, const char* __restrict__ Xc,
+                                             unsigned ldxb, uint64_t xbsb, int c0, const PeerTable& peers) {
   unsigned cj[K];
   float wv[K];
-  float xv[K][VEC];
+  float xv[K][NB][VEC];
 #pragma unroll
   for (int u = 0; u < K; ++u) {
     cj[u] = static_cast<unsigned>(__shfl_sync(0xffffffffu, myc, j + u));
@@ -624,21 +624,27 @@ __device__ __forceinline__ void gather_batch(float (&acc)[VEC], int myc, float m
     const char* src = PEER ? static_cast<const char*>(peers.p[cj[u] >> 28]) + c0 * sizeof(T) +
                                  static_cast<uint64_t>(cj[u] & 0x0FFFFFFFu) * ldxb
                            : Xc + static_cast<uint64_t>(cj[u]) * ldxb;
-    VecIO<T, VEC>::load(reinterpret_cast<const T*>(src), xv[u]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) VecIO<T, VEC>::load(reinterpret_cast<const T*>(src + b * xbsb), xv[u][b]);
   }
 #pragma unroll
   for (int u = 0; u < K; ++u)
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wv[u], xv[u][v], acc[v]);
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[b][v] = fmaf(wv[u], xv[u][b][v], acc[b][v]);
 }
 
-template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER>
+// NB > 1: NB feature matrices (xbsb / ybsb bytes apart, `nrows` rows each) share the graph -- one index read and one
+// dependency chain per row for NB gathers (the two bottleneck evaluations of a domain, models/a2gnn.py).
+template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER, int NB>
 __global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
 k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
              const float* __restrict__ vals, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
              const int* __restrict__ seg_long, int* __restrict__ counters,
              const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int H,
-             Epilogue epi, float* __restrict__ partial, PeerTable peers) {
+             Epilogue epi, float* __restrict__ partial, PeerTable peers, uint64_t xbsb, uint64_t ybsb, int nrows) {
+  static_assert(NB == 1 || !PEER, "batched form is local only");
   static_assert(U == 4 || U == 8, "batch depth");
   const int lane = threadIdx.x & 31;
   const int c0 = lane * VEC;
@@ -672,22 +678,24 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
 
     // ---- the task: len non-zeros starting at cur.x, first min(len, 32) pairs staged in (myc, myv) ----
     const int len = static_cast<int>((cur.y >> 25) & 63u) + 1;
-    float acc[VEC];
+    float acc[NB][VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[b][v] = 0.f;
     int base = 0;
     while (true) {
       const int n = min(len - base, 32);
       int j = 0;
-      for (; j + U <= n; j += U) gather_batch<T, VEC, U, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers);
+      for (; j + U <= n; j += U) gather_batch<T, VEC, U, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers);
       switch (n - j) {                                   // warp-uniform: exact tails, no padding gathers
-        case 1: gather_batch<T, VEC, 1, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 2: gather_batch<T, VEC, 2, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 3: gather_batch<T, VEC, 3, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 4: if (U > 4) gather_batch<T, VEC, 4, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 5: if (U > 4) gather_batch<T, VEC, 5, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 6: if (U > 4) gather_batch<T, VEC, 6, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
-        case 7: if (U > 4) gather_batch<T, VEC, 7, PEER>(acc, myc, myv, j, Xc, ldxb, c0, peers); break;
+        case 1: gather_batch<T, VEC, 1, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 2: gather_batch<T, VEC, 2, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 3: gather_batch<T, VEC, 3, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 4: if (U > 4) gather_batch<T, VEC, 4, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 5: if (U > 4) gather_batch<T, VEC, 5, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 6: if (U > 4) gather_batch<T, VEC, 6, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
+        case 7: if (U > 4) gather_batch<T, VEC, 7, PEER, NB>(acc, myc, myv, j, Xc, ldxb, xbsb, c0, peers); break;
         default: break;
       }
       base += 32;
@@ -701,14 +709,19 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
 
     if (!(cur.y & 0x80000000u)) {
       const unsigned row = cur.y & 0x01FFFFFFu;
-      if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
-      VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (EPI) apply_epilogue<VEC>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
+        VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+      }
     } else {                                             // segment of a long row: ordered reduction by the last arrival
       const int sgid = static_cast<int>(cur.y & 0x01FFFFFFu);
       const int L = __ldg(seg_long + sgid);
-      float* dst = partial + static_cast<int64_t>(sgid) * H + c0;
+      float* dst = partial + static_cast<int64_t>(sgid) * (NB * H) + c0;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) __stcg(dst + v, acc[v]);
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) __stcg(dst + b * H + v, acc[b][v]);
       __threadfence();
       __syncwarp();
       int old = 0;
@@ -719,14 +732,17 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
         __threadfence();
         const int row = __ldg(long_rows + L);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-        for (int sgi = 0; sgi < nseg; ++sgi) {
-          const float* srcp = partial + static_cast<int64_t>(first + sgi) * H + c0;
+        for (int b = 0; b < NB; ++b) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] += __ldcg(srcp + v);
+          for (int v = 0; v < VEC; ++v) acc[b][v] = 0.f;
+          for (int sgi = 0; sgi < nseg; ++sgi) {
+            const float* srcp = partial + static_cast<int64_t>(first + sgi) * (NB * H) + b * H + c0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[b][v] += __ldcg(srcp + v);
+          }
+          if (EPI) apply_epilogue<VEC>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
+          VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
         }
-        if (EPI) apply_epilogue<VEC>(acc, epi, row, c0, H);
-        VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + static_cast<uint64_t>(row) * ldyb), acc);
         if (lane == 0) counters[L] = 0;
       }
     }
@@ -745,7 +761,8 @@ inline int tasks_mode() {       // experiments: GDA_SPMM_TASKS=0 keeps k_spmm_ro
 
 template <typename T, int VEC, int LPR, int U>
 int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-           const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
+           const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0,
+           int nb = 1, int64_t xbs = 0, int64_t ybs = 0) {
   constexpr int RPG = RowsPerGroup<LPR>::value;
   const int64_t groups = static_cast<int64_t>(c.num_segs) + ceil_div(N, RPG);
   const bool generic = c.may_have_empty_rows || generic_forced();
@@ -768,10 +785,25 @@ int launch(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, in
       const int per_sm = tm == 8 ? GDA_TASKS_MIN_CTAS_WIDE : (tm == 12 ? 12 : GDA_TASKS_MIN_CTAS);
       int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
       if (tb > static_cast<int64_t>(kNumSMs) * per_sm) tb = static_cast<int64_t>(kNumSMs) * per_sm;
+      if (nb == 2) {                                     // two matrices per index read (never on the peer path)
+        int64_t tb2 = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
+        if (tb2 > static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS_WIDE) tb2 = static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS_WIDE;
+        const uint64_t xb = static_cast<uint64_t>(xbs) * sizeof(T), yb = static_cast<uint64_t>(ybs) * sizeof(T);
+        if (has_epi)
+          k_spmm_tasks<T, VEC, 4, GDA_TASKS_MIN_CTAS_WIDE, true, false, 2><<<static_cast<unsigned>(tb2), GDA_ROWS_BLOCK, 0, st>>>(
+              c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y,
+              ldyb, H, epi, partial, pt, xb, yb, static_cast<int>(N));
+        else
+          k_spmm_tasks<T, VEC, 4, GDA_TASKS_MIN_CTAS_WIDE, false, false, 2><<<static_cast<unsigned>(tb2), GDA_ROWS_BLOCK, 0, st>>>(
+              c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y,
+              ldyb, H, epi, partial, pt, xb, yb, static_cast<int>(N));
+        GDA_LAUNCH_CHECK();
+        return GDA_OK;
+      }
 #define GDA_TASKS_LAUNCH(UU, CC, E, P)                                                                     \
-      k_spmm_tasks<T, VEC, UU, CC, E, P><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(            \
+      k_spmm_tasks<T, VEC, UU, CC, E, P, 1><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(         \
           c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters,      \
-          X, ldxb, Y, ldyb, H, epi, partial, pt)
+          X, ldxb, Y, ldyb, H, epi, partial, pt, 0, 0, static_cast<int>(N))
 #define GDA_TASKS_LAUNCH_EP(UU, CC)                                                                        \
       do {                                                                                                 \
         if (peers) { if (has_epi) GDA_TASKS_LAUNCH(UU, CC, true, true); else GDA_TASKS_LAUNCH(UU, CC, false, true); } \
@@ -825,7 +857,8 @@ inline int pow2_at_least(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <typename T, int VEC>
 int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t N, int H,
-                 const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0) {
+                 const Epilogue& epi, float* partial, cudaStream_t st, const PeerTable* peers = nullptr, int pad_col = 0,
+                 int nb = 1, int64_t xbs = 0, int64_t ybs = 0) {
   int lanes = pow2_at_least(static_cast<int>(ceil_div(H, VEC)));
   if (lanes > 32) lanes = 32;
   if (lanes < 4) lanes = 4;
@@ -834,18 +867,28 @@ int dispatch_lpr(const Csr& c, int seg, const T* X, int64_t ldx, T* Y, int64_t l
     case 4:  return launch<T, VEC, 4, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
     case 8:  return launch<T, VEC, 8, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
     case 16: return launch<T, VEC, 16, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
-    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col);
+    default: return launch<T, VEC, 32, U>(c, seg, X, ldx, Y, ldy, N, H, epi, partial, st, peers, pad_col, nb, xbs, ybs);
   }
 }
 
+// true when launch<> will take the work-list kernel (the only one with a batched form)
+template <typename T, int WIDE>
+bool tasks_path(const Csr& c, int H, bool wide_ok) {
+  return wide_ok && H == 32 * WIDE && WIDE * sizeof(T) == 16 && !c.may_have_empty_rows && !generic_forced() &&
+         !fast_forced() && c.tasks != nullptr && c.num_tasks > 0 && tasks_mode() != 0;
+}
+
+// nb feature matrices X + b*xbs -> Y + b*ybs (elements) over the same graph.  The dropout mask of matrix b is the one of
+// rows [b*N, (b+1)*N) of a stacked [nb*N, H] matrix.
 template <typename T, int WIDE>
 int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, int64_t ldy, int H,
              const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
              void* workspace, int64_t workspace_bytes, cudaStream_t st, const PeerTable* peers = nullptr,
-             int my_rank = 0) {
+             int my_rank = 0, int nb = 1, int64_t xbs = 0, int64_t ybs = 0) {
   GDA_REQUIRE(g != nullptr, "gda_spmm: graph is NULL");
   GDA_REQUIRE(g->peer_packed == (peers != nullptr), "gda_spmm: partitioned graphs need gda_spmm_peer_* (and only they)");
   GDA_REQUIRE(H > 0, "gda_spmm: H must be positive");
+  GDA_REQUIRE(nb >= 1 && (nb == 1 || !peers), "gda_spmm: nb must be >= 1 (and 1 on the peer path)");
   if (g->N == 0) return GDA_OK;
   GDA_REQUIRE((X || peers) && Y, "gda_spmm: NULL feature pointer");
   GDA_REQUIRE(X != Y, "gda_spmm: X and Y must not alias");
@@ -853,10 +896,8 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32),
               "gda_spmm: N * ld must be below 2^32 elements");
   GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm: dropout_p outside [0,1)");
+  GDA_REQUIRE(nb == 1 || (xbs >= g->N * ldx && ybs >= g->N * ldy), "gda_spmm: batch strides smaller than one matrix");
   const Csr& c = transpose ? g->csr_t : g->csr;
-  const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
-  if (need > 0 && (workspace == nullptr || workspace_bytes < need))
-    return fail(GDA_E_WORKSPACE, "gda_spmm: workspace smaller than gda_spmm_workspace_bytes()");
   Epilogue epi;
   epi.bias = bias;
   epi.flags = epi_flags;
@@ -867,11 +908,37 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   float* partial = static_cast<float*>(workspace);
   bool wide_ok = (H % WIDE == 0) && (ldx % WIDE == 0) && (ldy % WIDE == 0) &&
                  (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
+  if (nb > 1) wide_ok = wide_ok && (xbs % WIDE == 0) && (ybs % WIDE == 0);
   const int pad_col = peers ? (my_rank << 28) : 0;
   if (peers)
     for (int i = 0; i < GDA_MAX_PEERS; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(peers->p[i]) % 16 == 0);
-  if (wide_ok) return dispatch_lpr<T, WIDE>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
-  return dispatch_lpr<T, 1>(c, g->seg, X, ldx, Y, ldy, g->N, H, epi, partial, st, peers, pad_col);
+  // pairs of matrices go through the batched work-list kernel; anything else one matrix at a time
+  int b = 0;
+  if (nb >= 2 && tasks_path<T, WIDE>(c, H, wide_ok)) {
+    const int64_t need2 = static_cast<int64_t>(c.num_segs) * H * 2 * sizeof(float);
+    if (need2 > 0 && (workspace == nullptr || workspace_bytes < need2))
+      return fail(GDA_E_WORKSPACE, "gda_spmm: workspace smaller than gda_spmm_workspace_bytes(H * nb)");
+    for (; b + 2 <= nb; b += 2) {
+      Epilogue e2 = epi;
+      e2.seed = seed + static_cast<uint64_t>(b) * static_cast<uint64_t>(g->N) * static_cast<uint64_t>(H) * 0x9E3779B97F4A7C15ull;
+      int rc = dispatch_lpr<T, WIDE>(c, g->seg, X + b * xbs, ldx, Y + b * ybs, ldy, g->N, H, e2, partial, st, nullptr, 0,
+                                     2, xbs, ybs);
+      if (rc) return rc;
+    }
+  }
+  const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
+  if (b < nb && need > 0 && (workspace == nullptr || workspace_bytes < need))
+    return fail(GDA_E_WORKSPACE, "gda_spmm: workspace smaller than gda_spmm_workspace_bytes()");
+  for (; b < nb; ++b) {
+    Epilogue e1 = epi;        // mask index (b*N + row)*H + col == hash seed shifted by b*N*H golden-ratio steps (common.cuh)
+    e1.seed = seed + static_cast<uint64_t>(b) * static_cast<uint64_t>(g->N) * static_cast<uint64_t>(H) * 0x9E3779B97F4A7C15ull;
+    const T* Xb = X ? X + b * xbs : X;
+    T* Yb = Y + b * ybs;
+    int rc = wide_ok ? dispatch_lpr<T, WIDE>(c, g->seg, Xb, ldx, Yb, ldy, g->N, H, e1, partial, st, peers, pad_col)
+                     : dispatch_lpr<T, 1>(c, g->seg, Xb, ldx, Yb, ldy, g->N, H, e1, partial, st, peers, pad_col);
+    if (rc) return rc;
+  }
+  return GDA_OK;
 }
 
 }  // namespace
@@ -917,27 +984,48 @@ int gda_spmm_peer_f32(const gda_graph_t* part, int transpose, const void* const*
                                  gda::as_stream(stream), &t, my_rank);
 }
 
+int gda_spmm_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* X, int64_t ldx, int64_t x_batch_stride,
+                    float* Y, int64_t ldy, int64_t y_batch_stride, int H, const float* bias, int epi_flags,
+                    float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                    int64_t workspace_bytes, gda_stream_t stream) {
+  return gda::spmm_any<float, 4>(g, transpose, X, ldx, Y, ldy, H, bias, epi_flags, dropout_p, seed, seed_offset,
+                                 workspace, workspace_bytes, gda::as_stream(stream), nullptr, 0, nb, x_batch_stride,
+                                 y_batch_stride);
+}
+
 // k chained steps in one call (host-side loop: k launches, one crossing of the ABI).
-// T0 / T1: ping-pong scratch [N, H] (needed for k >= 2 / k >= 3); the epilogue is applied on the last step.
-int gda_spmm_k_f32(const gda_graph_t* g, int transpose, int k, const float* X, int64_t ldx, float* Y, int64_t ldy,
-                   float* T0, float* T1, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
-                   const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
-  GDA_REQUIRE(k >= 1, "gda_spmm_k_f32: k must be >= 1");
-  GDA_REQUIRE(k < 2 || T0, "gda_spmm_k_f32: T0 scratch needed for k >= 2");
-  GDA_REQUIRE(k < 3 || T1, "gda_spmm_k_f32: T1 scratch needed for k >= 3");
+// T0 / T1: ping-pong scratch [nb * N, H] (needed for k >= 2 / k >= 3); the epilogue is applied on the last step.
+int gda_spmm_k_nb_f32(const gda_graph_t* g, int transpose, int k, int nb, const float* X, int64_t ldx,
+                      int64_t x_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, float* T0, float* T1, int H,
+                      const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                      void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(g != nullptr, "gda_spmm_k: graph is NULL");
+  GDA_REQUIRE(k >= 1, "gda_spmm_k: k must be >= 1");
+  GDA_REQUIRE(k < 2 || T0, "gda_spmm_k: T0 scratch needed for k >= 2");
+  GDA_REQUIRE(k < 3 || T1, "gda_spmm_k: T1 scratch needed for k >= 3");
   const float* src = X;
-  int64_t ld_src = ldx;
+  int64_t ld_src = ldx, bs_src = x_batch_stride;
   for (int i = 0; i < k; ++i) {
     const bool last = i == k - 1;
     float* dst = last ? Y : ((i & 1) ? T1 : T0);
     const int64_t ld_dst = last ? ldy : H;
-    int rc = gda_spmm_f32(g, transpose, src, ld_src, dst, ld_dst, H, last ? bias : nullptr, last ? epi_flags : 0,
-                          last ? dropout_p : 0.f, seed, seed_offset, workspace, workspace_bytes, stream);
+    const int64_t bs_dst = last ? y_batch_stride : g->N * static_cast<int64_t>(H);
+    int rc = gda_spmm_nb_f32(g, transpose, nb, src, ld_src, bs_src, dst, ld_dst, bs_dst, H, last ? bias : nullptr,
+                             last ? epi_flags : 0, last ? dropout_p : 0.f, seed, seed_offset, workspace,
+                             workspace_bytes, stream);
     if (rc) return rc;
     src = dst;
     ld_src = ld_dst;
+    bs_src = bs_dst;
   }
   return GDA_OK;
+}
+
+int gda_spmm_k_f32(const gda_graph_t* g, int transpose, int k, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                   float* T0, float* T1, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                   const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  return gda_spmm_k_nb_f32(g, transpose, k, 1, X, ldx, 0, Y, ldy, 0, T0, T1, H, bias, epi_flags, dropout_p, seed,
+                           seed_offset, workspace, workspace_bytes, stream);
 }
 
 int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t epoch, int* error_flag,

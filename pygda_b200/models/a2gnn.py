@@ -61,17 +61,18 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         side = self._side_stream() if self.overlap_streams else main
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            # Layer 1 of the bottleneck is evaluated twice per domain by the reference
-            # (a2gnn.py:181 & :192, :193 & :211) with identical inputs; it is computed once here
-            # and shared (same values -- dropout acts after it).
+            # The reference evaluates the bottleneck twice per domain (a2gnn.py:181 & :192, :193 & :211) on
+            # identical inputs with fresh dropout masks.  Both evaluations are made in one pass
+            # (A2GNNBase.feat_bottleneck_pair): layer 1 once, later layers on the stacked pair -- same values
+            # (SURVEY.md Appendix B.2).
             s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
-            source_logits = net(source_data, self.s_pnums, first_layer=s1)                # :181
+            s_feat_1, source_features = net.feat_bottleneck_pair(                         # :181 (bottleneck), :192
+                source_data.x, source_data.edge_index, source_batch, self.s_pnums, first_layer=s1)
+            source_logits = net.feat_classifier(s_feat_1, source_data.edge_index, source_batch, prop_nums=1)
             train_loss = ops.softmax_cross_entropy(source_logits, source_data.y)          # :182
-            source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, source_batch,
-                                                  self.s_pnums, first_layer=s1)           # :192
         t1 = net.first_conv(target_data.x, target_data.edge_index, self.t_pnums)
-        target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, target_batch,
-                                              self.t_pnums, first_layer=t1)               # :193
+        target_features, t_feat_2 = net.feat_bottleneck_pair(                             # :193, :211 (bottleneck)
+            target_data.x, target_data.edge_index, target_batch, self.t_pnums, first_layer=t1)
         if side is not main:
             main.wait_stream(side)
             for t in (source_logits, train_loss, source_features):
@@ -93,7 +94,7 @@ class A2GNN(TwoDomainLoop, BaseGDA):
             loss = ops.combine([(train_loss, 1.0), (mmd_loss, float(self.weight))] +
                                self._extra_loss_terms(target_features, target_data))
 
-        target_logits = net(target_data, self.t_pnums, first_layer=t1)                    # :211
+        target_logits = net.feat_classifier(t_feat_2, target_data.edge_index, target_batch, prop_nums=1)   # :211
         return loss, source_logits, target_logits
 
     def _extra_loss_terms(self, target_features, target_data):

@@ -1,6 +1,8 @@
 """A2GNNBase -- drop-in for pygda/nn/a2gnn_base.py:7-203 (same ctor, methods and
 state-dict names: ``convs.{i}.lin.weight``, ``convs.{i}.bias``, ``cls.*``,
 ``domain_discriminator.*``)."""
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -57,6 +59,27 @@ class A2GNNBase(nn.Module):
         if self.mode == 'graph':                                             # :140-141
             x = ops.global_mean_pool(x, batch)
         return x
+
+    def feat_bottleneck_pair(self, x, edge_index, batch, prop_nums=30, first_layer=None):
+        """The TWO ``feat_bottleneck`` evaluations the reference makes per domain and step
+        (models/a2gnn.py:181 & :192 for the source, :193 & :211 for the target) in one pass:
+        layer 1 once (its inputs are identical, dropout acts after it), every later layer on the
+        stacked pair with independent dropout masks.  Returns ``(features_1, features_2)`` with the
+        values two separate calls would give.  Without dropout the two evaluations coincide and
+        one tensor is returned twice."""
+        p = float(self.dropout) if self.training else 0.0
+        if p == 0.0:
+            f = self.feat_bottleneck(x, edge_index, batch, prop_nums=prop_nums, first_layer=first_layer)
+            return f, f
+        if self.mode != 'node' or not (self.act is F.relu or self.act is torch.relu) or \
+                os.environ.get("GDA_NO_PAIR") == "1":             # A/B switch for profiles/
+            return (self.feat_bottleneck(x, edge_index, batch, prop_nums=prop_nums, first_layer=first_layer),
+                    self.feat_bottleneck(x, edge_index, batch, prop_nums=prop_nums, first_layer=first_layer))
+        z1 = first_layer if first_layer is not None else self.convs[0](x, edge_index, prop_nums)
+        a, b = ops.act_dropout_pair(z1, p)
+        for conv in list(self.convs)[1:]:
+            a, b = conv.forward_pair(a, b, edge_index, prop_nums, dropout_p=p)
+        return a, b
 
     def feat_classifier(self, x, edge_index, batch, prop_nums=1):            # :145-176
         if self.mode == 'node':

@@ -87,6 +87,18 @@ class PropGCNConv(nn.Module):
         graph = self._graph(x, edge_index, edge_weight) if k > 0 else None
         return ops.graph_conv(x, self.lin.weight, self.bias, graph, k)
 
+    def forward_pair(self, xa, xb, edge_index, prop_nums=1, dropout_p=0.0, edge_weight=None):
+        """``dropout(relu(self(x, edge_index, prop_nums)))`` for two inputs at once, with independent masks:
+        what two consecutive ``feat_bottleneck`` evaluations of a layer compute (a2gnn_base.py:135-138),
+        as one stacked GEMM and one batched aggregation per step (ops.PairGraphConvActFn)."""
+        k = int(prop_nums)
+        graph = self._graph(xa, edge_index, edge_weight) if k > 0 else None
+        if graph is not None and hasattr(graph, "spmm_k"):        # partitioned graph: one matrix per call
+            import torch.nn.functional as F
+            return tuple(ops.act_dropout(ops.graph_conv(x, self.lin.weight, self.bias, graph, k), F.relu,
+                                         dropout_p, True) for x in (xa, xb))
+        return ops.graph_conv_act_pair(xa, xb, self.lin.weight, self.bias, graph, k, dropout_p)
+
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
 

@@ -38,43 +38,58 @@ def _workspace(nbytes, device):
 
 
 # ------------------------------------------------------------------ raw kernels
+_GOLDEN = 0x9E3779B97F4A7C15
+_M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def shift_seed(seed, elements):
+    """Seed under which mask index i equals mask index ``elements + i`` of ``seed`` (common.cuh mix_hash)."""
+    return (int(seed) + int(elements) * _GOLDEN) & _M64
+
+
 def spmm(graph, x, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, out=None,
-         seed_offset=None):
-    """One aggregation Y = A_hat X (or A_hat^T X) with the optional fused epilogue."""
+         seed_offset=None, nb=1):
+    """One aggregation Y = A_hat X (or A_hat^T X) with the optional fused epilogue.
+    ``nb`` > 1: x is ``nb`` stacked [N, H] matrices that share the graph."""
     x = x if x.is_contiguous() else x.contiguous()
-    n, h = x.shape
-    if n != graph.num_nodes:
-        raise ValueError(f"x has {n} rows but the graph has {graph.num_nodes} nodes")
+    rows, h = x.shape
+    n = rows // nb
+    if n != graph.num_nodes or n * nb != rows:
+        raise ValueError(f"x has {rows} rows but the graph has {graph.num_nodes} nodes (x {nb})")
     if out is None:
         out = torch.empty_like(x)
-    ws = graph.workspace(transpose, h)
+    ws = graph.workspace(transpose, h * nb)
     flags = (EPI_RELU if relu else 0) | (EPI_DROPOUT if dropout_p > 0 else 0)
-    args = (graph.handle, int(bool(transpose)), _p(x), h, _p(out), h, h, _p(bias), flags,
-            float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_offset), _p(ws), ws.numel(),
-            _stream())
+    tail = (h, _p(bias), flags, float(dropout_p), int(seed) & _M64, _p(seed_offset), _p(ws), ws.numel(), _stream())
     prof = PROFILE
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    if x.dtype == torch.float32:
-        gda.spmm_f32(*args)
+    if nb > 1:
+        if x.dtype != torch.float32:
+            raise TypeError("batched aggregation supports float32 features")
+        gda.spmm_nb_f32(graph.handle, int(bool(transpose)), nb, _p(x), h, n * h, _p(out), h, n * h, *tail)
+    elif x.dtype == torch.float32:
+        gda.spmm_f32(graph.handle, int(bool(transpose)), _p(x), h, _p(out), h, *tail)
     elif x.dtype == torch.bfloat16:
-        gda.spmm_bf16(*args)
+        gda.spmm_bf16(graph.handle, int(bool(transpose)), _p(x), h, _p(out), h, *tail)
     else:
         raise TypeError(f"aggregation supports float32 and bfloat16 features, got {x.dtype}")
     if prof is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        prof.append((e0, e1, (n, h, str(x.dtype).replace("torch.", ""))))
+        prof.append((e0, e1, (n, h, str(x.dtype).replace("torch.", "")) + ((nb,) if nb > 1 else ())))
     return out
 
 
 def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0,
-           seed_offset=None):
+           seed_offset=None, nb=1):
     """A_hat^k X with ping-pong buffers; the epilogue is applied on the last step."""
     if k == 0:
         raise ValueError("spmm_k needs k >= 1")
     if hasattr(graph, "spmm_k"):          # row-partitioned graph: NVLink peer path (pygda_b200/dist.py)
+        if nb != 1:
+            raise NotImplementedError("the peer path aggregates one matrix per call")
         return graph.spmm_k(x, k, transpose=transpose, bias=bias, relu=relu, dropout_p=dropout_p, seed=seed,
                             seed_offset=seed_offset)
     if x.dtype != torch.float32 or PROFILE is not None:
@@ -86,21 +101,22 @@ def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, s
             if dst is None:
                 dst = bufs[i & 1] = torch.empty_like(x)
             cur = spmm(graph, cur, transpose, bias if last else None, relu and last,
-                       dropout_p if last else 0.0, seed, out=dst, seed_offset=seed_offset)
+                       dropout_p if last else 0.0, seed, out=dst, seed_offset=seed_offset, nb=nb)
         return cur
-    # fp32: all k launches behind one call (gda_spmm_k_f32) -- k-fold less host work per conv
+    # fp32: all k launches behind one call (gda_spmm_k_nb_f32) -- k-fold less host work per conv
     x = x if x.is_contiguous() else x.contiguous()
-    n, h = x.shape
-    if n != graph.num_nodes:
-        raise ValueError(f"x has {n} rows but the graph has {graph.num_nodes} nodes")
+    rows, h = x.shape
+    n = rows // nb
+    if n != graph.num_nodes or n * nb != rows:
+        raise ValueError(f"x has {rows} rows but the graph has {graph.num_nodes} nodes (x {nb})")
     out = torch.empty_like(x)
     t0 = torch.empty_like(x) if k >= 2 else None
     t1 = torch.empty_like(x) if k >= 3 else None
-    ws = graph.workspace(transpose, h)
+    ws = graph.workspace(transpose, h * nb)
     flags = (EPI_RELU if relu else 0) | (EPI_DROPOUT if dropout_p > 0 else 0)
-    gda.spmm_k_f32(graph.handle, int(bool(transpose)), int(k), _p(x), h, _p(out), h, _p(t0), _p(t1), h, _p(bias),
-                   flags, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_offset), _p(ws), ws.numel(),
-                   _stream())
+    gda.spmm_k_nb_f32(graph.handle, int(bool(transpose)), int(k), int(nb), _p(x), h, n * h, _p(out), h, n * h, _p(t0),
+                      _p(t1), h, _p(bias), flags, float(dropout_p), int(seed) & _M64, _p(seed_offset), _p(ws),
+                      ws.numel(), _stream())
     return out
 
 
@@ -359,6 +375,130 @@ def act_dropout(x, act, p, training):
     if p_eff > 0:
         return ActDropoutFn.apply(x, 0, p_eff, next_seed())
     return x
+
+
+# ------------------------------------------------------------------ paired bottleneck evaluations
+# The reference evaluates feat_bottleneck twice per domain and step on the same graph and weights, with fresh
+# dropout masks (pygda/models/a2gnn.py:181 & :192, :193 & :211).  Layer 1 is shared (dropout acts after it);
+# from there on the two evaluations travel as one stacked [2N, .] matrix: one GEMM, and one aggregation launch
+# per propagation step that reads every (colidx, weight) once for both (gda_spmm_nb_f32).  Values are those of
+# two separate evaluations with the masks of rows [0, N) and [N, 2N) of the stacked matrix.
+def _stack2(a, b):
+    """[2N, C] matrix of two [N, C] halves -- a view when they already sit back to back in one buffer."""
+    if (a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.dtype == b.dtype and
+            a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr() and
+            b.storage_offset() == a.storage_offset() + a.numel()):
+        return a.new_empty(0).set_(a.untyped_storage(), a.storage_offset(), (2 * a.shape[0], a.shape[1]),
+                                   (a.shape[1], 1))
+    return torch.cat([a, b], 0)
+
+
+class ActDropoutPairFn(torch.autograd.Function):
+    """x -> (dropout_1(act(x)), dropout_2(act(x))): one read, two independently masked copies."""
+
+    @staticmethod
+    def forward(ctx, x, act, p, seed):
+        x = _f32c(x)
+        n, c = x.shape
+        y = torch.empty(2 * n, c, dtype=torch.float32, device=x.device)
+        off = dropout_rng.offset if p > 0 else None
+        gda.bias_act_dropout_rep_fwd(_p(x), _NULL, _p(y), n, c, 2, act, float(p), seed, _p(off), _stream())
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, float(p), seed, n, c, off)
+        ctx.set_materialize_grads(False)
+        return y[:n], y[n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        if ga is None and gb is None:
+            return None, None, None, None
+        (y,) = ctx.saved_tensors
+        act, p, seed, n, c, off = ctx.cfg
+        ga = _f32c(ga) if ga is not None else None
+        gb = _f32c(gb) if gb is not None else None
+        gx = torch.empty(n, c, dtype=torch.float32, device=y.device)
+        gda.bias_act_dropout_rep_bwd(_p(ga), _p(gb), _p(y), _p(gx), _NULL, n, c, 2, 1, act, p, seed, _p(off), _stream())
+        return gx, None, None, None
+
+
+class PairGraphConvActFn(torch.autograd.Function):
+    """(xa, xb) -> dropout(act(A_hat^k (x W^T) + b)) for both halves as ONE tape node: stacked GEMM, batched
+    aggregation with the bias / ReLU / dropout epilogue fused into its last step (k = 0: one elementwise pass).
+    A half whose output receives no gradient (the target-side evaluation that only yields ``target_logits``,
+    a2gnn.py:211) costs nothing in the backward."""
+
+    @staticmethod
+    def forward(ctx, xa, xb, weight, bias, graph, k, w_in_out, act, p, seed):
+        x = _stack2(_f32c(xa), _f32c(xb))
+        w = _f32c(weight)
+        n = x.shape[0] // 2
+        h, _, ws = mm(x, w, trans_b=not w_in_out)
+        off = dropout_rng.offset if p > 0 else None
+        if k > 0:
+            y = spmm_k(graph, h, k, bias=bias, relu=bool(act), dropout_p=p, seed=seed, seed_offset=off, nb=2)
+        else:
+            y = h
+            if bias is not None or act or p > 0:
+                gda.bias_act_dropout_fwd(_p(h), _p(bias), _p(y), 2 * n, h.shape[1], int(act), float(p), seed, _p(off),
+                                         _stream())
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (graph, k, w_in_out, bias is not None, int(act), float(p), seed, off, n)
+        ctx.w_split = ws
+        ctx.set_materialize_grads(False)
+        return y[:n], y[n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        none = (None,) * 10
+        if ga is None and gb is None:
+            return none
+        x, w, y = ctx.saved_tensors
+        graph, k, w_in_out, has_bias, act, p, seed, off, n = ctx.cfg
+        c = y.shape[1]
+        both = ga is not None and gb is not None
+        if both:
+            nb, xs, ys, sd = 2, x, y, seed
+        elif ga is not None:
+            nb, xs, ys, sd = 1, x[:n], y[:n], seed
+        else:                                              # masks of the second half: rows [N, 2N) of the stack
+            nb, xs, ys, sd = 1, x[n:], y[n:], shift_seed(seed, n * c)
+        g0_, g1_ = (ga, gb) if both else ((ga if ga is not None else gb), None)
+        g0_ = _f32c(g0_)
+        g1_ = _f32c(g1_) if g1_ is not None else None
+        if act or p > 0 or both:
+            g = torch.empty(nb * n, c, dtype=torch.float32, device=y.device)
+            gda.bias_act_dropout_rep_bwd(_p(g0_), _p(g1_), _p(ys), _p(g), _NULL, n, c, nb, 0, act, p, sd, _p(off),
+                                         _stream())
+        else:
+            g = g0_
+        gbias = colsum(g) if (has_bias and ctx.needs_input_grad[3]) else None
+        g0 = spmm_k(graph, g, k, transpose=True, nb=nb) if k > 0 else g
+        gw = gx = gs = None
+        if ctx.needs_input_grad[2]:
+            if w_in_out:
+                gw, _, gs = mm(xs, g0, trans_a=True)
+            else:
+                gw, gs, _ = mm(g0, xs, trans_a=True)
+        gxa = gxb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx, _, _ = mm(g0, w, trans_b=w_in_out, a_split=gs, b_split=ctx.w_split)
+            if both:
+                gxa, gxb = gx[:n], gx[n:]
+            elif ga is not None:
+                gxa = gx
+            else:
+                gxb = gx
+        return (gxa, gxb, gw, gbias) + (None,) * 6
+
+
+def act_dropout_pair(x, p):
+    """Two independently masked copies of dropout(relu(x)), p > 0."""
+    return ActDropoutPairFn.apply(x, 1, float(p), next_seed())
+
+
+def graph_conv_act_pair(xa, xb, weight, bias, graph, k, p, relu=True, w_in_out=False):
+    return PairGraphConvActFn.apply(xa, xb, weight, bias, graph, int(k), bool(w_in_out), 1 if relu else 0,
+                                    float(p), next_seed() if p > 0 else 0)
 
 
 class BiasAddFn(torch.autograd.Function):
