@@ -308,6 +308,29 @@ int gda_laplacian_finish_f32(const float* g, const float* u_in, const float* u_o
                              const float* in_deg, int64_t N, int H, float* loss, float* df, void* workspace,
                              int64_t workspace_bytes, gda_stream_t stream);
 
+/* ------------------------------------------- either side of the path --
+ * gda_collate_graphs: graph-mode mini-batch collation on the device -- what PyG's
+ * DataLoader / Batch.from_data_list yields for `DataLoader(dataset, batch_size, shuffle=True)`
+ * (pygda/models/a2gnn.py:276-286, adagcn.py:240-251): x rows of the chosen graphs concatenated,
+ * edge_index re-based to the running node count, batch[i] = position of node i's graph in the batch.
+ * The dataset lives in HBM as one concatenation: x_all [N_all, F], edge_index_all int64 [2, E_all] (node ids
+ * global in x_all, every edge inside its graph, edges of one graph contiguous), node_ptr / edge_ptr
+ * int64 [G_all + 1].  graph_ids int64 [B] = the batch, in order; out_node_ptr / out_edge_ptr int64 [B + 1] =
+ * exclusive scans of the chosen graphs' node / edge counts (device), num_*_out their last entries.
+ * Outputs: x_out [num_nodes_out, F], edge_index_out int64 [2, num_edges_out], batch_out int64 [num_nodes_out]. */
+int gda_collate_graphs(const float* x_all, int F, const int64_t* edge_index_all, int64_t E_all,
+                       const int64_t* node_ptr, const int64_t* edge_ptr, const int64_t* graph_ids, int64_t B,
+                       const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t num_nodes_out,
+                       int64_t num_edges_out, float* x_out, int64_t* edge_index_out, int64_t* batch_out,
+                       gda_stream_t stream);
+/* gda_argmax_confusion: pred[r] = argmax_c logits[r, c] (first maximal index) and counts[y * C + p] += 1
+ * (int64 [C, C], zeroed by the call): the per-epoch training score
+ * eval_micro_f1(labels, logits.argmax(dim=1)) (pygda/models/a2gnn.py:328-329, pygda/metrics/metrics.py)
+ * without moving N labels and N predictions to the host.  pred_out may be NULL; *bad_label (device int) is set
+ * when a label lies outside [0, C).  C <= 64. */
+int gda_argmax_confusion(const float* logits, int64_t rows, int C, int64_t ld, const int64_t* labels,
+                         int64_t* pred_out, int64_t* counts, int* bad_label, gda_stream_t stream);
+
 /* ---------------------------------------------------------------- pooling --
  * global_mean_pool over a sorted `batch` vector given as CSR-style ptr
  * (int64 [G+1]).  Call sites: a2gnn_base.py:141, adagcn_base.py:94,

@@ -73,6 +73,8 @@ SIGNATURES = {
     "gda_row_scale_rsqrt_f32": (i32, [vp, i64, vp, vp, i64, i32, vp]),
     "gda_laplacian_workspace_bytes": (i64, []),
     "gda_laplacian_finish_f32": (i32, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp]),
+    "gda_collate_graphs": (i32, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "gda_argmax_confusion": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "gda_segment_mean_bwd": (i32, [vp, vp, i64, i32, vp, i64, vp]),
     "gda_adam_step": (i32, [i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp]),

@@ -1,0 +1,137 @@
+// The steps either side of the hot path, on the device:
+//   gda_collate_graphs   the graph-mode mini-batch collation the reference gets from PyG's
+//                        DataLoader / Batch.from_data_list (pygda/models/a2gnn.py:276-286, same block in
+//                        udagcn / grade / adagcn): node-wise cat of x, edge_index offset by the running node
+//                        count, `batch` = graph id per node, from a dataset kept resident in HBM
+//   gda_argmax_confusion the per-epoch training score (pygda/models/a2gnn.py:328-329:
+//                        eval_micro_f1(labels, logits.argmax(dim=1)) -> .cpu().numpy() -> sklearn): argmax fused
+//                        with a C x C confusion count, so that C*C integers cross PCIe instead of 2N labels
+#include "common.cuh"
+
+namespace gda {
+namespace {
+
+// first i in [0, n) with ptr[i + 1] > v, for a non-decreasing ptr[0..n] with ptr[0] <= v < ptr[n]
+__device__ __forceinline__ int64_t owner_of(const int64_t* __restrict__ ptr, int64_t n, int64_t v) {
+  int64_t lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(ptr + mid + 1) > v) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// one warp per output node: copies the feature row, writes batch[i]
+__global__ void k_collate_nodes(const float* __restrict__ x_all, int F, const int64_t* __restrict__ node_ptr,
+                                const int64_t* __restrict__ ids, int64_t B, const int64_t* __restrict__ out_node_ptr,
+                                float* __restrict__ x_out, int64_t* __restrict__ batch_out) {
+  const int64_t total = __ldg(out_node_ptr + B);
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += nwarps) {
+    const int64_t g = owner_of(out_node_ptr, B, i);
+    const int64_t src = __ldg(node_ptr + __ldg(ids + g)) + (i - __ldg(out_node_ptr + g));
+    const float* __restrict__ s = x_all + src * F;
+    float* __restrict__ d = x_out + i * F;
+    for (int c = lane; c < F; c += 32) d[c] = __ldg(s + c);
+    if (lane == 0) batch_out[i] = g;
+  }
+}
+
+// one thread per output edge: both endpoints re-based from dataset node ids to batch node ids
+__global__ void k_collate_edges(const int64_t* __restrict__ ei_all, int64_t E_all, const int64_t* __restrict__ node_ptr,
+                                const int64_t* __restrict__ edge_ptr, const int64_t* __restrict__ ids, int64_t B,
+                                const int64_t* __restrict__ out_node_ptr, const int64_t* __restrict__ out_edge_ptr,
+                                int64_t* __restrict__ ei_out) {
+  const int64_t total = __ldg(out_edge_ptr + B);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = owner_of(out_edge_ptr, B, e);
+    const int64_t id = __ldg(ids + g);
+    const int64_t src = __ldg(edge_ptr + id) + (e - __ldg(out_edge_ptr + g));
+    const int64_t shift = __ldg(out_node_ptr + g) - __ldg(node_ptr + id);
+    ei_out[e] = __ldg(ei_all + src) + shift;
+    ei_out[total + e] = __ldg(ei_all + E_all + src) + shift;
+  }
+}
+
+constexpr int kMaxClasses = 64;
+
+// argmax (first maximal index, like torch.argmax on the CPU) + confusion counts[label * C + pred]
+__global__ void k_argmax_confusion(const float* __restrict__ logits, int64_t rows, int C, int64_t ld,
+                                   const int64_t* __restrict__ labels, int64_t* __restrict__ pred_out,
+                                   unsigned long long* __restrict__ counts, int* __restrict__ bad_label) {
+  extern __shared__ unsigned int hist[];                  // C * C
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* __restrict__ z = logits + r * ld;
+    int best = 0;
+    float bv = z[0];
+    for (int c = 1; c < C; ++c) {
+      const float v = z[c];
+      if (v > bv || (v != v && !(bv != bv))) { bv = v; best = c; }      // NaN counts as maximal, like torch
+    }
+    if (pred_out) pred_out[r] = best;
+    const int64_t y = labels[r];
+    if (y < 0 || y >= C) { atomicExch(bad_label, 1); continue; }
+    atomicAdd(&hist[static_cast<int>(y) * C + best], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (hist[i]) atomicAdd(counts + i, static_cast<unsigned long long>(hist[i]));
+}
+
+}  // namespace
+}  // namespace gda
+
+extern "C" {
+
+int gda_collate_graphs(const float* x_all, int F, const int64_t* edge_index_all, int64_t E_all,
+                       const int64_t* node_ptr, const int64_t* edge_ptr, const int64_t* graph_ids, int64_t B,
+                       const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t num_nodes_out,
+                       int64_t num_edges_out, float* x_out, int64_t* edge_index_out, int64_t* batch_out,
+                       gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(B >= 0 && F > 0 && E_all >= 0 && num_nodes_out >= 0 && num_edges_out >= 0, "gda_collate_graphs: bad size");
+  if (B == 0) return GDA_OK;
+  GDA_REQUIRE(node_ptr && edge_ptr && graph_ids && out_node_ptr && out_edge_ptr, "gda_collate_graphs: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  if (num_nodes_out > 0) {
+    GDA_REQUIRE(x_all && x_out && batch_out, "gda_collate_graphs: NULL node buffer");
+    int64_t blocks = ceil_div(num_nodes_out, 8);
+    if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+    k_collate_nodes<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x_all, F, node_ptr, graph_ids, B, out_node_ptr, x_out,
+                                                                  batch_out);
+    GDA_LAUNCH_CHECK();
+  }
+  if (num_edges_out > 0) {
+    GDA_REQUIRE(edge_index_all && edge_index_out, "gda_collate_graphs: NULL edge buffer");
+    int64_t blocks = ceil_div(num_edges_out, 256);
+    if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+    k_collate_edges<<<static_cast<unsigned>(blocks), 256, 0, st>>>(edge_index_all, E_all, node_ptr, edge_ptr, graph_ids, B,
+                                                                  out_node_ptr, out_edge_ptr, edge_index_out);
+    GDA_LAUNCH_CHECK();
+  }
+  return GDA_OK;
+}
+
+int gda_argmax_confusion(const float* logits, int64_t rows, int C, int64_t ld, const int64_t* labels,
+                         int64_t* pred_out, int64_t* counts, int* bad_label, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(rows >= 0 && C > 0 && C <= kMaxClasses && ld >= C, "gda_argmax_confusion: bad shape (need 0 < C <= 64)");
+  GDA_REQUIRE(counts && bad_label, "gda_argmax_confusion: NULL output");
+  cudaStream_t st = as_stream(stream);
+  GDA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * C * C, st));
+  GDA_CUDA(cudaMemsetAsync(bad_label, 0, sizeof(int), st));
+  if (rows == 0) return GDA_OK;
+  GDA_REQUIRE(logits && labels, "gda_argmax_confusion: NULL input");
+  int64_t blocks = ceil_div(rows, 256 * 4);
+  if (blocks > int64_t(kNumSMs) * 4) blocks = int64_t(kNumSMs) * 4;
+  if (blocks < 1) blocks = 1;
+  k_argmax_confusion<<<static_cast<unsigned>(blocks), 256, sizeof(unsigned int) * C * C, st>>>(
+      logits, rows, C, ld, labels, pred_out, reinterpret_cast<unsigned long long*>(counts), bad_label);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+}  // extern "C"

@@ -115,11 +115,65 @@ class NeighborLoader:
         return 1
 
 
-class DataLoader:
-    """``DataLoader(dataset, batch_size, shuffle)`` over a sequence of graphs."""
+class DeviceGraphDataset:
+    """A list of small graphs kept RESIDENT on the GPU as one concatenation (x_all, edge_index_all with global node
+    ids, node_ptr / edge_ptr), so that a mini-batch is collated by two kernels (``gda_collate_graphs``) instead
+    of a Python loop + ``torch.cat`` over hundreds of graphs per step (``Batch.from_data_list``).  The result is
+    the same ``Batch`` (tests/test_gpu_loader.py)."""
 
-    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+    def __init__(self, graphs, device):
+        self.device = torch.device(device)
+        graphs = list(graphs)
+        self.num_graphs = len(graphs)
+        nn_ = torch.tensor([g.x.size(0) for g in graphs], dtype=torch.long)
+        ne_ = torch.tensor([g.edge_index.size(1) for g in graphs], dtype=torch.long)
+        self.node_ptr_host = torch.zeros(self.num_graphs + 1, dtype=torch.long)
+        self.edge_ptr_host = torch.zeros(self.num_graphs + 1, dtype=torch.long)
+        self.node_ptr_host[1:] = torch.cumsum(nn_, 0)
+        self.edge_ptr_host[1:] = torch.cumsum(ne_, 0)
+        offs = self.node_ptr_host[:-1].tolist()
+        self.x_all = torch.cat([g.x for g in graphs]).to(self.device, torch.float32).contiguous()
+        self.ei_all = torch.cat([g.edge_index.cpu() + o for g, o in zip(graphs, offs)], 1).to(self.device).contiguous()
+        self.y_all = torch.cat([g.y.view(-1) for g in graphs]).to(self.device)
+        self.node_ptr, self.edge_ptr = self.node_ptr_host.to(self.device), self.edge_ptr_host.to(self.device)
+        self.num_features = self.x_all.size(1)
+
+    def __len__(self):
+        return self.num_graphs
+
+    def collate(self, ids):
+        """``Batch`` of the graphs ``ids`` (a list / CPU tensor, in batch order), built on the device."""
+        import ctypes as C
+        from ._lib import gda
+        ids_h = torch.as_tensor(ids, dtype=torch.long)
+        b = ids_h.numel()
+        out_np = torch.zeros(b + 1, dtype=torch.long)
+        out_ep = torch.zeros(b + 1, dtype=torch.long)
+        out_np[1:] = torch.cumsum(self.node_ptr_host[ids_h + 1] - self.node_ptr_host[ids_h], 0)
+        out_ep[1:] = torch.cumsum(self.edge_ptr_host[ids_h + 1] - self.edge_ptr_host[ids_h], 0)
+        n_out, e_out = int(out_np[-1]), int(out_ep[-1])
+        staged = torch.cat([ids_h, out_np, out_ep]).pin_memory().to(self.device, non_blocking=True)
+        ids_d, np_d, ep_d = staged[:b], staged[b:2 * b + 1], staged[2 * b + 1:]
+        x = torch.empty(n_out, self.num_features, dtype=torch.float32, device=self.device)
+        ei = torch.empty(2, e_out, dtype=torch.long, device=self.device)
+        batch = torch.empty(n_out, dtype=torch.long, device=self.device)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        gda.collate_graphs(p(self.x_all), self.num_features, p(self.ei_all), self.ei_all.size(1), p(self.node_ptr),
+                           p(self.edge_ptr), p(ids_d), b, p(np_d), p(ep_d), n_out, e_out, p(x), p(ei), p(batch),
+                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return Batch(x=x, edge_index=ei, y=self.y_all.index_select(0, ids_d), batch=batch, num_graphs=b, ptr=np_d)
+
+
+class DataLoader:
+    """``DataLoader(dataset, batch_size, shuffle)`` over a sequence of graphs.  With ``device`` set to a CUDA device
+    the dataset is moved there once (``DeviceGraphDataset``) and every batch is collated on the GPU; the shuffle
+    order still comes from ``torch.randperm`` on the CPU generator, as PyG's does."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, device=None, **kw):
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
+        self.resident = None
+        if device is not None and torch.device(device).type == "cuda" and len(dataset) > 0:
+            self.resident = dataset if isinstance(dataset, DeviceGraphDataset) else DeviceGraphDataset(dataset, device)
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
@@ -128,4 +182,8 @@ class DataLoader:
         n = len(self.dataset)
         order = torch.randperm(n).tolist() if self.shuffle else list(range(n))
         for s in range(0, n, self.batch_size):
-            yield Batch.from_data_list([self.dataset[i] for i in order[s:s + self.batch_size]])
+            ids = order[s:s + self.batch_size]
+            if self.resident is not None:
+                yield self.resident.collate(ids)
+            else:
+                yield Batch.from_data_list([self.dataset[i] for i in ids])

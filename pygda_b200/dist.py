@@ -294,6 +294,49 @@ class GatherRows(torch.autograd.Function):
         return gx, None, None, None
 
 
+class AllGatherRows(torch.autograd.Function):
+    """Row blocks of every rank concatenated in rank order, replicated on every rank (blocks may differ in
+    length).  Backward: a rank keeps the gradient of its own block -- correct when what is computed from the
+    gathered matrix is REPLICATED on every rank (every rank holds the same upstream gradient), as the pooled
+    graph encodings of the data-parallel graph-level path are (models/dist_adagcn.py)."""
+
+    @staticmethod
+    def forward(ctx, x, pg):
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        counts = torch.zeros(world, dtype=torch.int64, device=x.device)
+        counts[rank] = x.size(0)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
+        counts = [int(c) for c in counts.tolist()]
+        out = torch.zeros(sum(counts), *x.shape[1:], dtype=x.dtype, device=x.device)
+        lo = sum(counts[:rank])
+        out[lo:lo + x.size(0)] = x
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=pg)      # blocks are disjoint: sum == concatenation
+        ctx.lo, ctx.n = lo, x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.lo:ctx.lo + ctx.n].contiguous(), None
+
+
+def shard_batch(batch, rank, world):
+    """Graphs [lo, hi) of a collated ``Batch`` (contiguous 1-D split of its graphs over the ranks) as a new
+    ``Batch`` with local node ids -- the data-parallel split of one mini-batch."""
+    from .data import Batch
+    g = len(batch)
+    lo, hi = block_range(g, world, rank)
+    ptr = getattr(batch, "ptr", None)
+    if ptr is None:
+        counts = torch.bincount(batch.batch, minlength=g)
+        ptr = torch.zeros(g + 1, dtype=torch.long, device=counts.device)
+        ptr[1:] = torch.cumsum(counts, 0)
+    n_lo, n_hi = int(ptr[lo]), int(ptr[hi])
+    ei = batch.edge_index
+    keep = (ei[1] >= n_lo) & (ei[1] < n_hi)
+    return Batch(x=batch.x[n_lo:n_hi], edge_index=(ei[:, keep] - n_lo).contiguous(), y=batch.y[lo:hi],
+                 batch=batch.batch[n_lo:n_hi] - lo, num_graphs=hi - lo, ptr=(ptr[lo:hi + 1] - n_lo).clone())
+
+
 def allreduce_grads(params, pg=None):
     """Sum the weight gradients over ranks (one flat NCCL all-reduce)."""
     grads = [p.grad for p in params if p.grad is not None]

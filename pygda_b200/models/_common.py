@@ -6,7 +6,7 @@ import time
 import torch
 
 from ..data import DataLoader, NeighborLoader
-from ..metrics import eval_micro_f1
+from ..metrics import eval_micro_f1, micro_f1_from_logits
 from ..utils import logger
 
 
@@ -26,12 +26,15 @@ class TwoDomainLoop:
                 self.source_loader = NeighborLoader(source_data, self.num_neigh, batch_size=self.batch_size)
                 self.target_loader = NeighborLoader(target_data, self.num_neigh, batch_size=self.batch_size)
         elif self.mode == 'graph':
+            # datasets given as sequences of graphs are made resident on the device once and collated there
+            dev = self.device if isinstance(source_data, (list, tuple)) and isinstance(target_data, (list, tuple)) \
+                else None
             if self.batch_size == 0:
-                self.source_loader = DataLoader(source_data, batch_size=len(source_data), shuffle=True)
-                self.target_loader = DataLoader(target_data, batch_size=len(target_data), shuffle=True)
+                self.source_loader = DataLoader(source_data, batch_size=len(source_data), shuffle=True, device=dev)
+                self.target_loader = DataLoader(target_data, batch_size=len(target_data), shuffle=True, device=dev)
             else:
-                self.source_loader = DataLoader(source_data, batch_size=self.batch_size, shuffle=True)
-                self.target_loader = DataLoader(target_data, batch_size=self.batch_size, shuffle=True)
+                self.source_loader = DataLoader(source_data, batch_size=self.batch_size, shuffle=True, device=dev)
+                self.target_loader = DataLoader(target_data, batch_size=self.batch_size, shuffle=True, device=dev)
         else:
             assert self.mode in ('graph', 'node'), 'Invalid train mode'
 
@@ -56,7 +59,8 @@ class TwoDomainLoop:
             if self.verbose > 1:
                 # the reference scores F1 every epoch even when nothing is printed; the value is
                 # only ever printed, so it is skipped for verbose <= 1 (no observable change)
-                micro_f1_score = eval_micro_f1(epoch_source_labels, epoch_source_logits.argmax(dim=1))
+                # eval_micro_f1(labels, logits.argmax(dim=1)) (a2gnn.py:328-329) with the argmax + counting on the GPU
+                micro_f1_score = micro_f1_from_logits(epoch_source_labels, epoch_source_logits)
             logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
                    time=time.time() - start_time, verbose=self.verbose, train=True)
 

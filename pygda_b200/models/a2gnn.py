@@ -138,7 +138,7 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         """fit() with the loop body replayed from a CUDA graph: epoch 0 runs eagerly (and warms the
         caches), epochs 1.. are replays.  Logging as in _fit_loop."""
         import time
-        from ..metrics import eval_micro_f1
+        from ..metrics import micro_f1_from_logits
         from ..utils import logger
         from .graphed import GraphedStep
         start_time = time.time()
@@ -155,7 +155,7 @@ class A2GNN(TwoDomainLoop, BaseGDA):
             epoch_loss = loss.item()
             micro_f1_score = None
             if self.verbose > 1:
-                micro_f1_score = eval_micro_f1(step.src.y, source_logits.argmax(dim=1))
+                micro_f1_score = micro_f1_from_logits(step.src.y, source_logits)
             logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
                    time=time.time() - start_time, verbose=self.verbose, train=True)
 

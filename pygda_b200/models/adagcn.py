@@ -69,22 +69,25 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         loss = cls_loss + dis_loss * self.domain_weight                                   # :196
         return loss, source_logits, target_logits
 
+    def _rand(self, n):
+        return torch.rand((n, 1)).to(self.device)         # CPU generator, like the reference (:420,:429,:434)
+
     def gradient_penalty(self, encoded_source, encoded_target):
         num_s, num_t = encoded_source.shape[0], encoded_target.shape[0]                   # :387-454
         if num_s < num_t:
             hidden = encoded_target[-num_s:, ]
             hidden_s = torch.cat((encoded_source, encoded_source), dim=0)
             hidden_t = torch.cat((encoded_target[0:num_s, ], hidden), dim=0)
-            alpha = torch.rand((2 * num_s, 1)).to(self.device)
+            alpha = self._rand(2 * num_s)
             interpolates = hidden_t + (alpha * (hidden_s - hidden_t))
         elif num_s > num_t:
             hidden = encoded_source[-num_t:, ]
             hidden_s = torch.cat((encoded_source[0:num_t, ], hidden), dim=0)
             hidden_t = torch.cat((encoded_target, encoded_target), dim=0)
-            alpha = torch.rand((2 * num_t, 1)).to(self.device)
+            alpha = self._rand(2 * num_t)
             interpolates = hidden_t + (alpha * (hidden_s - hidden_t))
         else:
-            alpha = torch.rand((num_t, 1)).to(self.device)
+            alpha = self._rand(num_t)
             interpolates = encoded_target + (alpha * (encoded_source - encoded_target))
         inputs = torch.cat((encoded_source, encoded_target, interpolates), dim=0)
         if not inputs.requires_grad:                    # tape-free encoder outputs: differentiate w.r.t. a leaf

@@ -7,7 +7,7 @@ import torch.nn.functional as F
 from . import BaseGDA
 from .. import ops
 from ..data import NeighborLoader
-from ..metrics import eval_micro_f1
+from ..metrics import micro_f1_from_logits
 from ..nn.gnn_base import GNNBase
 from ..optim import Adam
 from ..utils import logger
@@ -57,7 +57,7 @@ class GNN(BaseGDA):
                     lg, lb = self.predict(s)
                     logits_all = lg if idx == 0 else torch.cat((logits_all, lg))
                     labels_all = lb if idx == 0 else torch.cat((labels_all, lb))
-            f1 = eval_micro_f1(labels_all, logits_all.argmax(dim=1)) if self.verbose > 1 else None
+            f1 = micro_f1_from_logits(labels_all, logits_all) if self.verbose > 1 else None
             logger(epoch=epoch, loss=epoch_loss, source_train_acc=f1, time=time.time() - start_time,
                    verbose=self.verbose, train=True)
 

@@ -87,6 +87,79 @@ def main():
             print(f"step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items() if not k.startswith("param")),
                   f"max param err {max(v for k, v in errs.items() if k.startswith('param')):.1e}")
     group.check()
+
+    # ---- 3. GRADE over the partition (config 4): MMD and JS discrepancies ------------------------
+    from pygda_b200.models import GRADE
+    from pygda_b200.models.dist_grade import DistGRADE
+    for disc in ("MMD", "JS"):
+        hp = dict(in_dim=64, hid_dim=32, num_classes=5, num_layers=2, dropout=0.0, disc=disc, weight=0.5,
+                  weight_decay=0.01, lr=0.01, epoch=200, verbose=0)
+        torch.manual_seed(1)
+        single = GRADE(device=str(dev), **hp)
+        single.grade = single.init_model()
+        multi = DistGRADE(device=str(dev), group=group, **hp)
+        multi.grade = multi.init_model()
+        single.grade.load_state_dict(multi.grade.state_dict())
+        mind = n - 1000
+        torch.manual_seed(6)
+        idx = tuple(t.to(dev) for t in draw_indices(mind, mind))
+        for t in idx:
+            dist.broadcast(t, src=0)
+        idx = tuple(t.cpu() for t in idx)
+        o1 = Adam(single.grade.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+        o2 = Adam(multi.grade.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+        for step in range(2):
+            l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=idx)
+            l2, sl2, tl2, _ = multi.train_step(s_part, t_part, 0.3, o2, mmd_indices=idx)
+            slo, shi = group.block(n)
+            tlo, thi = group.block(n - 1000)
+            errs = {"loss": rel(l2, l1), "source_logits": rel(sl2, sl1[slo:shi]), "target_logits": rel(tl2, tl1[tlo:thi])}
+            perr = max(rel(p, q) for p, q in zip(multi.grade.parameters(), single.grade.parameters()))
+            ok &= max(max(errs.values()), perr) < 2e-4
+            if rank == 0:
+                print(f"GRADE[{disc}] step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()),
+                      f"max param err {perr:.1e}")
+    group.check()
+
+    # ---- 4. graph-level AdaGCN, data-parallel over the graphs of a mini-batch (config 5) ---------
+    from pygda_b200.data import Batch
+    from pygda_b200.dist import shard_batch
+    from pygda_b200.models import AdaGCN
+    from pygda_b200.models.dist_adagcn import DistAdaGCN
+    from pygda_b200.synthetic import graph_dataset
+    hp = dict(in_dim=14, hid_dim=32, num_classes=2, mode="graph", num_layers=2, gp_weight=5, domain_weight=0.1,
+              weight_decay=0.01, lr=0.01, epoch=2, batch_size=64, verbose=0)
+    ds_s = graph_dataset(61, 30, 2.05, 14, 2, seed=0)
+    ds_t = graph_dataset(64, 39, 3.7, 14, 2, seed=1)
+    bs, bt = Batch.from_data_list(list(ds_s)).to(dev), Batch.from_data_list(list(ds_t)).to(dev)
+    torch.manual_seed(2)
+    single = AdaGCN(device=str(dev), **hp)
+    single.adagcn = single.init_model()
+    multi = DistAdaGCN(device=str(dev), **hp)
+    multi.adagcn = multi.init_model()
+    single.adagcn.load_state_dict(multi.adagcn.state_dict())
+    for est in (single, multi):
+        est.adagcn.encoder.dropout.p = 0.0                  # element-indexed masks differ between shards
+    multi.init_critic()
+    single.init_critic()
+    single.discriminator.load_state_dict(multi.discriminator.state_dict())
+    o1 = Adam(single.adagcn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    o2 = Adam(multi.adagcn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    ls, lt = shard_batch(bs, rank, world), shard_batch(bt, rank, world)
+    glo, ghi = group.block(61)
+    for step in range(2):
+        torch.manual_seed(100 + step); torch.cuda.manual_seed(100 + step)
+        l1, sl1, _, _ = single.train_step(bs, bt, o1)
+        torch.manual_seed(100 + step); torch.cuda.manual_seed(100 + step)
+        l2, sl2, _, _ = multi.train_step(ls, lt, o2)
+        errs = {"loss": rel(l2, l1), "source_logits": rel(sl2, sl1[glo:ghi]),
+                "encoder": max(rel(p, q) for p, q in zip(multi.adagcn.parameters(), single.adagcn.parameters())),
+                "critic": max(rel(p, q) for p, q in zip(multi.discriminator.parameters(),
+                                                         single.discriminator.parameters()))}
+        ok &= max(errs.values()) < 5e-4
+        if rank == 0:
+            print(f"AdaGCN graph DP step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -61,3 +61,54 @@ def test_autograd_collectives_world_size_2():
     for r in range(2):
         dl, dg, rows_ok = out[r]
         assert dl < 1e-5 and dg < 1e-5 and rows_ok
+
+
+def _gather_worker(rank, world, port, out):
+    from pygda_b200.dist import AllGatherRows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    full = torch.randn(7, 3)
+    w = torch.randn(3, requires_grad=True)
+    lo, hi = block_range(7, world, rank)                       # blocks of 4 and 3 rows
+    enc = AllGatherRows.apply(full[lo:hi] * w, None)
+    loss = (enc.mean(0) ** 2).sum() + enc[2].sum() * enc[5].sum()     # replicated on every rank, couples the blocks
+    loss.backward()
+    allreduce_grads([w])
+    w2 = w.detach().clone().requires_grad_(True)
+    e2 = full * w2
+    ref = (e2.mean(0) ** 2).sum() + e2[2].sum() * e2[5].sum()
+    ref.backward()
+    out[rank] = (torch.equal(enc.detach(), e2.detach()), float((loss - ref).abs()), float((w.grad - w2.grad).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_all_gather_rows_world_size_2():
+    """The replicated-loss contract of the data-parallel graph-level path (models/dist_adagcn.py)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, 29537, out), nprocs=2, join=True)
+    for r in range(2):
+        same, dl, dg = out[r]
+        assert same and dl < 1e-5 and dg < 1e-5
+
+
+def test_shard_batch_splits_graphs_contiguously():
+    from pygda_b200.data import Batch
+    from pygda_b200.dist import shard_batch
+    from pygda_b200.synthetic import graph_dataset
+    ds = graph_dataset(11, 6, 2.0, 4, 2, seed=3)
+    full = Batch.from_data_list(ds)
+    for world in (1, 2, 3, 4):
+        got_x, got_y, edges = [], [], 0
+        for rank in range(world):
+            sh = shard_batch(full, rank, world)
+            lo, hi = block_range(11, world, rank)
+            assert len(sh) == hi - lo
+            ref = Batch.from_data_list(ds[lo:hi]) if hi > lo else None
+            if ref is not None:
+                assert torch.equal(sh.x, ref.x) and torch.equal(sh.y, ref.y) and torch.equal(sh.batch, ref.batch)
+                assert torch.equal(sh.edge_index, ref.edge_index) and torch.equal(sh.ptr, ref.ptr)
+            got_x.append(sh.x); got_y.append(sh.y); edges += sh.edge_index.size(1)
+        assert torch.equal(torch.cat(got_x), full.x) and torch.equal(torch.cat(got_y), full.y)
+        assert edges == full.edge_index.size(1)

@@ -1,0 +1,71 @@
+"""The steps either side of the hot path on the device: graph-batch collation
+(gda_collate_graphs) against Batch.from_data_list, and the fused argmax + confusion count
+(gda_argmax_confusion) against torch.argmax + sklearn's f1_score, which is what the reference calls
+(pygda/models/a2gnn.py:328-329, pygda/metrics/metrics.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_collation_equals_from_data_list():
+    from pygda_b200.data import Batch, DataLoader, DeviceGraphDataset
+    from pygda_b200.synthetic import graph_dataset
+    ds = graph_dataset(200, 30, 2.05, 14, 2, seed=0)
+    res = DeviceGraphDataset(ds, "cuda:0")
+    g = torch.Generator().manual_seed(1)
+    for ids in ([0], [199, 0, 57], torch.randperm(200, generator=g)[:64].tolist(), list(range(200))):
+        got = res.collate(ids)
+        ref = Batch.from_data_list([ds[i] for i in ids])
+        assert torch.equal(got.x.cpu(), ref.x) and torch.equal(got.edge_index.cpu(), ref.edge_index)   # bit-exact
+        assert torch.equal(got.y.cpu(), ref.y) and torch.equal(got.batch.cpu(), ref.batch)
+        assert torch.equal(got.ptr.cpu(), ref.ptr) and len(got) == len(ref) == len(ids)
+    # the loader: same shuffle order as the host path for the same CPU seed
+    torch.manual_seed(3)
+    host = [b for b in DataLoader(ds, batch_size=64, shuffle=True)]
+    torch.manual_seed(3)
+    dev = [b for b in DataLoader(ds, batch_size=64, shuffle=True, device="cuda:0")]
+    assert len(host) == len(dev) == 4
+    for h, d in zip(host, dev):
+        assert d.x.is_cuda and torch.equal(d.x.cpu(), h.x) and torch.equal(d.edge_index.cpu(), h.edge_index)
+        assert torch.equal(d.y.cpu(), h.y)
+
+
+@pytest.mark.parametrize("rows,c", [(1, 2), (1000, 5), (100_000, 5), (5000, 64)])
+def test_confusion_counts_and_f1_match_sklearn(rows, c):
+    from sklearn.metrics import confusion_matrix, f1_score
+    from pygda_b200.metrics import confusion_from_logits, macro_f1_from_logits, micro_f1_from_logits
+    g = torch.Generator().manual_seed(rows + c)
+    logits = torch.randn(rows, c, generator=g)
+    logits[::7] = logits[::7].round()                       # ties: the first maximal index wins
+    labels = torch.randint(max(c - 1, 1), (rows,), generator=g)      # the last class never occurs as a label
+    cm, pred = confusion_from_logits(labels.cuda(), logits.cuda(), return_pred=True)
+    ref_pred = logits.argmax(dim=1)
+    assert torch.equal(pred.cpu(), ref_pred)
+    ref_cm = torch.from_numpy(confusion_matrix(labels.numpy(), ref_pred.numpy(), labels=list(range(c))))
+    assert torch.equal(cm, ref_cm)
+    assert abs(micro_f1_from_logits(labels.cuda(), logits.cuda())
+               - f1_score(labels.numpy(), ref_pred.numpy(), average="micro")) < 1e-12
+    assert abs(macro_f1_from_logits(labels.cuda(), logits.cuda())
+               - f1_score(labels.numpy(), ref_pred.numpy(), average="macro")) < 1e-12
+
+
+def test_bad_label_is_reported():
+    from pygda_b200.metrics import confusion_from_logits
+    with pytest.raises(ValueError):
+        confusion_from_logits(torch.tensor([0, 7]).cuda(), torch.randn(2, 5).cuda())
+
+
+def test_graph_mode_fit_uses_resident_dataset():
+    from pygda_b200.data import DeviceGraphDataset
+    from pygda_b200.models import AdaGCN
+    from pygda_b200.synthetic import graph_dataset
+    src = graph_dataset(96, 30, 2.05, 14, 2, seed=0)
+    tgt = graph_dataset(96, 39, 3.7, 14, 2, seed=1)
+    torch.manual_seed(0)
+    model = AdaGCN(in_dim=14, hid_dim=32, num_classes=2, mode="graph", num_layers=2, lr=0.01, epoch=2, batch_size=32,
+                   device="cuda:0", verbose=2)
+    model.fit(src, tgt)
+    assert isinstance(model.source_loader.resident, DeviceGraphDataset)
+    logits, labels = model.predict(None)
+    assert logits.shape == (96, 2) and labels.shape == (96,) and torch.isfinite(logits).all()

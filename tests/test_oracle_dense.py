@@ -96,3 +96,16 @@ def test_grad_reverse():
     x = torch.randn(4, 3, requires_grad=True)
     ONN.GradReverse.apply(x, 0.25).sum().backward()
     assert torch.allclose(x.grad, torch.full_like(x, -0.25))
+
+
+def test_f1_from_confusion_equals_sklearn():
+    """Host half of the device-side training score (pygda_b200/metrics): sklearn's micro / macro F1 from counts."""
+    from sklearn.metrics import confusion_matrix, f1_score
+    from pygda_b200.metrics import f1_from_confusion
+    g = torch.Generator().manual_seed(0)
+    for c, present in ((2, 2), (5, 5), (7, 4)):              # (7, 4): three classes absent from labels AND predictions
+        y = torch.randint(present, (500,), generator=g)
+        p = torch.randint(present, (500,), generator=g)
+        cm = torch.from_numpy(confusion_matrix(y.numpy(), p.numpy(), labels=list(range(c))))
+        for avg in ("micro", "macro"):
+            assert abs(f1_from_confusion(cm, avg) - f1_score(y.numpy(), p.numpy(), average=avg)) < 1e-12
