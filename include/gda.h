@@ -308,6 +308,27 @@ int gda_laplacian_finish_f32(const float* g, const float* u_in, const float* u_o
                              const float* in_deg, int64_t N, int H, float* loss, float* df, void* workspace,
                              int64_t workspace_bytes, gda_stream_t stream);
 
+/* ------------------------------------------------- PPMI graph --
+ * gda_ppmi_create replaces PPMIConv.norm up to the PPMI scores (pygda/nn/ppmi_conv.py:98-172): undirected
+ * de-duplicated adjacency, `rounds` (reference: 40, :134) random walks of random length in [1, path_len] from
+ * every node that has an edge, visit counters -> probabilities -> column sums ->
+ * ppmi = max(log(p / colsum * #visited / path_len), 0), one weighted edge (start, visited) per visited pair
+ * (zero scores kept, as the reference keeps them).  Edges come out sorted by (start, visited).  The symmetric
+ * normalisation with remaining self loops (:174-184) is gda_graph_create(flags = SELF_LOOPS | NORM_SYM_ROW,
+ * edge_weight = these scores).  The walks use the library's counter hash (np.random cannot be reproduced):
+ * same seed, same graph.  gda_ppmi_walks exports the walks themselves, int32 [rounds, N, path_len], -1 past a
+ * walk's length or for nodes without an edge (tests).  counts_out (may be NULL): visit count per edge.
+ * Errors: GDA_E_INDEX for ids outside [0, N). */
+typedef struct gda_wedges gda_wedges_t;
+int gda_ppmi_create(const int64_t* edge_index, int64_t E, int64_t N, int path_len, int rounds, uint64_t seed,
+                    gda_stream_t stream, gda_wedges_t** out);
+int gda_ppmi_walks(const int64_t* edge_index, int64_t E, int64_t N, int path_len, int rounds, uint64_t seed,
+                   int32_t* walks_out /* [rounds, N, path_len] */, gda_stream_t stream);
+int64_t gda_wedges_size(const gda_wedges_t* edges);
+int gda_wedges_export(const gda_wedges_t* edges, int64_t* edge_index_out /* [2, M] */, float* weight_out /* [M] */,
+                      int32_t* counts_out /* [M] or NULL */, gda_stream_t stream);
+int gda_wedges_destroy(gda_wedges_t* edges);
+
 /* ------------------------------------------- either side of the path --
  * gda_collate_graphs: graph-mode mini-batch collation on the device -- what PyG's
  * DataLoader / Batch.from_data_list yields for `DataLoader(dataset, batch_size, shuffle=True)`

@@ -145,11 +145,11 @@ class UDAGCN:
     :277-293).  Note the encoder's dropout layers are always active (oracle/nn.py)."""
 
     def __init__(self, in_dim, hid_dim, num_classes, mode="node", num_layers=2, adv_dim=40,
-                 weight_decay=3e-3, lr=4e-3, epoch=300, act=F.relu, **kwargs):
+                 weight_decay=3e-3, lr=4e-3, epoch=300, act=F.relu, ppmi=False, **kwargs):
         import itertools
         self.mode, self.epoch = mode, epoch
         self.udagcn = ONN.UDAGCNBase(in_dim, hid_dim, num_classes, num_layers=num_layers, act=act,
-                                     ppmi=False, adv_dim=adv_dim)
+                                     ppmi=ppmi, adv_dim=adv_dim)
         params = itertools.chain(*[m.parameters() for m in self.udagcn.models])
         self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
 

@@ -153,6 +153,27 @@ class CachedGCNConv(nn.Module):
         return out
 
 
+class PPMIConv(CachedGCNConv):
+    """pygda/nn/ppmi_conv.py:8-184: ``CachedGCNConv`` whose cached graph is the PPMI graph of random walks
+    (oracle/ppmi.py restates ``norm``; ``np.random`` is consumed in the reference's order)."""
+
+    def __init__(self, in_channels, out_channels, weight=None, bias=None, improved=False, use_bias=True,
+                 path_len=5, **kwargs):
+        super().__init__(in_channels, out_channels, weight, bias, improved, use_bias)
+        self.path_len = path_len
+
+    def forward(self, x, edge_index, cache_name="default_cache", edge_weight=None):
+        from . import ppmi as OP
+        x = torch.matmul(x, self.weight)                                   # cached_gcn_conv.py:130
+        if cache_name not in self.cache_dict:                              # :132-136 -> PPMIConv.norm
+            self.cache_dict[cache_name] = OP.ppmi_norm(edge_index, x.size(0), self.path_len, self.improved)
+        edge_index, norm = self.cache_dict[cache_name]
+        out = P.propagate(edge_index, x, norm)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
 class Attention(nn.Module):
     """pygda/nn/attention.py:6-55."""
 
@@ -173,8 +194,9 @@ class UDAGCNEncoder(nn.Module):
     Python list in the reference (:47) so it is never switched to eval mode --
     reproduced here."""
 
-    def __init__(self, in_dim, hid_dim, num_layers=3, base_model=None, act=F.relu):
+    def __init__(self, in_dim, hid_dim, num_layers=3, base_model=None, act=F.relu, gnn_type="gcn", **kwargs):
         super().__init__()
+        cls = PPMIConv if gnn_type == "ppmi" else CachedGCNConv            # udagcn_base.py:51
         if base_model is None:
             weights, biases = [None] * num_layers, [None] * num_layers
         else:
@@ -183,9 +205,9 @@ class UDAGCNEncoder(nn.Module):
         self.dropout_layers = [nn.Dropout(0.1) for _ in weights]
         self.act = act
         self.conv_layers = nn.ModuleList()
-        self.conv_layers.append(CachedGCNConv(in_dim, hid_dim, weight=weights[0], bias=biases[0]))
+        self.conv_layers.append(cls(in_dim, hid_dim, weight=weights[0], bias=biases[0], **kwargs))
         for i in range(1, num_layers):
-            self.conv_layers.append(CachedGCNConv(hid_dim, hid_dim, weight=weights[i], bias=biases[i]))
+            self.conv_layers.append(cls(hid_dim, hid_dim, weight=weights[i], bias=biases[i], **kwargs))
 
     def forward(self, x, edge_index, cache_name):
         for i, conv in enumerate(self.conv_layers):
@@ -197,25 +219,34 @@ class UDAGCNEncoder(nn.Module):
 
 
 class UDAGCNBase(nn.Module):
-    """pygda/nn/udagcn_base.py:92-267 with ``ppmi=False`` (the only
-    configuration in scope)."""
+    """pygda/nn/udagcn_base.py:92-267 (``ppmi=True``: a second, weight-sharing encoder over PPMIConv layers
+    fused with the first by ``Attention``)."""
 
     def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0.1,
                  act=F.relu, ppmi=False, adv_dim=40, **kwargs):
         super().__init__()
-        assert not ppmi, "oracle restates the ppmi=False path only"
         self.ppmi = ppmi
         self.encoder = UDAGCNEncoder(in_dim, hid_dim, num_layers=num_layers, act=act)
+        if ppmi:                                                           # udagcn_base.py:152-153
+            self.ppmi_encoder = UDAGCNEncoder(in_dim, hid_dim, num_layers=num_layers, base_model=self.encoder,
+                                              gnn_type="ppmi", path_len=10)
         self.cls_model = nn.Sequential(nn.Linear(hid_dim, num_classes))
         self.domain_model = nn.Sequential(
             nn.Linear(hid_dim, adv_dim), nn.ReLU(), nn.Dropout(0.1), nn.Linear(adv_dim, 2))
         self.att_model = Attention(hid_dim)
         self.models = [self.encoder, self.cls_model, self.domain_model]
+        if ppmi:                                                           # :168-169
+            self.models.extend([self.ppmi_encoder, self.att_model])
         self.loss_func = nn.CrossEntropyLoss()
 
-    def encode(self, data, cache_name, mask=None):
+    def encode(self, data, cache_name, mask=None):                         # :235-267
         out = self.encoder(data.x, data.edge_index, cache_name)
-        return out if mask is None else out[mask]
+        out = out if mask is None else out[mask]
+        if self.ppmi:
+            pp = self.ppmi_encoder(data.x, data.edge_index, cache_name)
+            pp = pp if mask is None else pp[mask]
+            return self.att_model([out, pp])
+        return out
 
 
 class GRADEBase(nn.Module):

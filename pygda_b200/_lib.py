@@ -73,6 +73,11 @@ SIGNATURES = {
     "gda_row_scale_rsqrt_f32": (i32, [vp, i64, vp, vp, i64, i32, vp]),
     "gda_laplacian_workspace_bytes": (i64, []),
     "gda_laplacian_finish_f32": (i32, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp]),
+    "gda_ppmi_create": (i32, [vp, i64, i64, i32, i32, u64, vp, C.POINTER(vp)]),
+    "gda_ppmi_walks": (i32, [vp, i64, i64, i32, i32, u64, vp, vp]),
+    "gda_wedges_size": (i64, [vp]),
+    "gda_wedges_export": (i32, [vp, vp, vp, vp, vp]),
+    "gda_wedges_destroy": (i32, [vp]),
     "gda_collate_graphs": (i32, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
     "gda_argmax_confusion": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),

@@ -3,6 +3,7 @@ from .reverse_layer import GradReverse
 from .prop_gcn_conv import PropGCNConv, GCNConv, gcn_norm
 from .a2gnn_base import A2GNNBase
 from .cached_gcn_conv import CachedGCNConv
+from .ppmi_conv import PPMIConv
 from .attention import Attention
 from .udagcn_base import UDAGCNBase
 from .grade_base import GRADEBase
@@ -10,5 +11,5 @@ from .adagcn_base import AdaGCNBase
 from .gnn_base import GNNBase
 from .gat_conv import GATConv
 
-__all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "Attention",
+__all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "PPMIConv", "Attention",
            "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv"]

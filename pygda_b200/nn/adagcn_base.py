@@ -1,25 +1,26 @@
 """AdaGCNBase -- drop-in for pygda/nn/adagcn_base.py:9-181: ``GNN`` encoder (stock ``GCNConv`` stack,
 act + Dropout between layers, ``global_mean_pool`` in graph mode) + ``cls_model`` Linear.
-``gnn_type='ppmi'`` needs the PPMI graph builder and is outside the accelerated path
-(SURVEY.md section 8 a9)."""
+``gnn_type='ppmi'`` swaps in ``PPMIConv`` layers (adagcn_base.py:53-57; PPMI graph built on the GPU)."""
 import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
 from .layers import Linear
+from .ppmi_conv import PPMIConv
 from .prop_gcn_conv import GCNConv
 
 
 class GNN(nn.Module):
     def __init__(self, in_dim, hid_dim, gnn_type='gcn', num_layers=3, act=F.relu, dropout=0.1, **kwargs):
         super().__init__()
-        if gnn_type != 'gcn':
-            raise NotImplementedError("only gnn_type='gcn' is on the accelerated path (PPMI: SURVEY.md 8 a9)")
         self.gnn_type, self.act, self.num_layers = gnn_type, act, num_layers
+        # adagcn_base.py:48-57: 'gcn' -> stock GCNConv, anything else -> PPMIConv (whose graph is cached under
+        # "default_cache" forever -- in graph mode the first batch's PPMI graph is re-used, as in the reference)
+        conv_cls = GCNConv if gnn_type == 'gcn' else PPMIConv
         self.conv_layers = nn.ModuleList()
-        self.conv_layers.append(GCNConv(in_dim, hid_dim))
+        self.conv_layers.append(conv_cls(in_dim, hid_dim))
         for _ in range(1, num_layers):
-            self.conv_layers.append(GCNConv(hid_dim, hid_dim))
+            self.conv_layers.append(conv_cls(hid_dim, hid_dim))
         self.dropout = nn.Dropout(dropout)          # holds p and the train/eval flag; applied fused below
 
     def forward(self, x, edge_index, batch, mode='node'):

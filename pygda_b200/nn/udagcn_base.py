@@ -6,24 +6,23 @@ they are never registered and stay in training mode even during ``predict``; rep
 (``ops.act_dropout(..., training=True)``).  The ctor's ``dropout`` argument is ignored by the
 reference (:136-151) and here.
 
-``ppmi=True`` needs the PPMI graph builder (pygda/nn/ppmi_conv.py:56-184: 40 rounds of Python
-random walks, hours at benchmark scale), which is out of scope; it
-raises here.  Its consumer -- a weighted aggregation -- is ``CachedGCNConv(edge_weight=...)``."""
+``ppmi=True`` (the reference's default) adds a second, weight-sharing encoder over ``PPMIConv`` layers
+(path_len 10, :153) fused with the first by ``Attention`` (:262-264); its PPMI graphs are built on the GPU
+(pygda_b200/nn/ppmi_conv.py)."""
 import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
 from .attention import Attention
 from .cached_gcn_conv import CachedGCNConv
+from .ppmi_conv import PPMIConv
 from .layers import Linear, ReLUDropout
 
 
 class GNN(nn.Module):
     def __init__(self, in_dim, hid_dim, gnn_type='gcn', num_layers=3, base_model=None, act=F.relu, **kwargs):
         super().__init__()
-        if gnn_type == 'ppmi':
-            raise NotImplementedError("PPMI graph construction is outside the accelerated path "
-                                      "(SURVEY.md section 8 a9); use ppmi=False")
+        model_cls = PPMIConv if gnn_type == 'ppmi' else CachedGCNConv                   # :51
         if base_model is None:
             weights, biases = [None] * num_layers, [None] * num_layers
         else:
@@ -32,9 +31,9 @@ class GNN(nn.Module):
         self.gnn_type, self.act = gnn_type, act
         self.dropout_p = [0.1 for _ in weights]              # the unregistered nn.Dropout(0.1) list
         self.conv_layers = nn.ModuleList()
-        self.conv_layers.append(CachedGCNConv(in_dim, hid_dim, weight=weights[0], bias=biases[0], **kwargs))
+        self.conv_layers.append(model_cls(in_dim, hid_dim, weight=weights[0], bias=biases[0], **kwargs))
         for idx in range(1, num_layers):
-            self.conv_layers.append(CachedGCNConv(hid_dim, hid_dim, weight=weights[idx], bias=biases[idx], **kwargs))
+            self.conv_layers.append(model_cls(hid_dim, hid_dim, weight=weights[idx], bias=biases[idx], **kwargs))
 
     def forward(self, x, edge_index, cache_name):
         for i, conv_layer in enumerate(self.conv_layers):

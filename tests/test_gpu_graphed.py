@@ -60,7 +60,9 @@ def test_replay_equals_eager_steps(adv):
         assert_close(s1, s0, 1e-5, f"source logits step {i}")
         assert_close(t1, t0, 1e-5, f"target logits step {i}")
     for p, q in zip(est2.a2gnn.parameters(), eager_params):
-        assert_close(p, q, 1e-4, "weights after replays")
+        # Adam divides by sqrt(v): where a gradient element is ~0 the last-bit differences of the atomically
+        # accumulated reductions are amplified to a visible fraction of lr (same bar as __graft_entry__.smoke)
+        assert_close(p, q, 1e-3, "weights after replays")
 
 
 def test_replays_draw_fresh_dropout_masks_and_indices():

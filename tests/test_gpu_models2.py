@@ -64,8 +64,15 @@ def test_adagcn_graph_level_fit_predict():
     model.fit(src, tgt)
     logits, labels = model.predict(None)
     assert logits.shape == (64, 2) and labels.shape == (64,)
-    with pytest.raises(NotImplementedError):
-        AdaGCN(in_dim=14, hid_dim=8, num_classes=2, gnn_type="ppmi", device="cuda:0").init_model()
+    # gnn_type='ppmi' (adagcn_base.py:53-57): PPMIConv layers, node level
+    from pygda_b200.nn import PPMIConv
+    from pygda_b200.synthetic import domain_pair
+    s2, t2 = domain_pair(600, 4000, 14, 2, seed=3)
+    pm = AdaGCN(in_dim=14, hid_dim=8, num_classes=2, num_layers=2, gnn_type="ppmi", epoch=1, device="cuda:0", verbose=0)
+    pm.fit(s2, t2)
+    assert all(isinstance(c, PPMIConv) for c in pm.adagcn.encoder.conv_layers)
+    out, _ = pm.predict(t2)
+    assert out.shape == (600, 2) and torch.isfinite(out).all()
 
 
 def test_gnn_fit_predict_uses_data():
