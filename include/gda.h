@@ -308,6 +308,16 @@ int gda_laplacian_finish_f32(const float* g, const float* u_in, const float* u_o
                              const float* in_deg, int64_t N, int H, float* loss, float* df, void* workspace,
                              int64_t workspace_bytes, gda_stream_t stream);
 
+/* ------------------------------------------------ two-view attention fusion --
+ * Attention.forward (pygda/nn/attention.py:52-55) for the two views UDAGCN(ppmi=True) fuses
+ * (pygda/nn/udagcn_base.py:262-264): out = a0 x0 + a1 x1, (a0, a1) = softmax(w.x0 + b, w.x1 + b).
+ * x0, x1, out, gout, g0, g1: [N, H] contiguous; w [H]; b device scalar (may be NULL); a0_out / a0 [N] saved
+ * for the backward.  The backward OVERWRITES g0, g1 (either may be NULL) and dw [H] (may be NULL); db = 0. */
+int gda_attention2_fwd(const float* x0, const float* x1, int64_t N, int H, const float* w, const float* b,
+                       float* out, float* a0_out, gda_stream_t stream);
+int gda_attention2_bwd(const float* x0, const float* x1, int64_t N, int H, const float* w, const float* a0,
+                       const float* gout, float* g0, float* g1, float* dw, gda_stream_t stream);
+
 /* ------------------------------------------------- PPMI graph --
  * gda_ppmi_create replaces PPMIConv.norm up to the PPMI scores (pygda/nn/ppmi_conv.py:98-172): undirected
  * de-duplicated adjacency, `rounds` (reference: 40, :134) random walks of random length in [1, path_len] from

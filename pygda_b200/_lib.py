@@ -73,6 +73,8 @@ SIGNATURES = {
     "gda_row_scale_rsqrt_f32": (i32, [vp, i64, vp, vp, i64, i32, vp]),
     "gda_laplacian_workspace_bytes": (i64, []),
     "gda_laplacian_finish_f32": (i32, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp]),
+    "gda_attention2_fwd": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp]),
+    "gda_attention2_bwd": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
     "gda_ppmi_create": (i32, [vp, i64, i64, i32, i32, u64, vp, C.POINTER(vp)]),
     "gda_ppmi_walks": (i32, [vp, i64, i64, i32, i32, u64, vp, vp]),
     "gda_wedges_size": (i64, [vp]),

@@ -645,6 +645,40 @@ class MMDFn(torch.autograd.Function):
         return gs, gt, None, None, None, None
 
 
+class Attention2Fn(torch.autograd.Function):
+    """out = a0 x0 + a1 x1 with (a0, a1) = softmax(w.x0 + b, w.x1 + b): Attention.forward
+    (pygda/nn/attention.py:52-55) for two views as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias):
+        x0, x1 = _f32c(x0), _f32c(x1)
+        w = _f32c(weight).reshape(-1)
+        n, h = x0.shape
+        if x1.shape != x0.shape or w.numel() != h:
+            raise ValueError("attention: the two views and the weight must agree in width")
+        out = torch.empty_like(x0)
+        a0 = torch.empty(n, dtype=torch.float32, device=x0.device)
+        gda.attention2_fwd(_p(x0), _p(x1), n, h, _p(w), _p(bias), _p(out), _p(a0), _stream())
+        ctx.save_for_backward(x0, x1, w, a0)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x0, x1, w, a0 = ctx.saved_tensors
+        go = _f32c(go)
+        n, h = x0.shape
+        g0 = torch.empty_like(x0) if ctx.needs_input_grad[0] else None
+        g1 = torch.empty_like(x1) if ctx.needs_input_grad[1] else None
+        dw = torch.empty(h, dtype=torch.float32, device=x0.device) if ctx.needs_input_grad[2] else None
+        gda.attention2_bwd(_p(x0), _p(x1), n, h, _p(w), _p(a0), _p(go), _p(g0), _p(g1), _p(dw), _stream())
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[3]:      # the scores share the bias: softmax is shift invariant
+            db = torch.empty(1, dtype=torch.float32, device=x0.device)
+            gda.fill_f32(_p(db), 1, 0.0, _stream())
+        return g0, g1, (dw.view(1, h) if dw is not None else None), db
+
+
 class SegmentMeanFn(torch.autograd.Function):
     """global_mean_pool over a sorted batch vector given as ptr [G+1]."""
 
