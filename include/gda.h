@@ -194,6 +194,25 @@ int     gda_gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K,
                         float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
                         gda_stream_t stream);
 
+/* --------------------------------------- bf16 feature path (BASELINE config 3) --
+ * "UDAGCN ... hid=256, bf16": activations and input features stored in bf16, parameters and every accumulation
+ * in fp32.  gda_gemm_bf16: C = op(A) op(B) from plain bf16 operands on the tcgen05 kernel (ONE UMMA per K step
+ * instead of the three of gda_gemm_bf16x3, half the operand bytes), C fp32 (weight gradients; split-K workspace
+ * of gda_gemm_bf16_workspace_bytes) or bf16 (activations; out_bf16 = 1, ldc in bf16 elements).  Same shape rules
+ * as gda_gemm_bf16x3.  The aggregation on bf16 rows is gda_spmm_bf16.  Casts, act/dropout (same counter-hash
+ * masks as the fp32 kernels) and bias-gradient column sums on bf16 follow. */
+int64_t gda_gemm_bf16_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_bf16);
+int gda_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                  const void* B, int64_t ldb, void* C, int64_t ldc, int out_bf16, void* workspace,
+                  int64_t workspace_bytes, gda_stream_t stream);
+int gda_cast_f32_bf16(const float* x, void* y, int64_t n, gda_stream_t stream);
+int gda_cast_bf16_f32(const void* x, float* y, int64_t n, gda_stream_t stream);
+int gda_act_dropout_bf16_fwd(const void* x, void* y, int64_t n, int act, float dropout_p, uint64_t seed,
+                             const uint64_t* seed_offset, gda_stream_t stream);
+int gda_act_dropout_bf16_bwd(const void* gy, const void* y, void* gx, int64_t n, int act, float dropout_p,
+                             uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream);
+int gda_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ldx, float* out, gda_stream_t stream);
+
 /* ------------------------------------------------------------ elementwise --
  * y = dropout(act(x + bias)) and its backward; act: 0 none, 1 relu.  The keep
  * mask is regenerated from (seed, element index): nothing is stored.

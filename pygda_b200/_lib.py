@@ -52,6 +52,13 @@ SIGNATURES = {
     "gda_gemm_bf16x3_supported": (i32, [i64, i64, i64, i64, i64]),
     "gda_gemm_bf16x3_workspace_bytes": (i64, [i64, i64, i64]),
     "gda_gemm_bf16x3": (i32, [i32, i32, i64, i64, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
+    "gda_gemm_bf16_workspace_bytes": (i64, [i64, i64, i64, i32]),
+    "gda_gemm_bf16": (i32, [i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp]),
+    "gda_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
+    "gda_cast_bf16_f32": (i32, [vp, vp, i64, vp]),
+    "gda_act_dropout_bf16_fwd": (i32, [vp, vp, i64, i32, f32, u64, vp, vp]),
+    "gda_act_dropout_bf16_bwd": (i32, [vp, vp, vp, i64, i32, f32, u64, vp, vp]),
+    "gda_colsum_bf16": (i32, [vp, i64, i64, i64, vp, vp]),
     "gda_bias_act_dropout_fwd": (i32, [vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_bwd": (i32, [vp, vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_rep_fwd": (i32, [vp, vp, vp, i64, i64, i32, i32, f32, u64, vp, vp]),

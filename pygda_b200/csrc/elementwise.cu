@@ -4,6 +4,8 @@
 //   softmax entropy fwd+bwd            pygda/models/udagcn.py:193-199
 //   segment mean (global_mean_pool)    pygda/nn/a2gnn_base.py:141, adagcn_base.py:94
 //   Adam                               pygda/models/a2gnn.py:292-296,317-319 (torch.optim.Adam)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gda {
@@ -107,6 +109,51 @@ __global__ void k_bias_act_dropout_bwd(const float* __restrict__ gy0, const floa
       if (V == 4) *reinterpret_cast<float4*>(gx + i) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
       else gx[i] = acc[0];
     }
+  }
+}
+
+// ---- bf16 feature path (BASELINE config 3): casts, act/dropout and column sums on bf16 activations ----
+__global__ void k_cast_f32_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+__global__ void k_cast_bf16_f32(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+// y = dropout(act(x)) on bf16; same (seed, element index) mask as the fp32 kernels and the aggregation epilogue
+__global__ void k_act_dropout_bf16_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, int act, uint32_t thresh,
+                                       float scale, uint64_t seed, const uint64_t* __restrict__ seed_offset, int do_drop) {
+  if (do_drop && seed_offset) seed += __ldg(seed_offset);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __bfloat162float(x[i]);
+    if (act == 1) v = fmaxf(v, 0.f);
+    if (do_drop) v = dropout_keep(seed, static_cast<uint64_t>(i), thresh) ? v * scale : 0.f;
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void k_act_dropout_bf16_bwd(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
+                                       __nv_bfloat16* __restrict__ gx, int64_t n, int act, uint32_t thresh, float scale,
+                                       uint64_t seed, const uint64_t* __restrict__ seed_offset, int do_drop) {
+  if (do_drop && seed_offset) seed += __ldg(seed_offset);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = __bfloat162float(gy[i]);
+    if (do_drop) g = dropout_keep(seed, static_cast<uint64_t>(i), thresh) ? g * scale : 0.f;
+    if (act == 1 && !(__bfloat162float(y[i]) > 0.f)) g = 0.f;
+    gx[i] = __float2bfloat16_rn(g);
+  }
+}
+
+__global__ void k_colsum_bf16(const __nv_bfloat16* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                              float* __restrict__ out, int64_t rows_per_block) {
+  const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += __bfloat162float(x[r * ldx + c]);
+    atomicAdd(out + c, s);
   }
 }
 
@@ -500,6 +547,66 @@ int gda_combine_scalars(int n, const float* const* terms, const float* weights, 
     a.t[i] = terms[i]; a.w[i] = weights[i];
   }
   k_combine<<<1, 1, 0, as_stream(stream)>>>(a, n, out);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_cast_f32_bf16(const float* x, void* y, int64_t n, gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0, "gda_cast_f32_bf16: negative size");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(x && y, "gda_cast_f32_bf16: NULL pointer");
+  k_cast_f32_bf16<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(x, static_cast<__nv_bfloat16*>(y), n);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_cast_bf16_f32(const void* x, float* y, int64_t n, gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0, "gda_cast_bf16_f32: negative size");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(x && y, "gda_cast_bf16_f32: NULL pointer");
+  k_cast_bf16_f32<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), y, n);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_act_dropout_bf16_fwd(const void* x, void* y, int64_t n, int act, float dropout_p, uint64_t seed,
+                             const uint64_t* seed_offset, gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0 && (act == 0 || act == 1) && dropout_p >= 0.f && dropout_p < 1.f, "gda_act_dropout_bf16_fwd: bad argument");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(x && y, "gda_act_dropout_bf16_fwd: NULL pointer");
+  k_act_dropout_bf16_fwd<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, act, dropout_threshold(dropout_p),
+      1.f / (1.f - dropout_p), seed, seed_offset, dropout_p > 0.f ? 1 : 0);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_act_dropout_bf16_bwd(const void* gy, const void* y, void* gx, int64_t n, int act, float dropout_p, uint64_t seed,
+                             const uint64_t* seed_offset, gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0 && (act == 0 || act == 1) && dropout_p >= 0.f && dropout_p < 1.f, "gda_act_dropout_bf16_bwd: bad argument");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(gy && gx && (act == 0 || y), "gda_act_dropout_bf16_bwd: NULL pointer");
+  k_act_dropout_bf16_bwd<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(gy), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(gx), n, act,
+      dropout_threshold(dropout_p), 1.f / (1.f - dropout_p), seed, seed_offset, dropout_p > 0.f ? 1 : 0);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ldx, float* out, gda_stream_t stream) {
+  GDA_REQUIRE(rows >= 0 && cols >= 0 && ldx >= cols, "gda_colsum_bf16: bad size");
+  if (cols == 0) return GDA_OK;
+  GDA_REQUIRE(out != nullptr, "gda_colsum_bf16: NULL output");
+  cudaStream_t st = as_stream(stream);
+  GDA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (rows == 0) return GDA_OK;
+  GDA_REQUIRE(x != nullptr, "gda_colsum_bf16: NULL input");
+  const int64_t want = ceil_div(rows, 64);
+  const int64_t blocks = want < 16 * kNumSMs ? (want > 0 ? want : 1) : 16 * kNumSMs;
+  const int64_t rpb = ceil_div(rows, blocks);
+  const int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
+  k_colsum_bf16<<<static_cast<unsigned>(ceil_div(rows, rpb)), threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows,
+                                                                                static_cast<int>(cols), ldx, out, rpb);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

@@ -69,4 +69,17 @@ int gda_gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, con
                           workspace_bytes, gda::as_stream(stream));
 }
 
+int64_t gda_gemm_bf16_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_bf16) {
+  return gda::bf16_workspace_bytes(M, N, K, out_bf16);
+}
+
+int gda_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                  int64_t ldb, void* C, int64_t ldc, int out_bf16, void* workspace, int64_t workspace_bytes,
+                  gda_stream_t stream) {
+  GDA_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gda_gemm_bf16: negative dimension");
+  if (M == 0 || N == 0) return GDA_OK;
+  return gda::gemm_bf16(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, out_bf16, workspace, workspace_bytes,
+                        gda::as_stream(stream));
+}
+
 }  // extern "C"

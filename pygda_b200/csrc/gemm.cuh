@@ -23,6 +23,10 @@ int64_t bf16x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_lo,
                 int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc, void* ws,
                 int64_t ws_bytes, cudaStream_t st);
+// plain bf16 operands (one UMMA per K step), fp32 accumulation, C fp32 or bf16
+int64_t bf16_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_bf16);
+int gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+              int64_t ldb, void* C, int64_t ldc, int out_bf16, void* ws, int64_t ws_bytes, cudaStream_t st);
 }  // namespace gda
 
 namespace gda {

@@ -32,10 +32,13 @@ constexpr int BM = 128, BK = 64, TC_THREADS = 192;
 // the B operand for tall outputs (round-1 profile: with 128 x 128 tiles every one of 782 CTAs
 // re-read all of W through L2 -- L2 at 70 %, DRAM only 60 %); (1, 256) does the same for the A
 // operand of the weight-gradient GEMM; (1, 128) is the small-shape default.
-template <int MT, int BN_> struct TileCfg {
+// TERMS = 3: split-bf16 operands (hi, lo), three UMMAs per K step (fp32-accurate).  TERMS = 1: plain bf16
+// operands, one UMMA per K step (the bf16 feature path of BASELINE config 3) -- half the bytes per stage.
+template <int MT, int BN_, int TERMS = 3> struct TileCfg {
   static constexpr int A_BYTES = MT * BM * BK * 2;      // one of (hi, lo)
   static constexpr int B_BYTES = BN_ * BK * 2;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int PARTS = TERMS == 3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = PARTS * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = MT * BN_;
@@ -118,12 +121,13 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) 
          (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int MT, int BN>
+template <bool A_MN, bool B_MN, int MT, int BN, int TERMS = 3, bool OUT_BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
               float* __restrict__ C, int64_t ldc, int M, int N, int K, int kb_per_split, int64_t split_stride) {
-  using Cfg = TileCfg<MT, BN>;
+  using Cfg = TileCfg<MT, BN, TERMS>;
+  static_assert(TERMS == 3 || TERMS == 1, "three split terms or one plain bf16 term");
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
   static_assert(!(A_MN && MT != 1), "MN-major A uses one 128-row tile");
@@ -166,24 +170,27 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
         const uint32_t bar = full0 + 8 * stage;
         mbar_expect_tx(bar, STAGE_BYTES);
         const int k0 = (kb_begin + kb) * BK;
-        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + 2 * A_BYTES, sBl = st + 2 * A_BYTES + B_BYTES;
+        constexpr int PARTS = Cfg::PARTS;              // stage layout: Ah [Al] Bh [Bl]
+        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + PARTS * A_BYTES, sBl = sBh + B_BYTES;
         if (!A_MN) {                                   // one box 64 x (MT*128)
           tma_load_2d(sAh, &mapAh, bar, k0, m0);
-          tma_load_2d(sAl, &mapAl, bar, k0, m0);
+          if (TERMS == 3) tma_load_2d(sAl, &mapAl, bar, k0, m0);
         } else {                                       // two boxes 64(m) x 64(k)
           tma_load_2d(sAh, &mapAh, bar, m0, k0);
           tma_load_2d(sAh + 8192, &mapAh, bar, m0 + 64, k0);
-          tma_load_2d(sAl, &mapAl, bar, m0, k0);
-          tma_load_2d(sAl + 8192, &mapAl, bar, m0 + 64, k0);
+          if (TERMS == 3) {
+            tma_load_2d(sAl, &mapAl, bar, m0, k0);
+            tma_load_2d(sAl + 8192, &mapAl, bar, m0 + 64, k0);
+          }
         }
         if (!B_MN) {                                   // one box 64 x BN
           tma_load_2d(sBh, &mapBh, bar, k0, n0);
-          tma_load_2d(sBl, &mapBl, bar, k0, n0);
+          if (TERMS == 3) tma_load_2d(sBl, &mapBl, bar, k0, n0);
         } else {                                       // BN/64 boxes 64(n) x 64(k)
 #pragma unroll
           for (int i = 0; i < BN / 64; ++i) {
             tma_load_2d(sBh + i * 8192, &mapBh, bar, n0 + 64 * i, k0);
-            tma_load_2d(sBl + i * 8192, &mapBl, bar, n0 + 64 * i, k0);
+            if (TERMS == 3) tma_load_2d(sBl + i * 8192, &mapBl, bar, n0 + 64 * i, k0);
           }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -198,7 +205,7 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         const uint32_t st = tiles + stage * STAGE_BYTES;
-        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + 2 * A_BYTES, sBl = st + 2 * A_BYTES + B_BYTES;
+        const uint32_t sAh = st, sAl = st + A_BYTES, sBh = st + Cfg::PARTS * A_BYTES, sBl = sBh + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
           // K-major: +32 B per K=16 step inside the 128 B swizzle row; MN-major: +16 rows * 128 B
@@ -213,8 +220,10 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
             const uint64_t al = make_desc(sAl + mt * (BM * 128) + a_off, a_lbo, 1024u);
             const uint32_t d = tmem_base + mt * BN;
             umma_bf16(d, ah, bh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_bf16(d, ah, bl, idesc, 1u);
-            umma_bf16(d, al, bh, idesc, 1u);
+            if (TERMS == 3) {
+              umma_bf16(d, ah, bl, idesc, 1u);
+              umma_bf16(d, al, bh, idesc, 1u);
+            }
           }
         }
         umma_commit(empty0 + 8 * stage);          // frees the smem stage once these MMAs retire
@@ -232,10 +241,36 @@ k_gemm_bf16x3(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__
       const int row = m0 + mt * BM + q * 32 + lane;
       float* crow = C + blockIdx.z * split_stride + static_cast<int64_t>(row) * ldc + n0;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0) && (ldc % 4 == 0);
+      // bf16 output (TERMS == 1 feature path): C is a __nv_bfloat16 matrix, ldc in bf16 elements, no K splits
+      __nv_bfloat16* hrow = reinterpret_cast<__nv_bfloat16*>(C) + static_cast<int64_t>(row) * ldc + n0;
+      const bool hvec_ok = ((reinterpret_cast<uintptr_t>(hrow) & 15u) == 0) && (ldc % 8 == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + c * 32, r);
+        if (OUT_BF16) {
+          if (row < M) {
+            const int col0 = n0 + c * 32;
+            if (hvec_ok && col0 + 32 <= N) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[8 * j + 2 * i]),
+                                                                  __uint_as_float(r[8 * j + 2 * i + 1]));
+                  w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(hrow + c * 32 + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) hrow[c * 32 + j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          }
+          continue;
+        }
         if (row < M) {
           const int col0 = n0 + c * 32;
           if (vec_ok && col0 + 32 <= N) {
@@ -344,22 +379,22 @@ TcPlan plan_for(bool a_mn, bool b_mn, int64_t M, int64_t N, int64_t K) {
   return p;
 }
 
-template <bool A_MN, bool B_MN, int MT, int BN_>
+template <bool A_MN, bool B_MN, int MT, int BN_, int TERMS = 3, bool OUT_BF16 = false>
 int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, int splits, int64_t split_stride, cudaStream_t st) {
-  using Cfg = TileCfg<MT, BN_>;
+  using Cfg = TileCfg<MT, BN_, TERMS>;
   static bool attr_set = false;
   if (!attr_set) {
-    GDA_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<A_MN, B_MN, MT, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
+    GDA_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<A_MN, B_MN, MT, BN_, TERMS, OUT_BF16>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int nkb = static_cast<int>(ceil_div(K, BK));
   const int kbps = static_cast<int>(ceil_div(nkb, splits));
   dim3 grid(static_cast<unsigned>(ceil_div(N, BN_)), static_cast<unsigned>(ceil_div(M, MT * BM)),
             static_cast<unsigned>(ceil_div(nkb, kbps)));
-  k_gemm_bf16x3<A_MN, B_MN, MT, BN_><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ah, al, bh, bl, C, ldc, (int)M, (int)N,
-                                                                               (int)K, kbps, split_stride);
+  k_gemm_bf16x3<A_MN, B_MN, MT, BN_, TERMS, OUT_BF16><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(
+      ah, al, bh, bl, C, ldc, (int)M, (int)N, (int)K, kbps, split_stride);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }
@@ -448,6 +483,60 @@ int gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const v
     const int kbps = static_cast<int>(ceil_div(nkb, splits));
     const int used = static_cast<int>(ceil_div(nkb, kbps));
     return splitk_reduce(static_cast<float*>(ws), used, M, N, 1.f, 0.f, C, ldc, st);
+  }
+  return GDA_OK;
+}
+
+// ---- plain bf16 operands, fp32 accumulation, fp32 or bf16 output (BASELINE config 3 feature path) ----
+int64_t bf16_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_bf16) {
+  return out_bf16 ? 0 : bf16x3_workspace_bytes(M, N, K);
+}
+
+int gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+              int64_t ldb, void* C, int64_t ldc, int out_bf16, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  GDA_REQUIRE(A && B && C, "gda_gemm_bf16: NULL pointer");
+  GDA_REQUIRE(bf16x3_shape_ok(M, N, K, lda, ldb), "gda_gemm_bf16: needs N >= 64, K >= 64 and lda, ldb multiples of 8");
+  GDA_REQUIRE(ldc >= N, "gda_gemm_bf16: ldc < N");
+  GDA_REQUIRE(reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0,
+              "gda_gemm_bf16: operands must be 16-byte aligned");
+  CUtensorMap am, bm;
+  int rc;
+  const int64_t a_in = transA ? M : K, a_out = transA ? K : M;
+  const int64_t b_in = transB ? K : N, b_out = transB ? N : K;
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  TcPlan plan = plan_for(a_mn, b_mn, M, N, K);
+  plan.bn = 128;
+  if (out_bf16) plan.splits = 1;                       // partial sums would need an fp32 detour
+  const int a_box = a_mn ? BK : plan.mt * BM, b_box = b_mn ? BK : plan.bn;
+  if ((rc = make_map(&am, A, a_in, a_out, lda, a_box)) || (rc = make_map(&bm, B, b_in, b_out, ldb, b_box))) return rc;
+  const int splits = plan.splits;
+  float* out = static_cast<float*>(C);
+  int64_t out_ld = ldc, stride = 0;
+  if (splits > 1) {
+    const int64_t need = static_cast<int64_t>(splits) * M * N * sizeof(float);
+    if (!ws || ws_bytes < need) return fail(GDA_E_WORKSPACE, "gda_gemm_bf16: workspace too small");
+    out = static_cast<float*>(ws); out_ld = N; stride = M * N;
+  }
+#define GDA_TC1_LAUNCH(AM, BM_, MTV, OB) \
+  rc = launch_tc<AM, BM_, MTV, 128, 1, OB>(am, am, bm, bm, out, out_ld, M, N, K, splits, stride, st)
+#define GDA_TC1_PICK(OB)                                                                   \
+  do {                                                                                     \
+    if (plan.mt == 2) {                                                                    \
+      if (!b_mn) GDA_TC1_LAUNCH(false, false, 2, OB); else GDA_TC1_LAUNCH(false, true, 2, OB); \
+    } else if (!a_mn && !b_mn) GDA_TC1_LAUNCH(false, false, 1, OB);                         \
+    else if (!a_mn && b_mn) GDA_TC1_LAUNCH(false, true, 1, OB);                             \
+    else if (a_mn && !b_mn) GDA_TC1_LAUNCH(true, false, 1, OB);                             \
+    else GDA_TC1_LAUNCH(true, true, 1, OB);                                                 \
+  } while (0)
+  if (out_bf16) GDA_TC1_PICK(true); else GDA_TC1_PICK(false);
+#undef GDA_TC1_PICK
+#undef GDA_TC1_LAUNCH
+  if (rc) return rc;
+  if (splits > 1) {
+    const int nkb = static_cast<int>(ceil_div(K, BK));
+    const int kbps = static_cast<int>(ceil_div(nkb, splits));
+    const int used = static_cast<int>(ceil_div(nkb, kbps));
+    return splitk_reduce(static_cast<float*>(ws), used, M, N, 1.f, 0.f, static_cast<float*>(C), ldc, st);
   }
   return GDA_OK;
 }

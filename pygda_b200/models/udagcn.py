@@ -22,11 +22,15 @@ class UDAGCN(TwoDomainLoop, BaseGDA):
         self.ppmi = ppmi
         self.adv_dim = adv_dim
         self.mode = mode
+        # pygda_b200 extension (BASELINE.json config 3, "bf16"): feature_dtype=torch.bfloat16 keeps the input
+        # features and the encoder activations in bf16 (parameters, accumulation and losses stay fp32)
+        self.feature_dtype = self.kwargs.pop('feature_dtype', None)
 
     def init_model(self, **kwargs):
+        kwargs.pop('feature_dtype', None)
         return UDAGCNBase(in_dim=self.in_dim, hid_dim=self.hid_dim, num_classes=self.num_classes,
                           num_layers=self.num_layers, dropout=self.dropout, act=self.act, ppmi=self.ppmi,
-                          adv_dim=self.adv_dim, **kwargs).to(self.device)
+                          adv_dim=self.adv_dim, feature_dtype=self.feature_dtype, **kwargs).to(self.device)
 
     def forward_model(self, source_data, target_data, alpha, epoch):
         net = self.udagcn

@@ -9,6 +9,7 @@ reference (:136-151) and here.
 ``ppmi=True`` (the reference's default) adds a second, weight-sharing encoder over ``PPMIConv`` layers
 (path_len 10, :153) fused with the first by ``Attention`` (:262-264); its PPMI graphs are built on the GPU
 (pygda_b200/nn/ppmi_conv.py)."""
+import torch
 import torch.nn.functional as F
 from torch import nn
 
@@ -45,8 +46,11 @@ class GNN(nn.Module):
 
 class UDAGCNBase(nn.Module):
     def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0.1, act=F.relu, ppmi=True,
-                 adv_dim=40, **kwargs):
+                 adv_dim=40, feature_dtype=None, **kwargs):
         super().__init__()
+        if feature_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("feature_dtype must be torch.float32 or torch.bfloat16")
+        self.bf16 = feature_dtype == torch.bfloat16        # bf16 rows through the encoders (BASELINE config 3)
         self.ppmi = ppmi
         self.encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, gnn_type='gcn', act=act, num_layers=num_layers)
         if self.ppmi:
@@ -63,13 +67,24 @@ class UDAGCNBase(nn.Module):
             self.models.extend([self.ppmi_encoder, self.att_model])
         self.loss_func = ops.softmax_cross_entropy
 
+    def _x(self, data):
+        # the input features are constant: their bf16 copy is made once per tensor (ops.bf16_cache)
+        return ops.bf16_cache.get(data.x) if self.bf16 else data.x
+
+    def _out(self, enc):
+        # heads, attention and losses run in fp32: one cast at the encoder boundary (its backward casts back)
+        return ops.CastFn.apply(enc, False) if enc.dtype == torch.bfloat16 else enc
+
     def gcn_encode(self, data, cache_name, mask=None):
-        encoded_output = self.encoder(data.x, data.edge_index, cache_name)
+        encoded_output = self._out(self.encoder(self._x(data), data.edge_index, cache_name))
+        return encoded_output if mask is None else encoded_output[mask]
+
+    def ppmi_encode(self, data, cache_name, mask=None):
+        encoded_output = self._out(self.ppmi_encoder(self._x(data), data.edge_index, cache_name))
         return encoded_output if mask is None else encoded_output[mask]
 
     def encode(self, data, cache_name, mask=None):
         gcn_output = self.gcn_encode(data, cache_name, mask)
         if self.ppmi:
-            ppmi_output = self.ppmi_encoder(data.x, data.edge_index, cache_name)
-            return self.att_model([gcn_output, ppmi_output if mask is None else ppmi_output[mask]])
+            return self.att_model([gcn_output, self.ppmi_encode(data, cache_name, mask)])
         return gcn_output

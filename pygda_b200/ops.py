@@ -33,6 +33,14 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _bf16c(t):
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"expected bfloat16, got {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError("pygda_b200 kernels run on the GPU only (no CPU fallback)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -342,11 +350,18 @@ class ActDropoutFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, act, p, seed):
+        off = dropout_rng.offset if p > 0 else None
+        if x.dtype == torch.bfloat16:                     # bf16 feature path (BASELINE config 3)
+            x = _bf16c(x)
+            y = torch.empty_like(x)
+            gda.act_dropout_bf16_fwd(_p(x), _p(y), x.numel(), act, float(p), seed, _p(off), _stream())
+            ctx.save_for_backward(y)
+            ctx.cfg = (act, float(p), seed, 0, 0, off)
+            return y
         x = _f32c(x)
         y = torch.empty_like(x)
         rows = x.shape[0] if x.dim() > 1 else 1
         cols = x.numel() // max(rows, 1)
-        off = dropout_rng.offset if p > 0 else None
         gda.bias_act_dropout_fwd(_p(x), _NULL, _p(y), rows, cols, act, float(p), seed, _p(off), _stream())
         ctx.save_for_backward(y)
         ctx.cfg = (act, float(p), seed, rows, cols, off)
@@ -356,6 +371,11 @@ class ActDropoutFn(torch.autograd.Function):
     def backward(ctx, gy):
         (y,) = ctx.saved_tensors
         act, p, seed, rows, cols, off = ctx.cfg
+        if y.dtype == torch.bfloat16:
+            gy = _bf16c(gy)
+            gx = torch.empty_like(gy)
+            gda.act_dropout_bf16_bwd(_p(gy), _p(y), _p(gx), gy.numel(), act, p, seed, _p(off), _stream())
+            return gx, None, None, None
         gy = _f32c(gy)
         gx = torch.empty_like(gy)
         gda.bias_act_dropout_bwd(_p(gy), _p(y), _p(gx), _NULL, rows, cols, act, p, seed, _p(off), _stream())
@@ -499,6 +519,123 @@ def act_dropout_pair(x, p):
 def graph_conv_act_pair(xa, xb, weight, bias, graph, k, p, relu=True, w_in_out=False):
     return PairGraphConvActFn.apply(xa, xb, weight, bias, graph, int(k), bool(w_in_out), 1 if relu else 0,
                                     float(p), next_seed() if p > 0 else 0)
+
+
+# ------------------------------------------------------------------ bf16 feature path (BASELINE config 3)
+# "UDAGCN ... hid=256, bf16": input features and activations live in bf16, parameters, accumulation, biases and
+# losses in fp32.  The layer GEMMs run as ONE tcgen05 UMMA per K step on bf16 operands (gda_gemm_bf16), the
+# aggregation gathers 2-byte rows (gda_spmm_bf16).
+def to_bf16(x):
+    x = _f32c(x)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    gda.cast_f32_bf16(_p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+def to_f32(x):
+    x = _bf16c(x)
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    gda.cast_bf16_f32(_p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+class CastFn(torch.autograd.Function):
+    """bf16 <-> fp32 boundary of the bf16 feature path; the gradient is cast the other way."""
+
+    @staticmethod
+    def forward(ctx, x, to_half):
+        ctx.to_half = to_half
+        return to_bf16(x) if to_half else to_f32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (to_f32(g) if ctx.to_half else to_bf16(g)), None
+
+
+class Bf16Cache:
+    """bf16 copies of CONSTANT fp32 tensors (the input features), keyed like SplitCache."""
+
+    def __init__(self, capacity=8):
+        self.capacity, self._d = capacity, {}
+
+    def get(self, x):
+        if x.dtype == torch.bfloat16:
+            return x
+        key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
+        hit = self._d.get(key)
+        if hit is not None:
+            return hit[0]
+        y = to_bf16(x)
+        if len(self._d) >= self.capacity:
+            self._d.pop(next(iter(self._d)))
+        self._d[key] = (y, x)
+        return y
+
+
+bf16_cache = Bf16Cache()
+
+
+def gemm_bf16(a, b, trans_a=False, trans_b=False, out_bf16=True):
+    """op(a) @ op(b) on bf16 operands, fp32 accumulation; bf16 or fp32 result."""
+    a, b = _bf16c(a), _bf16c(b)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    kb, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if k != kb:
+        raise ValueError(f"gemm inner dimensions differ: {k} vs {kb}")
+    lib = load()
+    if lib.gda_gemm_bf16x3_supported(m, n, k, a.stride(0), b.stride(0)) == 1 and \
+            a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0:
+        out = torch.empty(m, n, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a.device)
+        ws = _workspace(lib.gda_gemm_bf16_workspace_bytes(m, n, k, int(out_bf16)), a.device)
+        gda.gemm_bf16(int(trans_a), int(trans_b), m, n, k, _p(a), a.stride(0), _p(b), b.stride(0), _p(out),
+                      out.stride(0), int(out_bf16), _p(ws), ws.numel(), _stream())
+        return out
+    # shapes the tensor-core kernel does not take (tiny widths): the fp32 kernels on the same bf16 VALUES
+    out = gemm(to_f32(a), to_f32(b), trans_a=trans_a, trans_b=trans_b)
+    return to_bf16(out) if out_bf16 else out
+
+
+def colsum_bf16(x):
+    x = _bf16c(x)
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    gda.colsum_bf16(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream())
+    return out
+
+
+class GraphConvBf16Fn(torch.autograd.Function):
+    """GraphConvFn on bf16 rows: y = bf16(A_hat^k (x bf16(W)) + b), fp32 accumulation throughout.  Weight and
+    bias gradients are fp32; the gradient w.r.t. x (if needed) is bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, k, w_in_out):
+        x = _bf16c(x)
+        w16 = to_bf16(weight)
+        h = gemm_bf16(x, w16, trans_b=not w_in_out, out_bf16=True)
+        if k > 0:
+            y = spmm_k(graph, h, k, bias=bias)
+        elif bias is not None:
+            y = to_bf16(BiasAddFn.forward(None, to_f32(h), bias))
+        else:
+            y = h
+        ctx.save_for_backward(x, w16)
+        ctx.graph, ctx.k, ctx.w_in_out, ctx.has_bias = graph, k, w_in_out, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16 = ctx.saved_tensors
+        gy = _bf16c(gy)
+        gb = colsum_bf16(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        g0 = spmm_k(ctx.graph, gy, ctx.k, transpose=True) if ctx.k > 0 else gy
+        gw = gx = None
+        if ctx.needs_input_grad[1]:
+            if ctx.w_in_out:
+                gw = gemm_bf16(x, g0, trans_a=True, out_bf16=False)          # [in, out] = x^T g0
+            else:
+                gw = gemm_bf16(g0, x, trans_a=True, out_bf16=False)          # [out, in] = g0^T x
+        if ctx.needs_input_grad[0]:
+            gx = gemm_bf16(g0, w16, trans_b=ctx.w_in_out, out_bf16=True)
+        return gx, gw, gb, None, None, None
 
 
 class BiasAddFn(torch.autograd.Function):
@@ -714,6 +851,8 @@ def global_mean_pool(x, batch, size=None):
 
 
 def graph_conv(x, weight, bias, graph, k, w_in_out=False):
+    if x.dtype == torch.bfloat16:
+        return GraphConvBf16Fn.apply(x, weight, bias, graph, int(k), bool(w_in_out))
     return GraphConvFn.apply(x, weight, bias, graph, int(k), bool(w_in_out))
 
 
