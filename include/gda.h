@@ -373,6 +373,13 @@ int gda_collate_graphs(const float* x_all, int F, const int64_t* edge_index_all,
                        const int64_t* out_node_ptr, const int64_t* out_edge_ptr, int64_t num_nodes_out,
                        int64_t num_edges_out, float* x_out, int64_t* edge_index_out, int64_t* batch_out,
                        gda_stream_t stream);
+/* gda_unpack_rows_f32: dense out [N, F] (row pitch ldo) from a row-compressed copy -- vals fp32 [nnz], cols uint16
+ * (col_bytes = 2, F <= 65536) or int32 (col_bytes = 4) [nnz], rowptr int64 [N + 1]; entries not listed are +0.0f.
+ * The reference moves every batch host->device on every step (`.to(self.device)`, pygda/models/a2gnn.py:311-312);
+ * for bag-of-words features (a few per cent non-zero) the pinned staging copy is kept compressed
+ * (pygda_b200.data.Data.pin_memory) and only the non-zeros cross PCIe. */
+int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, const int64_t* rowptr, int64_t N,
+                        int64_t F, float* out, int64_t ldo, gda_stream_t stream);
 /* gda_argmax_confusion: pred[r] = argmax_c logits[r, c] (first maximal index) and counts[y * C + p] += 1
  * (int64 [C, C], zeroed by the call): the per-epoch training score
  * eval_micro_f1(labels, logits.argmax(dim=1)) (pygda/models/a2gnn.py:328-329, pygda/metrics/metrics.py)

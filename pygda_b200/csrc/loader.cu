@@ -3,6 +3,9 @@
 //                        DataLoader / Batch.from_data_list (pygda/models/a2gnn.py:276-286, same block in
 //                        udagcn / grade / adagcn): node-wise cat of x, edge_index offset by the running node
 //                        count, `batch` = graph id per node, from a dataset kept resident in HBM
+//   gda_unpack_rows_f32  the per-step `batch.to(device)` of the fit loop (pygda/models/a2gnn.py:311-312) for sparse
+//                        (bag-of-words) feature matrices: the pinned host copy is kept row-compressed, only the
+//                        non-zeros cross PCIe and the dense [N, F] matrix is rebuilt on the device, bit for bit
 //   gda_argmax_confusion the per-epoch training score (pygda/models/a2gnn.py:328-329:
 //                        eval_micro_f1(labels, logits.argmax(dim=1)) -> .cpu().numpy() -> sklearn): argmax fused
 //                        with a C x C confusion count, so that C*C integers cross PCIe instead of 2N labels
@@ -51,6 +54,20 @@ __global__ void k_collate_edges(const int64_t* __restrict__ ei_all, int64_t E_al
     const int64_t shift = __ldg(out_node_ptr + g) - __ldg(node_ptr + id);
     ei_out[e] = __ldg(ei_all + src) + shift;
     ei_out[total + e] = __ldg(ei_all + E_all + src) + shift;
+  }
+}
+
+// one warp per row of a row-compressed feature matrix: out[r, cols[p]] = vals[p]; the rest of the row is zero-filled
+// by the memset that precedes the launch
+template <typename CI>
+__global__ void k_unpack_rows(const float* __restrict__ vals, const CI* __restrict__ cols, const int64_t* __restrict__ rowptr,
+                              int64_t N, int64_t ldo, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < N; r += nwarps) {
+    const int64_t p0 = __ldg(rowptr + r), p1 = __ldg(rowptr + r + 1);
+    float* __restrict__ row = out + r * ldo;
+    for (int64_t p = p0 + lane; p < p1; p += 32) row[static_cast<int64_t>(__ldg(cols + p))] = __ldg(vals + p);
   }
 }
 
@@ -130,6 +147,31 @@ int gda_argmax_confusion(const float* logits, int64_t rows, int C, int64_t ld, c
   if (blocks < 1) blocks = 1;
   k_argmax_confusion<<<static_cast<unsigned>(blocks), 256, sizeof(unsigned int) * C * C, st>>>(
       logits, rows, C, ld, labels, pred_out, reinterpret_cast<unsigned long long*>(counts), bad_label);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, const int64_t* rowptr, int64_t N, int64_t F,
+                        float* out, int64_t ldo, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(N >= 0 && F >= 0 && ldo >= F, "gda_unpack_rows_f32: bad size");
+  GDA_REQUIRE(col_bytes == 2 || col_bytes == 4, "gda_unpack_rows_f32: column ids are uint16 or int32");
+  if (N == 0 || F == 0) return GDA_OK;
+  GDA_REQUIRE(rowptr && out, "gda_unpack_rows_f32: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  if (ldo == F) {
+    GDA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(N) * F, st));
+  } else {
+    GDA_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * F, static_cast<size_t>(N), st));
+  }
+  int64_t blocks = ceil_div(N, 8);
+  if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+  if (col_bytes == 2)
+    k_unpack_rows<uint16_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, static_cast<const uint16_t*>(cols), rowptr, N,
+                                                                          ldo, out);
+  else
+    k_unpack_rows<int32_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, static_cast<const int32_t*>(cols), rowptr, N,
+                                                                         ldo, out);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

@@ -7,7 +7,64 @@ duck-typed equivalents the estimators in ``pygda_b200.models`` accept.  Any
 object with ``.x [N,F]``, ``.edge_index [2,E] int64``, ``.y`` (and ``.batch``
 in graph mode) and ``.to(device)`` works, including real PyG objects.
 """
+import ctypes as C
+
+import numpy as np
 import torch
+
+
+class PackedRows:
+    """Row-compressed PINNED host copy of a sparse fp32 matrix (bag-of-words features are a few per cent
+    non-zero): values, column ids (uint16 when the width allows) and row pointers.  ``to_dense(device)`` copies
+    only these over PCIe and rebuilds the dense [N, F] matrix on the GPU bit for bit (``gda_unpack_rows_f32``;
+    an entry is kept iff its BIT PATTERN is non-zero, so -0.0 survives)."""
+
+    def __init__(self, x, chunk=8192):
+        n, f = x.shape
+        x = x.contiguous()
+        vals, cols, counts = [], [], []
+        for s in range(0, n, chunk):
+            blk = x[s:s + chunk]
+            mask = blk.view(torch.int32) != 0
+            counts.append(mask.sum(1))
+            vals.append(blk[mask])
+            cols.append(mask.nonzero(as_tuple=True)[1])
+        rowptr = torch.zeros(n + 1, dtype=torch.int64)
+        if counts:
+            rowptr[1:] = torch.cumsum(torch.cat(counts), 0)
+        col = torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int64)
+        if f <= 65536:
+            self.col_bytes = 2
+            col = torch.from_numpy(col.numpy().astype(np.uint16).view(np.int16))
+        else:
+            self.col_bytes = 4
+            col = col.to(torch.int32)
+        self.shape = (n, f)
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        self.vals = pin(torch.cat(vals) if vals else torch.zeros(0))
+        self.cols = pin(col)
+        self.rowptr = pin(rowptr)
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.vals, self.cols, self.rowptr))
+
+    def to_dense(self, device, non_blocking=True):
+        from ._lib import gda
+        n, f = self.shape
+        dev = torch.device(device)
+        v, c, r = (t.to(dev, non_blocking=non_blocking) for t in (self.vals, self.cols, self.rowptr))
+        out = torch.empty(n, f, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            gda.unpack_rows_f32(C.c_void_p(v.data_ptr()), C.c_void_p(c.data_ptr()), self.col_bytes,
+                                C.c_void_p(r.data_ptr()), n, f, C.c_void_p(out.data_ptr()), f,
+                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        for t in (v, c, r):
+            t.record_stream(torch.cuda.current_stream(dev))
+        return out
+
+
+PACK_DENSITY = 0.25      # pin_memory() keeps x row-compressed below this fraction of non-zeros
 
 
 class Data:
@@ -26,7 +83,13 @@ class Data:
         if all((not torch.is_tensor(v)) or v.device == dev for v in self.__dict__.values()):
             return self                      # same no-op PyG performs when already resident
         out = self.__class__.__new__(self.__class__)
+        packed = self.__dict__.get("_packed_x") if dev.type == "cuda" else None
         for k, v in self.__dict__.items():
+            if k == "_packed_x":
+                continue
+            if k == "x" and packed is not None:
+                out.__dict__[k] = packed.to_dense(dev)          # only the non-zeros cross PCIe
+                continue
             out.__dict__[k] = v.to(dev, non_blocking=non_blocking) if torch.is_tensor(v) else v
         ei, src = out.__dict__.get("edge_index"), self.edge_index
         if torch.is_tensor(ei) and ei is not src:
@@ -41,16 +104,42 @@ class Data:
                 ei._gda_partition = part
         return out
 
-    def pin_memory(self):
+    def pin_memory(self, pack="auto"):
+        """Pinned host copy for the per-step ``.to(device)`` of the fit loops.  ``pack``: keep a sparse fp32 ``x``
+        row-compressed in the pinned staging area (``PackedRows``) -- "auto" does so below ``PACK_DENSITY``
+        non-zeros; ``.x`` of the result stays the caller's host tensor, ``.to(device)`` rebuilds it densely."""
         out = self.__class__.__new__(self.__class__)
+        x = self.__dict__.get("x")
+        do_pack = False
+        if pack and torch.is_tensor(x) and not x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.numel():
+            if pack == "auto":
+                probe = x[:: max(1, x.size(0) // 512)]
+                do_pack = float((probe.reshape(-1).view(torch.int32) != 0).float().mean()) < PACK_DENSITY
+            else:
+                do_pack = True
         for k, v in self.__dict__.items():
+            if k == "x" and do_pack:
+                out.__dict__[k] = v
+                continue
             out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v
+        if do_pack:
+            out.__dict__["_packed_x"] = PackedRows(x)
         src, ei = self.edge_index, out.__dict__.get("edge_index")
         if torch.is_tensor(ei) and ei is not src:
             for attr in ("_gda_partition", "_gda_key", "_gda_keepalive"):
                 if hasattr(src, attr):
                     setattr(ei, attr, getattr(src, attr))
         return out
+
+    def h2d_nbytes(self):
+        """Bytes ``.to(cuda)`` moves over PCIe for this (host) object."""
+        total = 0
+        for k, v in self.__dict__.items():
+            if k == "x" and "_packed_x" in self.__dict__:
+                total += self.__dict__["_packed_x"].nbytes
+            elif torch.is_tensor(v) and not v.is_cuda:
+                total += v.numel() * v.element_size()
+        return total
 
     @property
     def num_nodes(self):

@@ -69,3 +69,32 @@ def test_graph_mode_fit_uses_resident_dataset():
     assert isinstance(model.source_loader.resident, DeviceGraphDataset)
     logits, labels = model.predict(None)
     assert logits.shape == (96, 2) and labels.shape == (96,) and torch.isfinite(logits).all()
+
+
+@pytest.mark.parametrize("n,f,density", [(3000, 6775, 0.07), (500, 40000, 0.01), (300, 70000, 0.01), (64, 33, 0.2)])
+def test_packed_pinned_features_rebuild_bit_exactly(n, f, density):
+    """Data.pin_memory() keeps a sparse x row-compressed; .to(cuda) must give back the same bits."""
+    from pygda_b200.data import Data
+    g = torch.Generator().manual_seed(n + f)
+    x = torch.randn(n, f, generator=g) * (torch.rand(n, f, generator=g) < density)
+    x[0, f - 1] = 1.5                                    # last column (uint16 ids above 32767 when f > 32768)
+    x[1].zero_()                                         # an all-zero row
+    x[2, 3] = -0.0                                       # a negative zero is data too
+    d = Data(x=x, edge_index=torch.randint(n, (2, 50)), y=torch.randint(5, (n,)))
+    p = d.pin_memory()
+    assert "_packed_x" in p.__dict__ and p.x is x
+    assert p.h2d_nbytes() < 0.5 * d.pin_memory(pack=False).h2d_nbytes()
+    on = p.to("cuda:0")
+    assert "_packed_x" not in on.__dict__ and on.x.is_cuda
+    assert torch.equal(on.x.cpu().view(torch.int32), x.view(torch.int32))
+    assert torch.equal(on.edge_index.cpu(), d.edge_index) and torch.equal(on.y.cpu(), d.y)
+    again = p.to("cuda:0")
+    assert torch.equal(again.x, on.x)
+
+
+def test_dense_features_are_not_packed():
+    from pygda_b200.data import Data
+    d = Data(x=torch.randn(200, 64), edge_index=torch.randint(200, (2, 50)), y=torch.randint(5, (200,)))
+    p = d.pin_memory()
+    assert "_packed_x" not in p.__dict__ and p.x.is_pinned()
+    assert torch.equal(p.to("cuda:0").x.cpu(), d.x)
