@@ -76,7 +76,7 @@ def test_packed_pinned_features_rebuild_bit_exactly(n, f, density):
     """Data.pin_memory() keeps a sparse x row-compressed; .to(cuda) must give back the same bits."""
     from pygda_b200.data import Data
     g = torch.Generator().manual_seed(n + f)
-    x = torch.randn(n, f, generator=g) * (torch.rand(n, f, generator=g) < density)
+    x = torch.where(torch.rand(n, f, generator=g) < density, torch.randn(n, f, generator=g), torch.zeros(()))
     x[0, f - 1] = 1.5                                    # last column (uint16 ids above 32767 when f > 32768)
     x[1].zero_()                                         # an all-zero row
     x[2, 3] = -0.0                                       # a negative zero is data too
