@@ -213,6 +213,16 @@ int gda_act_dropout_bf16_bwd(const void* gy, const void* y, void* gx, int64_t n,
                              uint64_t seed, const uint64_t* seed_offset, gda_stream_t stream);
 int gda_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ldx, float* out, gda_stream_t stream);
 
+/* -------------------------------------- Bernstein propagation --
+ * BernProp.forward (pygda/nn/dgsda_base.py:101-153): out = sum_k C(K,k)/2^K relu(temp_k) L^k (2I-L)^(K-k) x.
+ * The propagations are gda_spmm_f32 on two graphs (L and 2I-L, built with explicit weights); these two are the
+ * glue between them: y = beta*y + coef*relu(*temp_k)*x with the temperature read on the device, and
+ * *out = coef * [temp_k > 0] * <g, x> (fp64 accumulation; scratch: one device double). */
+int gda_bern_axpy_f32(float* y, const float* x, int64_t n, float beta, float coef, const float* temp_k,
+                      gda_stream_t stream);
+int gda_bern_dtemp_f32(const float* g, const float* x, int64_t n, float coef, const float* temp_k, float* out,
+                       double* scratch, gda_stream_t stream);
+
 /* ------------------------------------------------------------ elementwise --
  * y = dropout(act(x + bias)) and its backward; act: 0 none, 1 relu.  The keep
  * mask is regenerated from (seed, element index): nothing is stored.

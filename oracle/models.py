@@ -296,3 +296,45 @@ class GNN:
         source_logits = self.gnn(source_data.x, source_data.edge_index)
         target_logits = self.gnn(target_data.x, target_data.edge_index)
         return F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y), source_logits, target_logits
+
+
+class DGSDA:
+    """pygda/models/dgsda.py:73-227 (forward_model :144-196, entropy_minimization_loss :198-227, loop body
+    :300-330): CE(source) + alpha * L1(temp_s, temp_t) + beta * MMD(relu(lin1 x_s), relu(lin1 x_t)) +
+    gamma * weighted target entropy."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, mode="node", num_layers=2, dropout=0., K=8, alpha=0.05,
+                 beta=0.5, gamma=0.05, weight_decay=0., lr=4e-3, epoch=200, **kwargs):
+        assert num_layers == 2 and mode == "node"
+        self.alpha, self.beta, self.gamma, self.epoch = alpha, beta, gamma, epoch
+        self.dgsda = ONN.DGSDABase(in_dim, hid_dim, num_classes, dprate=dropout, K=K)
+        self.optimizer = torch.optim.Adam(self.dgsda.parameters(), lr=lr, weight_decay=weight_decay)
+        self.mmd_indices, self.mmd_sqdist = None, M.pairwise_sqdist_broadcast
+
+    @staticmethod
+    def entropy_minimization_loss(output):
+        probs = F.softmax(output, dim=1)
+        log_probs = F.log_softmax(output, dim=1)
+        a = torch.sum(probs, dim=0)
+        return -torch.sum(probs * log_probs / (a / torch.sum(a)), dim=1).mean()
+
+    def forward_model(self, source_data, target_data):
+        net = self.dgsda
+        source_logits = net(source_data)
+        loss = F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y)
+        loss = loss + F.l1_loss(net.prop1.temp, net.prop2.temp) * self.alpha
+        source_feature = F.relu(net.lin1(source_data.x))
+        target_feature = F.relu(net.lin1(target_data.x))
+        loss = loss + M.MMD(source_feature, target_feature, indices=self.mmd_indices, sqdist=self.mmd_sqdist) * self.beta
+        target_outputs = net(target_data, False)
+        loss = loss + self.entropy_minimization_loss(target_outputs) * self.gamma
+        return loss, source_logits
+
+    def train_step(self, source_data, target_data):
+        self.dgsda.train()
+        loss, s_logits = self.forward_model(source_data, target_data)
+        val = loss.item()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return val, s_logits

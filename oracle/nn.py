@@ -380,3 +380,65 @@ class GATConv(nn.Module):
         alpha = ex / den[ei[1]]
         out = P.scatter_add(alpha.unsqueeze(-1) * h[ei[0]], ei[1], 0, n)        # [N, 1, C]
         return out.mean(dim=1) + self.bias
+
+
+class BernProp(nn.Module):
+    """pygda/nn/dgsda_base.py:11-183: Bernstein-polynomial propagation
+    ``out = sum_k C(K,k)/2^K relu(temp_k) L^k (2I - L)^(K-k) x`` evaluated the reference's way -- K propagations
+    with 2I - L, then k propagations with L for the k-th term (K(K+1)/2 more)."""
+
+    def __init__(self, K, is_source_domain=True, bias=True, **kwargs):
+        super().__init__()
+        self.K, self.is_source_domain = K, is_source_domain
+        self.temp = nn.Parameter(torch.Tensor(K + 1), requires_grad=is_source_domain)   # :59
+        self.reset_parameters()
+
+    def reset_parameters(self):                                            # :63-77
+        if self.is_source_domain:
+            self.temp.data.fill_(1)
+        else:
+            self.temp.data = torch.linspace(1, 0, self.K + 1)
+
+    def forward(self, x, edge_index, edge_weight=None):                    # :101-153
+        from math import comb
+        TEMP = F.relu(self.temp)
+        ei1, norm1 = P.get_laplacian(edge_index, edge_weight, normalization="sym", dtype=x.dtype,
+                                     num_nodes=x.size(0))
+        ei2, norm2 = P.add_self_loops_attr(ei1, -norm1, 2.0, x.size(0))
+        tmp = [x]
+        for _ in range(self.K):
+            x = P.propagate(ei2, x, norm2)
+            tmp.append(x)
+        out = (comb(self.K, 0) / (2 ** self.K)) * TEMP[0] * tmp[self.K]
+        for i in range(self.K):
+            x = tmp[self.K - i - 1]
+            x = P.propagate(ei1, x, norm1)
+            for _ in range(i):
+                x = P.propagate(ei1, x, norm1)
+            out = out + (comb(self.K, i + 1) / (2 ** self.K)) * TEMP[i + 1] * x
+        return out
+
+
+class DGSDABase(nn.Module):
+    """pygda/nn/dgsda_base.py:186-315.  NOTE (reference quirk, kept): prop1 / prop2 / prop3 are all built
+    with the default ``is_source_domain=True`` (:222-224), so all three ``temp`` vectors start at 1 and train."""
+
+    def __init__(self, features, hidden, classes, dprate=0.0, K=15):
+        super().__init__()
+        self.lin1 = nn.Linear(features, hidden)
+        self.lin2 = nn.Linear(hidden, classes)
+        self.prop1, self.prop2, self.prop3 = BernProp(K), BernProp(K), BernProp(K)
+        self.dprate = dprate
+
+    def get_props(self, x, edge_index, is_source_domain=True):             # :278-315
+        x = F.dropout(x, p=self.dprate, training=self.training)
+        x = F.relu(self.lin1(x))
+        x = F.dropout(x, p=self.dprate, training=self.training)
+        return self.prop1(x, edge_index) if is_source_domain else self.prop2(x, edge_index)
+
+    def forward(self, data, is_source_domain=True):                        # :238-276
+        x = self.get_props(data.x, data.edge_index, is_source_domain)
+        x = F.dropout(x, p=self.dprate, training=self.training)
+        x = self.lin2(x)
+        x = F.dropout(x, p=self.dprate, training=self.training)
+        return self.prop3(x, data.edge_index)

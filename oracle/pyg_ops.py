@@ -64,6 +64,37 @@ def add_self_loops(edge_index, num_nodes):
     return torch.cat([edge_index, loops.unsqueeze(0).repeat(2, 1)], dim=1)
 
 
+def add_self_loops_attr(edge_index, edge_attr=None, fill_value=1.0, num_nodes=None):
+    """PyG ``add_self_loops`` with attributes: N loops are APPENDED (existing loops stay, duplicates are not
+    coalesced), their attribute is ``fill_value``.  Call site: pygda/nn/dgsda_base.py:133."""
+    n = maybe_num_nodes(edge_index, num_nodes)
+    ei = add_self_loops(edge_index, n)
+    if edge_attr is None:
+        return ei, None
+    return ei, torch.cat([edge_attr, edge_attr.new_full((n,), fill_value)], dim=0)
+
+
+def get_laplacian(edge_index, edge_weight=None, normalization=None, dtype=None, num_nodes=None):
+    """PyG ``get_laplacian`` (upstream, restated from torch_geometric 2.4): self loops removed, degree at the
+    SOURCE index, ``'sym'``: L = I - D^-1/2 A D^-1/2 returned as (edges with -w_norm, then N loops with 1);
+    ``None``: L = D - A.  Call site: pygda/nn/dgsda_base.py:130-131."""
+    edge_index, edge_weight = remove_self_loops(edge_index, edge_weight)
+    if edge_weight is None:
+        edge_weight = torch.ones(edge_index.size(1), dtype=dtype, device=edge_index.device)
+    n = maybe_num_nodes(edge_index, num_nodes)
+    row, col = edge_index[0], edge_index[1]
+    deg = scatter_add(edge_weight, row, 0, n)
+    if normalization is None:
+        ei = add_self_loops(edge_index, n)
+        return ei, torch.cat([-edge_weight, deg], dim=0)
+    if normalization != "sym":
+        raise NotImplementedError("only normalization in (None, 'sym') is restated")
+    dis = deg.pow(-0.5)
+    dis.masked_fill_(dis == float("inf"), 0)
+    w = dis[row] * edge_weight * dis[col]
+    return add_self_loops_attr(edge_index, -w, 1.0, n)
+
+
 def propagate(edge_index, x, edge_weight=None, num_nodes=None):
     """PyG ``MessagePassing.propagate`` with aggr='add', flow source->target
     (SURVEY Appendix A.2): gather rows at edge_index[0], scale, scatter-add at

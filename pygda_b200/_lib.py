@@ -59,6 +59,8 @@ SIGNATURES = {
     "gda_act_dropout_bf16_fwd": (i32, [vp, vp, i64, i32, f32, u64, vp, vp]),
     "gda_act_dropout_bf16_bwd": (i32, [vp, vp, vp, i64, i32, f32, u64, vp, vp]),
     "gda_colsum_bf16": (i32, [vp, i64, i64, i64, vp, vp]),
+    "gda_bern_axpy_f32": (i32, [vp, vp, i64, f32, f32, vp, vp]),
+    "gda_bern_dtemp_f32": (i32, [vp, vp, i64, f32, vp, vp, vp, vp]),
     "gda_bias_act_dropout_fwd": (i32, [vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_bwd": (i32, [vp, vp, vp, vp, i64, i64, i32, f32, u64, vp, vp]),
     "gda_bias_act_dropout_rep_fwd": (i32, [vp, vp, vp, i64, i64, i32, i32, f32, u64, vp, vp]),

@@ -157,6 +157,28 @@ __global__ void k_colsum_bf16(const __nv_bfloat16* __restrict__ x, int64_t rows,
   }
 }
 
+// ---- Bernstein propagation glue (pygda/nn/dgsda_base.py:135-153): y = beta * y + coef * relu(*t) * x with the
+// temperature read on the device (no host sync), and d loss / d temp_k = coef * [temp_k > 0] * <g, x> ----
+__global__ void k_bern_axpy(float* __restrict__ y, const float* __restrict__ x, int64_t n, float beta, float coef,
+                            const float* __restrict__ t) {
+  const float a = coef * fmaxf(__ldg(t), 0.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (beta == 0.f ? 0.f : beta * y[i]) + a * x[i];
+}
+
+__global__ void k_bern_dot(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* __restrict__ acc) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += static_cast<double>(a[i]) * static_cast<double>(b[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+
+__global__ void k_bern_dtemp(const double* __restrict__ acc, float coef, const float* __restrict__ t, float* __restrict__ out) {
+  *out = (__ldg(t) > 0.f) ? static_cast<float>(static_cast<double>(coef) * *acc) : 0.f;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // out[c] += sum over this block's row range; out pre-zeroed
@@ -607,6 +629,31 @@ int gda_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ldx, floa
   const int threads = cols >= 256 ? 256 : (cols >= 128 ? 128 : 64);
   k_colsum_bf16<<<static_cast<unsigned>(ceil_div(rows, rpb)), threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows,
                                                                                 static_cast<int>(cols), ldx, out, rpb);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_bern_axpy_f32(float* y, const float* x, int64_t n, float beta, float coef, const float* temp_k,
+                      gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0, "gda_bern_axpy_f32: negative size");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(y && x && temp_k, "gda_bern_axpy_f32: NULL pointer");
+  k_bern_axpy<<<grid_for(n, 4), kThreads, 0, as_stream(stream)>>>(y, x, n, beta, coef, temp_k);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_bern_dtemp_f32(const float* g, const float* x, int64_t n, float coef, const float* temp_k, float* out,
+                       double* scratch, gda_stream_t stream) {
+  GDA_REQUIRE(n >= 0 && temp_k && out && scratch, "gda_bern_dtemp_f32: bad argument");
+  cudaStream_t st = as_stream(stream);
+  GDA_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  if (n > 0) {
+    GDA_REQUIRE(g && x, "gda_bern_dtemp_f32: NULL pointer");
+    k_bern_dot<<<grid_for(n, 8), kThreads, 0, st>>>(g, x, n, scratch);
+    GDA_LAUNCH_CHECK();
+  }
+  k_bern_dtemp<<<1, 1, 0, st>>>(scratch, coef, temp_k, out);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

@@ -6,5 +6,6 @@ from .grade import GRADE
 from .adagcn import AdaGCN
 from .gnn import GNN
 from .tdss import TDSS
+from .dgsda import DGSDA
 
-__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE", "AdaGCN", "GNN", "TDSS"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn
+__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE", "AdaGCN", "GNN", "TDSS", "DGSDA"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn

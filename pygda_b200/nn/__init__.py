@@ -10,6 +10,7 @@ from .grade_base import GRADEBase
 from .adagcn_base import AdaGCNBase
 from .gnn_base import GNNBase
 from .gat_conv import GATConv
+from .dgsda_base import BernProp, DGSDABase
 
 __all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "PPMIConv", "Attention",
-           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv"]
+           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv", "BernProp", "DGSDABase"]

@@ -73,4 +73,7 @@ def load_reference():
     pkg.nn.GNNBase = ns.gnn_base.GNNBase
     ns.gnn = imp("pygda.models.gnn")
     ns.tdss = imp("pygda.models.tdss")
+    ns.dgsda_base = imp("pygda.nn.dgsda_base")
+    pkg.nn.DGSDABase = ns.dgsda_base.DGSDABase
+    ns.dgsda = imp("pygda.models.dgsda")
     return ns
