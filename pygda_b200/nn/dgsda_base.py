@@ -88,8 +88,9 @@ class BernPropFn(torch.autograd.Function):
                                    C.c_void_p(gtemp.data_ptr() + 4 * k), _p(scratch), st())
         gx = None
         if ctx.needs_input_grad[0]:
-            S = torch.empty_like(go)                           # S <- M^T S + a_(K-j) G_(K-j), from j = K down to 0
-            gda.bern_axpy_f32(_p(S), _p(G[K]), n, 0.0, coef[0], C.c_void_p(temp.data_ptr()), st())
+            # dx = sum_k a_k (M^T)^(K-k) G_k: Horner in M^T from the k = 0 term (power K) down to k = K (power 0)
+            S = torch.empty_like(go)
+            gda.bern_axpy_f32(_p(S), _p(G[0]), n, 0.0, coef[0], C.c_void_p(temp.data_ptr()), st())
             for j in range(K - 1, -1, -1):
                 S = ops.spmm(mid, S, transpose=True)
                 k = K - j
