@@ -183,7 +183,7 @@ class NeighborLoader:
     reference's own scaling tool and is replaced here by node partitioning
     (DESIGN.md section 6); asking for it raises."""
 
-    def __init__(self, data, num_neighbors, batch_size=None, **kw):
+    def __init__(self, data, num_neighbors, batch_size=None, pin=False, **kw):
         n = data.x.shape[0]
         if batch_size is not None and batch_size != n:
             raise NotImplementedError(
@@ -194,8 +194,13 @@ class NeighborLoader:
         order = torch.argsort(ei[1], stable=True)
         extra = {k: v for k, v in data.__dict__.items()
                  if k not in ("x", "edge_index", "y", "batch", "num_graphs")}
+        extra.pop("_packed_x", None)
         self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
                            batch=data.batch, num_graphs=data.num_graphs, **extra)
+        # the fit loops send this one batch host->device on EVERY step (pygda/models/a2gnn.py:311-312): stage it in
+        # pinned memory once (a sparse x row-compressed, Data.pin_memory) instead of paging it through each time
+        if pin and torch.cuda.is_available() and torch.is_tensor(data.x) and not data.x.is_cuda:
+            self._batch = self._batch.pin_memory()
 
     def __iter__(self):
         yield self._batch
