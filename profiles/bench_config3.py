@@ -43,6 +43,24 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+if os.environ.get("PROFILE_ONE"):
+    # ncu --profile-from-start off: one training step of one variant between cudaProfilerStart/Stop, then exit
+    src, tgt = domain_pair(N, E, F_, C, seed=0, device=dev)
+    dt = torch.bfloat16 if os.environ["PROFILE_ONE"] == "bf16" else None
+    torch.manual_seed(0)
+    est = UDAGCN(in_dim=F_, hid_dim=H, num_classes=C, num_layers=2, ppmi=False, lr=1e-4, weight_decay=1e-3,
+                 epoch=400, device=str(dev), verbose=0, feature_dtype=dt)
+    est.udagcn = est.init_model()
+    opt = Adam(itertools.chain(*[m.parameters() for m in est.udagcn.models]), lr=1e-4, weight_decay=1e-3)
+    for _ in range(2):
+        est.train_step(src, tgt, 0.05, 10, opt)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    est.train_step(src, tgt, 0.05, 10, opt)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
+
 if not os.environ.get("SKIP_STEP"):
     src, tgt = domain_pair(N, E, F_, C, seed=0, device=dev)
     for name, dt in (("fp32", None), ("bf16", torch.bfloat16)):
@@ -91,7 +109,7 @@ if not os.environ.get("SKIP_STEP"):
     torch.cuda.empty_cache()
 
 # ---- aggregation size sweep at the config-2 shape family (mean degree 10, H = 128 fp32) ----
-for n in (12_500, 25_000, 50_000, 100_000, 200_000, 400_000, 800_000):
+for n in (() if os.environ.get("SKIP_SWEEP") else (12_500, 25_000, 50_000, 100_000, 200_000, 400_000, 800_000)):
     ei = powerlaw_edge_index(n, 10 * n, seed=2, offset=48.0).cuda()
     g = Graph(ei, n)
     x = torch.randn(n, 128, device=dev)

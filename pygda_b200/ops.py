@@ -199,9 +199,26 @@ def gemm_split(a, b, trans_a, trans_b, m, n, k):
     return out
 
 
+def _pad_to(t, dim, size):
+    """Zero-padded copy of a 2-D tensor along ``dim``."""
+    shape = list(t.shape)
+    shape[dim] = size
+    out = torch.zeros(shape, dtype=t.dtype, device=t.device)
+    out.narrow(dim, 0, t.shape[dim]).copy_(t)
+    return out
+
+
+TC_PAD = 64      # the tcgen05 kernel needs N >= 64 and K >= 64
+
+
 def mm(a, b, trans_a=False, trans_b=False, a_split=None, b_split=None, cache_a=False, cache_b=False):
     """op(a) @ op(b): tensor cores (split-bf16, fp32-accurate) for the big shapes, SIMT otherwise.
-    Returns (result, a_split, b_split) so callers can re-use the splits in the backward."""
+    Returns (result, a_split, b_split) so callers can re-use the splits in the backward.
+
+    Tall products with a NARROW output or reduction width between the skinny kernels' 16 and the tensor-core
+    kernel's 64 -- UDAGCN's / AdaGCN's 40-wide domain MLP on 1 M rows (pygda/nn/udagcn_base.py:157-162) -- are
+    zero-padded to 64 and run on the tensor cores too: exact (the padding contributes zeros), and 10x faster than
+    the SIMT kernel there (profiles/r1_h_config3: 4 x 1.9 ms of a 28 ms step)."""
     m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
     n = b.shape[0] if trans_b else b.shape[1]
     if tc_eligible(m, n, k):
@@ -210,6 +227,15 @@ def mm(a, b, trans_a=False, trans_b=False, a_split=None, b_split=None, cache_a=F
         if b_split is None:
             b_split = split_cache.get(b) if cache_b else Split(b)
         return gemm_split(a_split, b_split, trans_a, trans_b, m, n, k), a_split, b_split
+    if 16 < n < TC_PAD and tc_eligible(m, TC_PAD, k):                 # narrow output: pad op(b)'s columns
+        bp = Split(_pad_to(_f32c(b), 0 if trans_b else 1, TC_PAD))
+        ap = a_split if a_split is not None else (split_cache.get(a) if cache_a else Split(a))
+        out = gemm_split(ap, bp, trans_a, trans_b, m, TC_PAD, k)
+        return out[:, :n].contiguous(), ap, b_split
+    if 16 < k < TC_PAD and tc_eligible(m, n, TC_PAD):                 # narrow reduction: pad both operands along k
+        ap = Split(_pad_to(_f32c(a), 0 if trans_a else 1, TC_PAD))
+        bp = Split(_pad_to(_f32c(b), 1 if trans_b else 0, TC_PAD))
+        return gemm_split(ap, bp, trans_a, trans_b, m, n, TC_PAD), a_split, b_split
     return gemm(a, b, trans_a=trans_a, trans_b=trans_b), a_split, b_split
 
 

@@ -38,3 +38,36 @@ def test_cls_layer_autograd_at_benchmark_width():
     assert_close(y, ref(x, ei, 1), 1e-4, "fwd")
     assert_close(conv.lin.weight.grad, ref.lin.weight.grad, 1e-4, "dW")
     assert_close(xg.grad, xr.grad, 1e-4, "dx")
+
+
+@pytest.mark.parametrize("ta,tb,m,n,k", [(False, True, 200_000, 40, 256), (False, False, 200_000, 256, 40),
+                                         (False, False, 150_000, 33, 128), (True, False, 300, 40, 100_000)])
+def test_narrow_widths_are_padded_onto_the_tensor_cores_exactly(ta, tb, m, n, k):
+    """Widths between the skinny kernels (<= 16) and the tcgen05 kernel (>= 64) -- the 40-wide domain MLP of
+    UDAGCN / AdaGCN (pygda/nn/udagcn_base.py:157-162) -- are zero-padded to 64 (ops.mm): same values."""
+    from pygda_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g).cuda()
+    b = torch.randn((n, k) if tb else (k, n), generator=g).cuda()
+    out, _, _ = ops.mm(a, b, trans_a=ta, trans_b=tb)
+    ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    assert out.shape == (m, n) and out.is_contiguous()
+    assert_close(out, ref, 3e-5, "padded tensor-core product")
+
+
+def test_linear_256_to_40_forward_and_backward():
+    from pygda_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(120_000, 256, device="cuda", requires_grad=True)
+    w = (torch.randn(40, 256, device="cuda") * 0.1).requires_grad_(True)
+    b = torch.randn(40, device="cuda", requires_grad=True)
+    y = ops.linear(x, w, b)
+    go = torch.randn_like(y)
+    y.backward(go)
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yr = xr @ wr.t() + br
+    yr.backward(go.double())
+    assert_close(y, yr, 3e-5, "forward")
+    assert_close(x.grad, xr.grad, 3e-5, "dX (reduction width 40)")
+    assert_close(w.grad, wr.grad, 1e-4, "dW")
+    assert_close(b.grad, br.grad, 1e-4, "db")
