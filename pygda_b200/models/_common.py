@@ -6,7 +6,7 @@ import time
 import torch
 
 from ..data import DataLoader, NeighborLoader
-from ..metrics import eval_micro_f1, micro_f1_from_logits
+from ..metrics import micro_f1_from_logits
 from ..utils import logger
 
 

@@ -14,7 +14,6 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import BaseGDA
-from .. import ops
 from ..nn.adagcn_base import AdaGCNBase
 from ..optim import Adam
 from ._common import TwoDomainLoop

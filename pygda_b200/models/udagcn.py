@@ -2,7 +2,6 @@
 fit :203-308, predict :310-387)."""
 import itertools
 
-import torch
 import torch.nn.functional as F
 
 from . import BaseGDA

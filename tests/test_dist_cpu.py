@@ -112,3 +112,27 @@ def test_shard_batch_splits_graphs_contiguously():
             got_x.append(sh.x); got_y.append(sh.y); edges += sh.edge_index.size(1)
         assert torch.equal(torch.cat(got_x), full.x) and torch.equal(torch.cat(got_y), full.y)
         assert edges == full.edge_index.size(1)
+
+
+def test_packed_rows_format_roundtrip_on_the_host():
+    """Host half of the row-compressed pinned staging (pygda_b200/data.py: PackedRows): values, uint16 / int32
+    column ids and row pointers reproduce the matrix bit for bit (the device half is gda_unpack_rows_f32)."""
+    import numpy as np
+    from pygda_b200.data import Data, PackedRows
+    g = torch.Generator().manual_seed(0)
+    for n, f in ((300, 6775), (40, 70000), (5, 1)):
+        x = torch.where(torch.rand(n, f, generator=g) < 0.05, torch.randn(n, f, generator=g), torch.zeros(()))
+        x[0, f - 1] = 2.0
+        x[1].zero_()
+        if f > 3:
+            x[2, 3] = -0.0
+        p = PackedRows(x, chunk=64)
+        assert p.col_bytes == (2 if f <= 65536 else 4) and p.shape == (n, f)
+        cols = p.cols.numpy().view(np.uint16).astype(np.int64) if p.col_bytes == 2 else p.cols.numpy().astype(np.int64)
+        rows = torch.repeat_interleave(torch.arange(n), p.rowptr[1:] - p.rowptr[:-1])
+        dense = torch.zeros(n, f)
+        dense[rows, torch.from_numpy(cols)] = p.vals
+        assert torch.equal(dense.view(torch.int32), x.view(torch.int32))
+        assert int(p.rowptr[-1]) == p.vals.numel() == p.cols.numel()
+    d = Data(x=torch.zeros(10, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.zeros(10, dtype=torch.long))
+    assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
