@@ -45,6 +45,39 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and b"negative" in lib.gda_last_error()
 
 
+def test_newer_entry_points_validate_before_touching_the_device():
+    """Error behaviour at the boundary (negative status + thread-local message), no GPU involved."""
+    import ctypes as C
+    from pygda_b200 import _lib
+    lib = _lib.load()
+    out = C.c_void_p(0)
+    cases = [
+        (lib.gda_spmm_f32(None, 0, None, 4, None, 4, 4, None, 0, 0.0, 0, None, None, 0, None), b"graph is NULL"),
+        (lib.gda_spmm_nb_f32(None, 0, 2, None, 4, 0, None, 4, 0, 4, None, 0, 0.0, 0, None, None, 0, None), b"graph is NULL"),
+        (lib.gda_bias_act_dropout_rep_fwd(None, None, None, -1, 4, 2, 0, 0.0, 0, None, None), b"negative"),
+        (lib.gda_bias_act_dropout_rep_bwd(None, None, None, None, None, 4, 4, 3, 0, 0, 0.0, 0, None, None), b"rep must be 1 or 2"),
+        (lib.gda_ppmi_create(None, 0, 10, 0, 40, 0, None, C.byref(out)), b"path_len"),
+        (lib.gda_ppmi_create(None, 5, 10, 5, 40, 0, None, C.byref(out)), b"edge_index is NULL"),
+        (lib.gda_argmax_confusion(None, 10, 65, 65, None, None, None, None, None), b"C <= 64"),
+        (lib.gda_unpack_rows_f32(None, None, 3, None, 4, 4, None, 4, None), b"uint16 or int32"),
+        (lib.gda_collate_graphs(None, 0, None, 0, None, None, None, 1, None, None, 0, 0, None, None, None, None), b"bad size"),
+        (lib.gda_gemm_bf16(0, 0, -1, 64, 64, None, 64, None, 64, None, 64, 1, None, 0, None), b"negative"),
+        (lib.gda_attention2_bwd(None, None, 4, 9000, None, None, None, None, None, None, None), b"H <= 8192"),
+        (lib.gda_bern_axpy_f32(None, None, -1, 0.0, 1.0, None, None), b"negative"),
+    ]
+    for rc, needle in cases:
+        assert rc < 0
+    # the message is the one of the LAST failing call on this thread
+    rc = lib.gda_unpack_rows_f32(None, None, 3, None, 4, 4, None, 4, None)
+    assert rc < 0 and b"uint16 or int32" in lib.gda_last_error()
+    rc = lib.gda_ppmi_create(None, 0, 10, 0, 40, 0, None, C.byref(out))
+    assert rc < 0 and b"path_len" in lib.gda_last_error() and not out.value
+    # sizes that mean "nothing to do" succeed without a device
+    assert lib.gda_bias_act_dropout_rep_fwd(None, None, None, 0, 4, 2, 0, 0.0, 0, None, None) == 0
+    assert lib.gda_gemm_bf16(0, 0, 0, 64, 64, None, 64, None, 64, None, 64, 1, None, 0, None) == 0
+    assert lib.gda_wedges_size(None) == -1
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     from pygda_b200 import ops
