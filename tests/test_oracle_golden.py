@@ -102,3 +102,20 @@ def test_a2gnn_mmd_indices_follow_cpu_generator():
     torch.manual_seed(g["seed"])
     s_idx, t_idx = OM.draw_mmd_indices(60, 50)
     assert torch.equal(s_idx, g["source_idx"]) and torch.equal(t_idx, g["target_idx"])
+
+
+def test_logger_lines_equal_the_reference(capsys):
+    """pygda_b200.utils.logger prints what the reference's own logger prints (tests/golden/logger.json, made by
+    executing pygda/utils/utility.py): the per-epoch line of every fit loop."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from pygda_b200.utils import logger
+    cases = json.load(open(os.path.join(GOLDEN, "logger.json")))
+    assert len(cases) >= 8
+    for c in cases:
+        kw = dict(c["kwargs"])
+        if isinstance(kw.get("loss"), list):
+            kw["loss"] = tuple(kw["loss"])
+        logger(**kw)
+        assert capsys.readouterr().out == c["stdout"], kw
