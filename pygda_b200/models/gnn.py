@@ -15,13 +15,14 @@ import time
 
 
 class GNN(BaseGDA):
-    def __init__(self, in_dim, hid_dim, num_classes, num_layers=3, dropout=0., act=F.relu, gnn='gcn',
-                 weight_decay=0., lr=4e-3, epoch=200, device='cuda:0', batch_size=0, num_neigh=-1, verbose=2,
-                 **kwargs):
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=2, dropout=0., gnn='gcn', act=F.relu,
+                 weight_decay=0.0001, lr=0.05, epoch=100, device='cuda:0', batch_size=0, num_neigh=-1, verbose=2,
+                 **kwargs):                                                               # gnn.py:59-75
         super().__init__(in_dim=in_dim, hid_dim=hid_dim, num_classes=num_classes, num_layers=num_layers,
                          dropout=dropout, act=act, weight_decay=weight_decay, lr=lr, epoch=epoch, device=device,
                          batch_size=batch_size, num_neigh=num_neigh, verbose=verbose, **kwargs)
         self.gnn_type = gnn
+        self.gnn = gnn            # the reference keeps the backbone NAME here until fit() replaces it by the module (:92)
 
     def init_model(self, **kwargs):
         return GNNBase(in_dim=self.in_dim, hid_dim=self.hid_dim, num_classes=self.num_classes,

@@ -119,3 +119,45 @@ def test_logger_lines_equal_the_reference(capsys):
             kw["loss"] = tuple(kw["loss"])
         logger(**kw)
         assert capsys.readouterr().out == c["stdout"], kw
+
+
+def test_public_signatures_start_with_the_reference_signatures():
+    """Drop-in boundary, level 1: every constructor / method of the hot-path classes takes the reference's
+    parameters -- same names, order, kinds and defaults (tests/golden/signatures.json, read from the reference's
+    own files).  Extra parameters (e.g. ``mmd_indices=None`` for tests) must come last and be optional."""
+    import inspect
+    import json
+    import os
+    from conftest import GOLDEN
+    import pygda_b200.models as M
+    import pygda_b200.nn as NN
+    import pygda_b200.utils as U
+    ref = json.load(open(os.path.join(GOLDEN, "signatures.json")))
+    assert len(ref) >= 70
+
+    def resolve(key):
+        parts = key.split(".")
+        mod = {"models": M, "nn": NN, "utils": U}[parts[0]]
+        obj = getattr(mod, parts[1])
+        return getattr(obj, parts[2]) if len(parts) > 2 else obj
+
+    problems = []
+    for key, want in ref.items():
+        fn = resolve(key)
+        got = []
+        for p in inspect.signature(fn).parameters.values():
+            d = None if p.default is inspect.Parameter.empty else (p.default.__name__ if callable(p.default) else repr(p.default))
+            got.append([p.name, p.kind.name, d])
+        # a trailing **kwargs of the reference may be followed by nothing; ours may insert optional extras before it
+        # (static methods of ours that the reference declares as instance methods differ by `self` only)
+        want_core = [w for w in want if w[1] != "VAR_KEYWORD" and w[0] != "self"]
+        got_core = [g for g in got if g[1] != "VAR_KEYWORD" and g[0] != "self"]
+        if got_core[:len(want_core)] != want_core:
+            problems.append((key, want_core, got_core[:len(want_core)]))
+            continue
+        for extra in got_core[len(want_core):]:
+            if extra[2] is None and extra[1] not in ("VAR_POSITIONAL",):
+                problems.append((key, "extra parameter without default", extra))
+        if any(w[1] == "VAR_KEYWORD" for w in want) and not any(g[1] == "VAR_KEYWORD" for g in got):
+            problems.append((key, "reference accepts **kwargs", None))
+    assert not problems, problems
