@@ -1,5 +1,6 @@
 """The oracle against the vectors produced by executing the reference's own source
 files (tests/golden/make_golden.py).  Index results bit-exact, fp32 within 1e-5."""
+import pytest
 import torch
 
 from oracle import mmd as OM
@@ -161,3 +162,27 @@ def test_public_signatures_start_with_the_reference_signatures():
         if any(w[1] == "VAR_KEYWORD" for w in want) and not any(g[1] == "VAR_KEYWORD" for g in got):
             problems.append((key, "reference accepts **kwargs", None))
     assert not problems, problems
+
+
+def test_estimator_constructors_set_the_reference_attributes():
+    """Every simple attribute the reference's constructors set (hyper-parameters, the expanded ``num_neigh`` list,
+    mode flags ...) exists with the same value on the pygda_b200 estimator (tests/golden/estimator_attrs.json)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    import pygda_b200.models as M
+    ref = json.load(open(os.path.join(GOLDEN, "estimator_attrs.json")))
+    assert len(ref) == 14
+    for key, blob in ref.items():
+        est = getattr(M, key.split("/")[0])(**blob["kwargs"])
+        for k, v in blob["attrs"].items():
+            assert hasattr(est, k), f"{key}: attribute {k} missing"
+            assert getattr(est, k) == v, f"{key}: {k} = {getattr(est, k)!r}, reference {v!r}"
+
+
+def test_num_neigh_validation_errors_like_the_reference():
+    import pygda_b200.models as M
+    with pytest.raises(ValueError, match="same length"):
+        M.A2GNN(in_dim=4, hid_dim=4, num_classes=2, num_layers=2, num_neigh=[1, 2, 3], device="cpu")
+    with pytest.raises(ValueError, match="must be int or list"):
+        M.GRADE(in_dim=4, hid_dim=4, num_classes=2, num_neigh="all", device="cpu")
