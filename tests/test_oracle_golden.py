@@ -186,3 +186,18 @@ def test_num_neigh_validation_errors_like_the_reference():
         M.A2GNN(in_dim=4, hid_dim=4, num_classes=2, num_layers=2, num_neigh=[1, 2, 3], device="cpu")
     with pytest.raises(ValueError, match="must be int or list"):
         M.GRADE(in_dim=4, hid_dim=4, num_classes=2, num_neigh="all", device="cpu")
+
+
+def test_module_state_dict_layouts_equal_the_reference():
+    """Parameter / buffer names, shapes and trainability of every hot-path module equal the reference's
+    (tests/golden/state_dicts.json, from its own files), so reference checkpoints load with strict=True."""
+    import json
+    import os
+    from conftest import GOLDEN
+    import pygda_b200.nn as NN
+    ref = json.load(open(os.path.join(GOLDEN, "state_dicts.json")))
+    assert len(ref) == 15
+    for key, blob in ref.items():
+        m = getattr(NN, key.split("/")[0])(**blob["kwargs"])
+        assert {k: list(v.shape) for k, v in m.state_dict().items()} == blob["state"], key
+        assert sorted(k for k, p in m.named_parameters() if p.requires_grad) == blob["trainable"], key
