@@ -261,7 +261,7 @@ class DeviceGraphDataset:
 class DataLoader:
     """``DataLoader(dataset, batch_size, shuffle)`` over a sequence of graphs.  With ``device`` set to a CUDA device
     the dataset is moved there once (``DeviceGraphDataset``) and every batch is collated on the GPU; the shuffle
-    order still comes from ``torch.randperm`` on the CPU generator, as PyG's does."""
+    order comes from torch's own ``RandomSampler`` on the CPU generator, exactly as PyG's does."""
 
     def __init__(self, dataset, batch_size=1, shuffle=False, device=None, **kw):
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
@@ -273,10 +273,13 @@ class DataLoader:
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        n = len(self.dataset)
-        order = torch.randperm(n).tolist() if self.shuffle else list(range(n))
-        for s in range(0, n, self.batch_size):
-            ids = order[s:s + self.batch_size]
+        # PyG's DataLoader IS torch.utils.data.DataLoader with a graph collate function: the index batches come from
+        # torch's own sampler machinery, so the same torch seed gives the same batches as the reference
+        # (RandomSampler draws its seed from the global CPU generator, after the iterator's base seed)
+        import torch.utils.data as tud
+        index_batches = tud.DataLoader(range(len(self.dataset)), batch_size=self.batch_size, shuffle=self.shuffle,
+                                       collate_fn=list)
+        for ids in index_batches:
             if self.resident is not None:
                 yield self.resident.collate(ids)
             else:

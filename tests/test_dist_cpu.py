@@ -136,3 +136,23 @@ def test_packed_rows_format_roundtrip_on_the_host():
         assert int(p.rowptr[-1]) == p.vals.numel() == p.cols.numel()
     d = Data(x=torch.zeros(10, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.zeros(10, dtype=torch.long))
     assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
+
+
+def test_graph_loader_batches_follow_torchs_own_sampler():
+    """PyG's DataLoader is torch's DataLoader with a graph collate: for the same torch seed our loader must yield the
+    same graphs per batch and consume the CPU generator identically (pygda/models/a2gnn.py:276-286)."""
+    import torch.utils.data as tud
+    from pygda_b200.data import Data, DataLoader
+    ds = [Data(x=torch.full((2, 3), float(i)), edge_index=torch.tensor([[0], [1]]), y=torch.tensor([i])) for i in range(23)]
+    for bs in (1, 5, 23, 40):
+        torch.manual_seed(5)
+        ours = [b.y.tolist() for b in DataLoader(ds, batch_size=bs, shuffle=True)]
+        after_ours = torch.rand(1)
+        torch.manual_seed(5)
+        ref = [list(map(int, b)) for b in tud.DataLoader(list(range(23)), batch_size=bs, shuffle=True, collate_fn=list)]
+        assert ours == ref and torch.equal(after_ours, torch.rand(1))
+        assert len(DataLoader(ds, batch_size=bs)) == len(ref)
+    plain = [b.y.tolist() for b in DataLoader(ds, batch_size=10, shuffle=False)]
+    assert plain == [list(range(10)), list(range(10, 20)), [20, 21, 22]]
+    b = next(iter(DataLoader(ds, batch_size=4, shuffle=False)))
+    assert len(b) == 4 and b.batch.tolist() == [0, 0, 1, 1, 2, 2, 3, 3] and b.edge_index.tolist() == [[0, 2, 4, 6], [1, 3, 5, 7]]
