@@ -7,7 +7,7 @@ device-side forms the fit loops use for the per-epoch training score (pygda/mode
 import ctypes as C
 
 import torch
-from sklearn.metrics import f1_score
+from sklearn.metrics import average_precision_score, f1_score, roc_auc_score
 
 
 def eval_micro_f1(label, pred):
@@ -16,6 +16,32 @@ def eval_micro_f1(label, pred):
 
 def eval_macro_f1(label, pred):
     return f1_score(label.cpu().numpy(), pred.cpu().numpy(), average='macro')
+
+
+# The remaining host-side wrappers of pygda/metrics/metrics.py (binary scores of other estimators; never on the hot
+# path): same signatures and values, so that ``pygda.metrics`` is complete for callers that switch packages.
+def eval_roc_auc(label, score):
+    """ROC-AUC, mirrored into [0.5, 1] like the reference (metrics.py:4-40)."""
+    auc = roc_auc_score(y_true=label.cpu().numpy(), y_score=score.cpu().numpy())
+    return 1 - auc if auc < 0.5 else auc
+
+
+def eval_recall_at_k(label, score, k=None):
+    """Fraction of the positives among the k best-scored items (metrics.py:43-80); k defaults to #positives."""
+    if k is None:
+        k = sum(label)
+    return sum(label[score.topk(k).indices]) / sum(label)
+
+
+def eval_precision_at_k(label, score, k=None):
+    """Fraction of positives in the k best-scored items (metrics.py:83-118)."""
+    if k is None:
+        k = sum(label)
+    return sum(label[score.topk(k).indices]) / k
+
+
+def eval_average_precision(label, score):
+    return average_precision_score(y_true=label.cpu().numpy(), y_score=score.cpu().numpy())
 
 
 def confusion_from_logits(label, logits, return_pred=False):
@@ -65,5 +91,6 @@ def macro_f1_from_logits(label, logits):
     return f1_from_confusion(confusion_from_logits(label, logits), 'macro')
 
 
-__all__ = ["eval_micro_f1", "eval_macro_f1", "confusion_from_logits", "f1_from_confusion", "micro_f1_from_logits",
+__all__ = ["eval_micro_f1", "eval_macro_f1", "eval_roc_auc", "eval_recall_at_k", "eval_precision_at_k",
+           "eval_average_precision", "confusion_from_logits", "f1_from_confusion", "micro_f1_from_logits",
            "macro_f1_from_logits"]

@@ -201,3 +201,29 @@ def test_module_state_dict_layouts_equal_the_reference():
         m = getattr(NN, key.split("/")[0])(**blob["kwargs"])
         assert {k: list(v.shape) for k, v in m.state_dict().items()} == blob["state"], key
         assert sorted(k for k, p in m.named_parameters() if p.requires_grad) == blob["trainable"], key
+
+
+def test_host_metrics_equal_the_reference():
+    """pygda_b200.metrics (host-side wrappers) against values computed by the reference's own metrics.py."""
+    import json
+    import os
+    from conftest import GOLDEN
+    import pygda_b200.metrics as M
+    cases = json.load(open(os.path.join(GOLDEN, "metrics.json")))
+    assert len(cases) == 9
+    for c in cases:
+        label = torch.tensor(c["label"])
+        if c["tag"] == "multiclass":
+            pred = torch.tensor(c["pred"])
+            assert abs(M.eval_micro_f1(label, pred) - c["eval_micro_f1"]) < 1e-12
+            assert abs(M.eval_macro_f1(label, pred) - c["eval_macro_f1"]) < 1e-12
+            cm = torch.zeros(4, 4, dtype=torch.int64)
+            cm.index_put_((label, pred), torch.ones_like(label), accumulate=True)
+            assert abs(M.f1_from_confusion(cm, "micro") - c["eval_micro_f1"]) < 1e-12
+            assert abs(M.f1_from_confusion(cm, "macro") - c["eval_macro_f1"]) < 1e-12
+            continue
+        score = torch.tensor(c["score"])
+        assert abs(float(M.eval_roc_auc(label, score)) - c["eval_roc_auc"]) < 1e-12
+        assert abs(float(M.eval_recall_at_k(label, score)) - c["eval_recall_at_k"]) < 1e-7
+        assert abs(float(M.eval_precision_at_k(label, score, 7)) - c["eval_precision_at_k"]) < 1e-7
+        assert abs(float(M.eval_average_precision(label, score)) - c["eval_average_precision"]) < 1e-12
