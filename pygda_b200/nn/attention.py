@@ -17,6 +17,10 @@ class Attention(nn.Module):
     def forward(self, inputs):
         if len(inputs) == 2 and inputs[0].is_cuda and inputs[0].dim() == 2:
             return ops.Attention2Fn.apply(inputs[0], inputs[1], self.dense_weight.weight, self.dense_weight.bias)
-        stacked = torch.stack(inputs, dim=1)
-        weights = F.softmax(self.dense_weight(stacked), dim=1)
-        return torch.sum(stacked * weights, dim=1)
+        # any other number of views: one score per view, softmax across the views, weighted sum (:52-55)
+        scores = torch.cat([self.dense_weight(v) for v in inputs], dim=-1)
+        alpha = F.softmax(scores, dim=-1)
+        out = alpha[..., 0:1] * inputs[0]
+        for i in range(1, len(inputs)):
+            out = out + alpha[..., i:i + 1] * inputs[i]
+        return out
