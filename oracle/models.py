@@ -338,3 +338,136 @@ class DGSDA:
         loss.backward()
         self.optimizer.step()
         return val, s_logits
+
+
+class StruRW:
+    """pygda/models/strurw.py:21-758 -- ctor :83-139, init_model :141-187, forward_model :189-257,
+    forward_model_mixup :259-323, loop body of fit :406-421, cal_reweight :446-487, cal_edge_prob_sep :489-548,
+    predict :669-700, shuffle_data / id_node :702-758."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=2, cls_dim=128, cls_layers=2, dropout=0., gnn="GS",
+                 pooling="mean", reweight=True, pseudo=True, ew_start=100, ew_freq=20, lamb=0.8, mode="erm",
+                 act=F.relu, bn=False, weight_decay=0.0001, lr=0.05, epoch=100, **kwargs):
+        assert mode in ["erm", "mixup", "mmd", "adv"], "unsupport training mode"
+        self.num_classes, self.mode, self.epoch = num_classes, mode, epoch
+        self.reweight, self.pseudo, self.ew_start, self.ew_freq = reweight, pseudo, ew_start, ew_freq
+        if mode == "mixup":
+            self.gnn = ONN.MixupBase(in_dim, hid_dim, num_classes, num_layers=num_layers, dropout=dropout,
+                                     rw_lmda=lamb)
+        else:
+            self.gnn = ONN.ReweightGNN(in_dim, hid_dim, num_classes, cls_dim, gnn_layers=num_layers,
+                                       cls_layers=cls_layers, backbone=gnn, pooling=pooling, dropout=dropout, bn=bn,
+                                       rw_lmda=lamb)
+        params = list(self.gnn.parameters())
+        if mode == "adv":
+            self.domain_discriminator = torch.nn.Linear(hid_dim, 2)
+            params += list(self.domain_discriminator.parameters())
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
+        self.mmd_indices, self.mmd_sqdist = None, M.pairwise_sqdist_broadcast
+
+    # ---- edge re-weighting -----------------------------------------------------------------
+    @staticmethod
+    def class_edge_counts(edge_index, labels, num_classes):
+        """``one_hot.T * to_dense_adj(edge_index) * one_hot`` (:533-535): entry [i, j] = number of edges (with
+        multiplicity -- to_dense_adj sums duplicates) whose edge_index[0] end has class i and whose
+        edge_index[1] end has class j.  Counted directly instead of through the dense N x N adjacency; the
+        values are exact integers either way."""
+        code = labels[edge_index[0]] * num_classes + labels[edge_index[1]]
+        return torch.bincount(code, minlength=num_classes * num_classes).view(num_classes, num_classes).double()
+
+    def cal_edge_prob_sep(self, src_graph, tgt_graph, tgt_pred):           # :489-548
+        C = self.num_classes
+        n_src = torch.bincount(src_graph.y, minlength=C).double()
+        n_pred = torch.bincount(tgt_pred, minlength=C).double()
+        n_tgt = torch.bincount(tgt_graph.y, minlength=C).double()
+        src_edge_prob = self.class_edge_counts(src_graph.edge_index, src_graph.y, C) / torch.outer(n_src, n_src)
+        tgt_edge_prob = self.class_edge_counts(tgt_graph.edge_index, tgt_pred, C) / (torch.outer(n_pred, n_pred) + 1e-12)
+        tgt_true_edge_prob = self.class_edge_counts(tgt_graph.edge_index, tgt_graph.y, C) / torch.outer(n_tgt, n_tgt)
+        return src_edge_prob, tgt_edge_prob, tgt_true_edge_prob
+
+    def cal_reweight(self, source_data, target_data, target_pred):         # :446-487
+        src_edge_prob, tgt_edge_prob, _ = self.cal_edge_prob_sep(source_data, target_data, target_pred)
+        reweight_matrix = torch.div(tgt_edge_prob, src_edge_prob)
+        reweight_matrix[torch.isinf(reweight_matrix)] = 1
+        reweight_matrix[torch.isnan(reweight_matrix)] = 1
+        # :479-485 -- edge e gets reweight_matrix[i][j] with i = class of edge_index[1][e], j = class of
+        # edge_index[0][e] (both source labels: the indices of a source edge never reach the target_pred part
+        # of ``label_pred``); float64 -> float32 on assignment
+        y = source_data.y
+        ei = source_data.edge_index
+        source_data.edge_weight = reweight_matrix[y[ei[1]], y[ei[0]]].float()
+
+    def _maybe_reweight(self, source_data, target_data, target_pred, epoch):   # :220-226 / :283-289
+        if self.reweight and (epoch + 1) >= self.ew_start:
+            if self.pseudo:
+                if (epoch + 1) % self.ew_freq == 0:
+                    self.cal_reweight(source_data, target_data, target_pred)
+            elif epoch == self.ew_start - 1:
+                self.cal_reweight(source_data, target_data, target_pred)
+
+    # ---- objectives ------------------------------------------------------------------------
+    def forward_model(self, source_data, target_data, alpha, epoch):       # :189-257
+        target_feat, target_logits = self.gnn.forward(target_data, target_data.x)
+        target_pred = torch.max(F.softmax(target_logits, dim=1), dim=1)[1]
+        self._maybe_reweight(source_data, target_data, target_pred, epoch)
+        source_feat, source_logits = self.gnn.forward(source_data, source_data.x)
+        loss = F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y)
+        if self.mode == "adv":
+            sd = self.domain_discriminator(ONN.GradReverse.apply(source_feat, alpha))
+            td = self.domain_discriminator(ONN.GradReverse.apply(target_feat, alpha))
+            domain_label = torch.tensor([0] * source_data.x.shape[0] + [1] * target_data.x.shape[0])
+            loss = loss + F.cross_entropy(torch.cat([sd, td], 0), domain_label)
+        elif self.mode == "mmd":
+            loss = loss + M.MMD(source_feat, target_feat, indices=self.mmd_indices, sqdist=self.mmd_sqdist)
+        return loss, source_logits, target_logits
+
+    @staticmethod
+    def shuffle_edges(edge_index, num_nodes):
+        """shuffle_data / id_node (:702-758): a node permutation from ``np.random.shuffle`` and the edge list
+        re-labelled through its inverse."""
+        id_new_value_old = np.arange(num_nodes)
+        np.random.shuffle(id_new_value_old)
+        perm = torch.from_numpy(id_new_value_old)
+        id_old_value_new = torch.zeros(num_nodes, dtype=torch.long)
+        id_old_value_new[perm] = torch.arange(num_nodes, dtype=torch.long)
+        return torch.stack([id_old_value_new[edge_index[0]], id_old_value_new[edge_index[1]]], dim=0), id_new_value_old
+
+    def forward_model_mixup(self, source_data, target_data, epoch):        # :259-323
+        n_t = target_data.x.shape[0]
+        target_feat = self.gnn.feat_bottleneck(target_data.x, target_data.edge_index, target_data.edge_index, 1,
+                                               np.arange(n_t), target_data.edge_weight)
+        target_logits = self.gnn.feat_classifier(target_feat)
+        target_pred = torch.max(F.softmax(target_logits, dim=1), dim=1)[1]
+        self._maybe_reweight(source_data, target_data, target_pred, epoch)
+        lam = np.random.beta(4.0, 4.0)
+        edge_index_b, id_new_value_old = self.shuffle_edges(source_data.edge_index, source_data.x.shape[0])
+        source_feat = self.gnn.feat_bottleneck(source_data.x, source_data.edge_index, edge_index_b, lam,
+                                               id_new_value_old, source_data.edge_weight)
+        source_logits = self.gnn.feat_classifier(source_feat)
+        # :321 -- the loss uses the UNMIXED labels only (kept as in the reference)
+        loss = F.nll_loss(F.log_softmax(source_logits, dim=1), source_data.y)
+        return loss, source_logits, target_logits
+
+    def train_step(self, source_data, target_data, epoch=0):               # :406-421
+        self.gnn.train()
+        if self.mode == "mixup":
+            loss, s_logits, t_logits = self.forward_model_mixup(source_data, target_data, epoch)
+        else:
+            alpha = A2GNN.alpha_at(epoch, self.epoch)
+            loss, s_logits, t_logits = self.forward_model(source_data, target_data, alpha, epoch)
+        val = loss.item()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return val, s_logits, t_logits
+
+    def predict(self, data):                                               # :669-700
+        self.gnn.eval()
+        with torch.no_grad():
+            if self.mode == "mixup":
+                data.edge_weight = torch.ones(data.edge_index.shape[1])
+                logits = self.gnn(data.x, data.edge_index, data.edge_index, 1, np.arange(data.x.shape[0]),
+                                  data.edge_weight)
+            else:
+                _, logits = self.gnn(data, data.x)
+        return logits, data.y

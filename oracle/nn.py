@@ -442,3 +442,172 @@ class DGSDABase(nn.Module):
         x = self.lin2(x)
         x = F.dropout(x, p=self.dprate, training=self.training)
         return self.prop3(x, data.edge_index)
+
+
+def _reduce_rows(msg, row, n, aggr):
+    """PyG aggregation at ``edge_index[0]`` (flow='target_to_source'): 'add' = scatter-add, 'mean' = the sum
+    divided by max(#edges of the row, 1) [upstream MeanAggregation] -- rows without edges give 0."""
+    out = P.scatter_add(msg, row, 0, n)
+    if aggr == "mean":
+        cnt = P.scatter_add(torch.ones(row.numel(), dtype=msg.dtype), row, 0, n)
+        out = out / cnt.clamp(min=1).view(-1, 1)
+    return out
+
+
+class GCNReweight(nn.Module):
+    """``GCN_reweight`` pygda/nn/reweight_gnn.py:51-249 (ctor :78-113, forward :122-194, message :196-225).
+    flow='target_to_source' (:92): gathers x[edge_index[1]], reduces at edge_index[0].  aggr == 'add' switches
+    the normalisation OFF (:99-102); otherwise gcn_norm on unit weights without self loops (:161-163; degree at
+    edge_index[1], the upstream default flow of gcn_norm).  Message: w x_j ((1 - lmda) + lmda rw) (:223-224)."""
+
+    def __init__(self, in_channels, out_channels, aggr, improved=False, cached=False, add_self_loops=False,
+                 normalize=True, bias=True, **kwargs):
+        super().__init__()
+        self.aggr, self.improved, self.add_self_loops = aggr, improved, add_self_loops
+        self.normalize = aggr != "add"
+        self.lin = P.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+    def forward(self, x, edge_index, edge_weight, lmda):
+        edge_rw = edge_weight
+        edge_weight = torch.ones_like(edge_rw)
+        if self.normalize:
+            edge_index, edge_weight = P.gcn_norm_by_col(edge_index, edge_weight, x.size(0), self.improved,
+                                                        self.add_self_loops, x.dtype)
+        x = self.lin(x)
+        x_j = edge_weight.view(-1, 1) * x.index_select(0, edge_index[1])
+        x_j = (1 - lmda) * x_j + lmda * (edge_rw.view(-1, 1) * x_j)
+        out = _reduce_rows(x_j, edge_index[0], x.size(0), self.aggr)
+        return out if self.bias is None else out + self.bias
+
+
+class GSReweight(nn.Module):
+    """``GS_reweight`` pygda/nn/reweight_gnn.py:252-372: message = lin(x_j) ((1 - lmda) + lmda w) (:338-339, lin WITH
+    bias applied per edge), reduced at edge_index[0] (:275), update = relu(agg_lin(cat(aggr, x))) (+ L2
+    normalisation) (:366-372)."""
+
+    def __init__(self, in_channels, out_channels, reducer, normalize_embedding=False):
+        super().__init__()
+        self.aggr = reducer
+        self.lin = nn.Linear(in_channels, out_channels)
+        self.agg_lin = nn.Linear(out_channels + in_channels, out_channels)
+        self.normalize_emb = normalize_embedding
+
+    def forward(self, x, edge_index, edge_weight, lmda):
+        x_j = self.lin(x.index_select(0, edge_index[1]))
+        x_j = (1 - lmda) * x_j + lmda * (edge_weight.view(-1, 1) * x_j)
+        aggr_out = _reduce_rows(x_j, edge_index[0], x.size(0), self.aggr)
+        aggr_out = F.relu(self.agg_lin(torch.cat((aggr_out, x), dim=-1)))
+        if self.normalize_emb:
+            aggr_out = F.normalize(aggr_out, p=2, dim=-1)
+        return aggr_out
+
+
+class ReweightGNN(nn.Module):
+    """pygda/nn/reweight_gnn.py:375-502.  Quirks kept: ONE ``prop_hidden`` module serves every layer after the
+    first (:437-446 -- shared weights); ``bns`` are created but never applied (:493-494 commented out);
+    ``F.dropout(x, p)`` without ``training=`` (:496) -- dropout stays on in eval mode."""
+
+    def __init__(self, input_dim, gnn_dim, output_dim, cls_dim, gnn_layers=3, cls_layers=2, backbone="GS",
+                 pooling="mean", dropout=0.5, bn=False, rw_lmda=1.0, **kwargs):
+        super().__init__()
+        conv = {"GCN": GCNReweight, "GS": GSReweight}[backbone]
+        self.prop_input = conv(input_dim, gnn_dim, pooling)
+        self.prop_hidden = conv(gnn_dim, gnn_dim, pooling)
+        self.dropout, self.bn, self.lmda = dropout, bn, rw_lmda
+        self.conv = nn.ModuleList([self.prop_input] + [self.prop_hidden] * (gnn_layers - 1))
+        self.bns = nn.ModuleList([nn.BatchNorm1d(gnn_dim) for _ in range(gnn_layers - 1)])
+        self.bn_mlp = nn.BatchNorm1d(cls_dim)
+        self.mlp_classify = nn.ModuleList()
+        if cls_layers == 1:
+            self.mlp_classify.append(nn.Linear(gnn_dim, output_dim))
+        else:
+            self.mlp_classify.append(nn.Linear(gnn_dim, cls_dim))
+            for _ in range(cls_layers - 2):
+                self.mlp_classify.append(nn.Linear(cls_dim, cls_dim))
+            self.mlp_classify.append(nn.Linear(cls_dim, output_dim))
+
+    def forward(self, data, h):                                            # :462-502
+        x, edge_index, edge_weight = h, data.edge_index, data.edge_weight
+        for layer in self.conv:
+            x = layer(x, edge_index, edge_weight, self.lmda)
+            x = F.relu(x)
+            x = F.dropout(x, p=self.dropout)
+        y = x
+        for i, lin in enumerate(self.mlp_classify):
+            y = lin(y)
+            if i != len(self.mlp_classify) - 1:
+                if self.bn:
+                    y = self.bn_mlp(y)
+                y = F.relu(y)
+        return x, y
+
+
+class MixUpGCNConv(nn.Module):
+    """pygda/nn/mixup_gcnconv.py:91-247: out = sum_e w_e ((1 - lmda) + lmda rw_e) lin(x)[row_e] at col_e (default
+    flow) + lin_cen(x_cen) + bias, w = gcn_norm WITHOUT self loops on unit weights (:204-206; edge_weight is reset
+    to None first, :199-200)."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=False,
+                 normalize=True, bias=True, **kwargs):
+        super().__init__()
+        self.improved, self.add_self_loops, self.normalize = improved, add_self_loops, normalize
+        self.lin = P.Linear(in_channels, out_channels, bias=False)
+        self.lin_cen = P.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+    def forward(self, x, x_cen, edge_index, edge_weight=None, lmda=1):
+        edge_rw, edge_weight = edge_weight, None
+        if self.normalize:
+            edge_index, edge_weight = P.gcn_norm_by_col(edge_index, edge_weight, x.size(0), self.improved,
+                                                        self.add_self_loops, x.dtype)
+        x = self.lin(x)
+        x_j = edge_weight.view(-1, 1) * x.index_select(0, edge_index[0])
+        x_j = (1 - lmda) * x_j + lmda * (edge_rw.view(-1, 1) * x_j)
+        out = P.scatter_add(x_j, edge_index[1], 0, x.size(0)) + self.lin_cen(x_cen)
+        return out if self.bias is None else out + self.bias
+
+
+class MixupBase(nn.Module):
+    """pygda/nn/mixup_base.py:10-200: two-branch mixup over MixUpGCNConv layers (feat_bottleneck :99-178)."""
+
+    def __init__(self, in_dim, hid_dim, num_classes, num_layers=1, dropout=0.1, act=F.relu, rw_lmda=0.8, **kwargs):
+        super().__init__()
+        self.dropout, self.act, self.rw_lmda = dropout, act, rw_lmda
+        self.convs = nn.ModuleList([MixUpGCNConv(in_dim, hid_dim)] +
+                                   [MixUpGCNConv(hid_dim, hid_dim) for _ in range(num_layers - 1)])
+        self.cls = nn.Linear(hid_dim, num_classes)
+
+    def forward(self, x, edge_index, edge_index_b, lam, id_new_value_old, edge_weight):
+        return self.cls(self.feat_bottleneck(x, edge_index, edge_index_b, lam, id_new_value_old, edge_weight))
+
+    def feat_classifier(self, x):
+        return self.cls(x)
+
+    def feat_bottleneck(self, x, edge_index, edge_index_b, lam, id_new_value_old, edge_weight):
+        def drop(t):
+            return F.dropout(t, p=self.dropout, training=self.training)
+
+        def conv(i, a, cen, ei):
+            return self.convs[i](a, cen, ei, edge_weight, self.rw_lmda)
+
+        perm = torch.as_tensor(id_new_value_old, dtype=torch.long)
+        x1 = drop(self.act(conv(0, x, x, edge_index)))                     # :129-135
+        x2 = drop(self.act(conv(1, x1, x1, edge_index)))
+        x0_b, x1_b = x[perm], x1[perm]                                     # :137-138
+        x_mix = x * lam + x0_b * (1 - lam)                                 # :140
+        new_x1 = self.act(conv(0, x, x_mix, edge_index))                   # :142-146
+        new_x1_b = self.act(conv(0, x0_b, x_mix, edge_index_b))
+        x1_mix = drop(new_x1 * lam + new_x1_b * (1 - lam))
+        new_x2 = self.act(conv(1, x1, x1_mix, edge_index))                 # :150-156
+        new_x2_b = self.act(conv(1, x1_b, x1_mix, edge_index_b))
+        x_mix = drop(new_x2 * lam + new_x2_b * (1 - lam))
+        x = x2
+        for i in range(2, len(self.convs)):                                # :161-176
+            x_t = drop(self.act(conv(i, x, x, edge_index)))
+            x_b = x[perm]
+            new_x = self.act(conv(i, x, x_mix, edge_index))
+            new_x_b = self.act(conv(i, x_b, x_mix, edge_index_b))
+            x_mix = drop(new_x * lam + new_x_b * (1 - lam))
+            x = x_t
+        return x_mix

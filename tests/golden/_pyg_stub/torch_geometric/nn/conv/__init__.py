@@ -6,32 +6,41 @@ from oracle import pyg_ops as P
 
 
 class MessagePassing(torch.nn.Module):
-    """aggr='add', flow='source_to_target', node_dim=0."""
+    """node_dim=0; aggr 'add' | 'mean'; flow 'source_to_target' (x_j = x[edge_index[0]], reduce at
+    edge_index[1]) | 'target_to_source' (x_j = x[edge_index[1]], reduce at edge_index[0])
+    (SURVEY Appendix A.2).  'mean' = sum / max(count, 1) as in PyG's MeanAggregation."""
 
     def __init__(self, aggr='add', flow='source_to_target', node_dim=0, **kwargs):
         super().__init__()
-        assert aggr == 'add' and flow == 'source_to_target' and node_dim == 0
+        assert aggr in ('add', 'mean') and flow in ('source_to_target', 'target_to_source') and node_dim == 0
         self.aggr, self.flow, self.node_dim = aggr, flow, node_dim
 
     def propagate(self, edge_index, size=None, **kwargs):
         assert torch.is_tensor(edge_index)
+        j, i = (0, 1) if self.flow == 'source_to_target' else (1, 0)
         params = list(inspect.signature(self.message).parameters)
         args = {}
-        n = None
+        n = None if size is None else size[i]
         for name in params:
             if name.endswith('_j'):
                 src = kwargs[name[:-2]]
-                n = src.size(0)
-                args[name] = src.index_select(0, edge_index[0])
+                n = src.size(0) if n is None else n
+                args[name] = src.index_select(0, edge_index[j])
             elif name.endswith('_i'):
                 src = kwargs[name[:-2]]
-                n = src.size(0)
-                args[name] = src.index_select(0, edge_index[1])
+                n = src.size(0) if n is None else n
+                args[name] = src.index_select(0, edge_index[i])
+            elif name == 'edge_index':
+                args[name] = edge_index
             else:
                 args[name] = kwargs.get(name)
         msg = self.message(**args)
-        out = P.scatter_add(msg, edge_index[1], 0, n)
-        return self.update(out)
+        out = P.scatter_add(msg, edge_index[i], 0, n)
+        if self.aggr == 'mean':
+            cnt = P.scatter_add(torch.ones(edge_index.size(1), dtype=msg.dtype), edge_index[i], 0, n)
+            out = out / cnt.clamp(min=1).view(-1, 1)
+        extra = {k: kwargs[k] for k in list(inspect.signature(self.update).parameters)[1:] if k in kwargs}
+        return self.update(out, **extra)
 
     def message(self, x_j):
         return x_j

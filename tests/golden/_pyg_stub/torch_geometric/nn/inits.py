@@ -9,3 +9,10 @@ def glorot(t):
 def zeros(t):
     if t is not None:
         t.data.fill_(0.)
+
+
+def uniform(size, t):
+    import math
+    if t is not None:
+        bound = 1.0 / math.sqrt(size)
+        t.data.uniform_(-bound, bound)

@@ -15,3 +15,13 @@ def add_self_loops(edge_index, edge_attr=None, fill_value=None, num_nodes=None):
 def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce="sum", is_sorted=False, sort_by_row=True):
     # pygda/models/tdss.py:79 calls coalesce(edge_index, None, N, N): the 4th positional lands in `reduce`
     return _coalesce(edge_index, edge_attr, num_nodes)
+
+
+def to_dense_adj(edge_index, batch=None, edge_attr=None, max_num_nodes=None):
+    """[1, N, N] with adj[0, row, col] += 1 per edge (pygda/models/strurw.py:509-510)."""
+    import torch
+    assert batch is None and edge_attr is None
+    n = max_num_nodes if max_num_nodes is not None else int(edge_index.max()) + 1
+    adj = torch.zeros(n, n)
+    adj.index_put_((edge_index[0], edge_index[1]), torch.ones(edge_index.size(1)), accumulate=True)
+    return adj.unsqueeze(0)

@@ -76,4 +76,11 @@ def load_reference():
     ns.dgsda_base = imp("pygda.nn.dgsda_base")
     pkg.nn.DGSDABase = ns.dgsda_base.DGSDABase
     ns.dgsda = imp("pygda.models.dgsda")
+    ns.reweight_gnn = imp("pygda.nn.reweight_gnn")
+    pkg.nn.ReweightGNN = ns.reweight_gnn.ReweightGNN
+    ns.mixup_gcnconv = imp("pygda.nn.mixup_gcnconv")
+    pkg.nn.MixUpGCNConv = ns.mixup_gcnconv.MixUpGCNConv
+    ns.mixup_base = imp("pygda.nn.mixup_base")
+    pkg.nn.MixupBase = ns.mixup_base.MixupBase
+    ns.strurw = imp("pygda.models.strurw")
     return ns
