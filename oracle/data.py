@@ -43,11 +43,19 @@ class FullBatchNeighborLoader:
         # attributes PyG classifies as neither node- nor edge-level (e.g. TDSS's edge_index_smooth,
         # pygda/models/tdss.py:503) are copied through unchanged by NeighborLoader's filter_data
         extra = {k: v for k, v in data.__dict__.items() if k not in ("x", "edge_index", "y", "batch", "num_graphs")}
+        for k in ("edge_weight", "edge_attr"):      # edge-level attributes are filtered with their edges
+            v = extra.get(k)
+            if torch.is_tensor(v) and v.dim() >= 1 and v.size(0) == ei.size(1):
+                extra[k] = v[order].contiguous()
         self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
                            batch=getattr(data, "batch", None), **extra)
 
     def __iter__(self):
-        yield self._batch
+        # a NEW Data per batch, as PyG's filter_data builds one: attributes set on a yielded batch
+        # (pygda/models/strurw.py:487) are gone the next epoch
+        out = Data.__new__(Data)
+        out.__dict__.update(self._batch.__dict__)
+        yield out
 
     def __len__(self):
         return 1

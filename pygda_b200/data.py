@@ -102,6 +102,11 @@ class Data:
             part = getattr(src, "_gda_partition", None)      # row-partitioned multi-GPU graph tag
             if part is not None:
                 ei._gda_partition = part
+        ew, wsrc = out.__dict__.get("edge_weight"), self.__dict__.get("edge_weight")
+        if torch.is_tensor(ew) and ew is not wsrc:
+            # same for per-edge weights (StruRW): the re-weighted CSR is keyed by the host tensor they came from
+            ew._gda_key = getattr(wsrc, "_gda_key", None) or ("src", wsrc.data_ptr(), wsrc._version, str(wsrc.device))
+            ew._gda_keepalive = getattr(wsrc, "_gda_keepalive", wsrc)
         return out
 
     def pin_memory(self, pack="auto"):
@@ -195,6 +200,10 @@ class NeighborLoader:
         extra = {k: v for k, v in data.__dict__.items()
                  if k not in ("x", "edge_index", "y", "batch", "num_graphs")}
         extra.pop("_packed_x", None)
+        for k in ("edge_weight", "edge_attr"):      # edge-level attributes travel with their edges [upstream filter_data]
+            v = extra.get(k)
+            if torch.is_tensor(v) and v.dim() >= 1 and v.size(0) == ei.size(1):
+                extra[k] = v[order.to(v.device)].contiguous()
         self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
                            batch=data.batch, num_graphs=data.num_graphs, **extra)
         # the fit loops send this one batch host->device on EVERY step (pygda/models/a2gnn.py:311-312): stage it in
@@ -203,7 +212,12 @@ class NeighborLoader:
             self._batch = self._batch.pin_memory()
 
     def __iter__(self):
-        yield self._batch
+        # PyG builds a NEW Data object for every batch: attributes a fit loop sets on the batch it was handed
+        # (StruRW's re-weighted ``edge_weight``, pygda/models/strurw.py:487) do not survive into the next epoch.
+        # The copy is shallow -- same tensors, so graph / split caches keyed by tensor identity keep hitting.
+        out = self._batch.__class__.__new__(self._batch.__class__)
+        out.__dict__.update(self._batch.__dict__)
+        yield out
 
     def __len__(self):
         return 1

@@ -7,5 +7,6 @@ from .adagcn import AdaGCN
 from .gnn import GNN
 from .tdss import TDSS
 from .dgsda import DGSDA
+from .strurw import StruRW
 
-__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE", "AdaGCN", "GNN", "TDSS", "DGSDA"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn
+__all__ = ["BaseGDA", "A2GNN", "UDAGCN", "GRADE", "AdaGCN", "GNN", "TDSS", "DGSDA", "StruRW"]   # DistA2GNN: import pygda_b200.models.dist_a2gnn

@@ -11,6 +11,10 @@ from .adagcn_base import AdaGCNBase
 from .gnn_base import GNNBase
 from .gat_conv import GATConv
 from .dgsda_base import BernProp, DGSDABase
+from .reweight_gnn import GCN_reweight, GS_reweight, ReweightGNN
+from .mixup_gcnconv import MixUpGCNConv
+from .mixup_base import MixupBase
 
 __all__ = ["GradReverse", "PropGCNConv", "GCNConv", "gcn_norm", "A2GNNBase", "CachedGCNConv", "PPMIConv", "Attention",
-           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv", "BernProp", "DGSDABase"]
+           "UDAGCNBase", "GRADEBase", "AdaGCNBase", "GNNBase", "GATConv", "BernProp", "DGSDABase",
+           "GCN_reweight", "GS_reweight", "ReweightGNN", "MixUpGCNConv", "MixupBase"]

@@ -1,0 +1,167 @@
+"""GCN_reweight / GS_reweight / ReweightGNN -- drop-in for pygda/nn/reweight_gnn.py:51-502.
+
+Both layers are the aggregation kernel of the GCN path (``gda_spmm_f32``) with a different ``vals[]``: the
+reference's per-edge message  w_e x_j ((1 - lmda) + lmda rw_e)  (:223-224, :338-339) reduced at ``edge_index[0]``
+(flow='target_to_source', :92, :275) by 'add' or 'mean' is  out = A X  with
+
+    A[row_e, col_e] += w_e ((1 - lmda) + lmda rw_e) / (number of edges of row_e  if 'mean' else 1)
+
+so the weights are folded into one CSR per (edge_index, edge_weight, lmda) -- rebuilt only when StruRW re-weights
+the source edges (every ``ew_freq`` epochs, pygda/models/strurw.py:220-226), not per call -- and the [E, H] message
+tensor of the reference is never formed.  GS_reweight applies its Linear (with bias) per EDGE (:338); a linear map
+commutes with the gather, so it is applied per NODE here (N rows instead of E).
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..graph import NORM_SYM_COL, Graph, GraphCache
+from .layers import Linear
+from .prop_gcn_conv import GlorotLinear
+
+_graphs = OrderedDict()
+_GRAPH_SLOTS = 16
+
+
+def message_values(edge_index, w_norm, edge_rw, lmda, num_nodes, aggr, to_source=True):
+    """``vals[e]`` of the folded aggregation matrix: w_e ((1 - lmda) + lmda rw_e), divided by the number of edges
+    that reduce into the same node for 'mean' [upstream MeanAggregation: sum / max(count, 1)].  Plain torch on
+    [E]-sized vectors -- index plumbing done once per edge-weight version, not per step."""
+    if aggr not in ("add", "mean"):
+        raise ValueError(f"unsupported aggregation {aggr!r}")
+    val = w_norm if w_norm is not None else torch.ones(edge_index.size(1), dtype=torch.float32,
+                                                        device=edge_index.device)
+    if edge_rw is not None:
+        val = val * ((1 - lmda) + lmda * edge_rw.to(torch.float32))
+    if aggr == "mean":
+        tgt = edge_index[0] if to_source else edge_index[1]
+        cnt = torch.bincount(tgt, minlength=num_nodes).clamp_(min=1)
+        val = val / cnt[tgt].to(torch.float32)
+    return val
+
+
+def message_graph(edge_index, edge_rw, lmda, num_nodes, normalize, aggr, to_source=True):
+    """Aggregation graph of the re-weighted message passing described in the module docstring.
+
+    ``normalize``: gcn_norm on unit weights WITHOUT self loops, degree at ``edge_index[1]`` (gcn_norm's default flow;
+    reweight_gnn.py:161-163, mixup_gcnconv.py:204-206).  ``to_source``: reduce at ``edge_index[0]`` (the two
+    *_reweight layers) instead of ``edge_index[1]`` (MixUpGCNConv)."""
+    rw_key = None
+    if edge_rw is not None:
+        rw_key = getattr(edge_rw, "_gda_key", None) or ("dev", edge_rw.data_ptr(), edge_rw._version)
+    key = (GraphCache.key_of(edge_index), rw_key, float(lmda), int(num_nodes), bool(normalize), aggr, bool(to_source))
+    hit = _graphs.get(key)
+    if hit is not None:
+        _graphs.move_to_end(key)
+        return hit[0]
+    w_norm = None
+    if normalize:
+        _, w_norm = Graph(edge_index, num_nodes, None, NORM_SYM_COL).coo()     # d^-1/2[row] d^-1/2[col], input order
+    val = message_values(edge_index, w_norm, edge_rw, lmda, num_nodes, aggr, to_source)
+    ei = edge_index.flip(0).contiguous() if to_source else edge_index       # Graph reduces at its second row
+    g = Graph(ei, num_nodes, val, 0)
+    # the entry keeps the keyed tensors (or the host tensors they were copied from) alive: no address re-use
+    _graphs[key] = (g, getattr(edge_index, "_gda_keepalive", edge_index),
+                    None if edge_rw is None else getattr(edge_rw, "_gda_keepalive", edge_rw))
+    while len(_graphs) > _GRAPH_SLOTS:
+        _graphs.popitem(last=False)
+    return g
+
+
+class GCN_reweight(nn.Module):
+    def __init__(self, in_channels, out_channels, aggr, improved=False, cached=False, add_self_loops=False,
+                 normalize=True, bias=True, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels, self.aggr = in_channels, out_channels, aggr
+        self.improved, self.cached, self.add_self_loops = improved, cached, add_self_loops
+        if improved or add_self_loops:
+            raise NotImplementedError("GCN_reweight is only ever built with its defaults (reweight_gnn.py:429-430)")
+        self.normalize = aggr != "add"                                        # :99-102
+        self.lin = GlorotLinear(in_channels, out_channels)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    def forward(self, x, edge_index, edge_weight, lmda):                      # :122-194
+        g = message_graph(edge_index, edge_weight, lmda, x.size(0), self.normalize, self.aggr)
+        return ops.graph_conv(x, self.lin.weight, self.bias, g, 1)
+
+
+class GS_reweight(nn.Module):
+    def __init__(self, in_channels, out_channels, reducer, normalize_embedding=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.aggr = in_channels, out_channels, reducer
+        self.lin = Linear(in_channels, out_channels)
+        self.agg_lin = Linear(out_channels + in_channels, out_channels)
+        self.normalize_emb = normalize_embedding
+
+    def forward(self, x, edge_index, edge_weight, lmda):                      # :281-372
+        g = message_graph(edge_index, edge_weight, lmda, x.size(0), False, self.aggr)
+        aggr_out = ops.PropagateFn.apply(self.lin(x), g, 1)
+        # agg_lin(cat(aggr_out, x)) (:366-367) without materialising the [N, out + in] concatenation
+        # (in = 6775 input features at the first layer): the weight is split instead
+        w = self.agg_lin.weight
+        out = ops.linear(aggr_out, w[:, :self.out_channels], self.agg_lin.bias) + \
+            ops.linear(x, w[:, self.out_channels:], None)
+        out = ops.act_dropout(out, F.relu, 0.0, False)                        # :368
+        if self.normalize_emb:                                                # :370-371 (never enabled by ReweightGNN)
+            out = F.normalize(out, p=2, dim=-1)
+        return out
+
+
+class ReweightGNN(nn.Module):
+    """reweight_gnn.py:375-502.  Quirks kept: ONE ``prop_hidden`` module serves every layer after the first
+    (:437-446); ``bns`` exist but are never applied (:493-494); ``F.dropout(x, p)`` has no ``training=`` (:496), so
+    the dropout stays on in eval mode / ``predict``."""
+
+    def __init__(self, input_dim, gnn_dim, output_dim, cls_dim, gnn_layers=3, cls_layers=2, backbone='GS',
+                 pooling='mean', dropout=0.5, bn=False, rw_lmda=1.0, **kwargs):
+        super().__init__()
+        if backbone == 'GCN':
+            self.prop_input = GCN_reweight(input_dim, gnn_dim, pooling)
+            self.prop_hidden = GCN_reweight(gnn_dim, gnn_dim, pooling)
+        elif backbone == 'GS':
+            self.prop_input = GS_reweight(input_dim, gnn_dim, pooling)
+            self.prop_hidden = GS_reweight(gnn_dim, gnn_dim, pooling)
+        self.dropout, self.bn, self.lmda = dropout, bn, rw_lmda
+        self.conv = nn.ModuleList()
+        self.conv.append(self.prop_input)
+        for _ in range(gnn_layers - 1):
+            self.conv.append(self.prop_hidden)
+        self.bns = nn.ModuleList()
+        for _ in range(gnn_layers - 1):
+            self.bns.append(nn.BatchNorm1d(gnn_dim))
+        self.bn_mlp = nn.BatchNorm1d(cls_dim)
+        self.mlp_classify = nn.ModuleList()
+        if cls_layers == 1:
+            self.mlp_classify.append(Linear(gnn_dim, output_dim))
+        else:
+            self.mlp_classify.append(Linear(gnn_dim, cls_dim))
+            for _ in range(cls_layers - 2):
+                self.mlp_classify.append(Linear(cls_dim, cls_dim))
+            self.mlp_classify.append(Linear(cls_dim, output_dim))
+
+    def forward(self, data, h):                                               # :462-502
+        x, edge_index, edge_weight = h, data.edge_index, data.edge_weight
+        for layer in self.conv:
+            x = layer(x, edge_index, edge_weight, self.lmda)
+            x = ops.act_dropout(x, F.relu, self.dropout, True)                # relu + always-on dropout (:495-496)
+        y = x
+        last = len(self.mlp_classify) - 1
+        for i, lin in enumerate(self.mlp_classify):
+            y = lin(y)
+            if i != last:
+                if self.bn:
+                    y = self.bn_mlp(y)        # torch BatchNorm1d on [N, cls_dim]; off by default (bn=False)
+                y = ops.act_dropout(y, F.relu, 0.0, False)
+        return x, y

@@ -22,7 +22,7 @@ def simple(v):
 def main():
     ref = load_reference()
     classes = {"A2GNN": ref.a2gnn.A2GNN, "UDAGCN": ref.udagcn.UDAGCN, "GRADE": ref.grade.GRADE, "AdaGCN": ref.adagcn.AdaGCN,
-               "GNN": ref.gnn.GNN, "TDSS": ref.tdss.TDSS, "DGSDA": ref.dgsda.DGSDA}
+               "GNN": ref.gnn.GNN, "TDSS": ref.tdss.TDSS, "DGSDA": ref.dgsda.DGSDA, "StruRW": ref.strurw.StruRW}
     out = {}
     for name, cls in classes.items():
         for tag, kw in (("defaults", dict(in_dim=12, hid_dim=8, num_classes=3, device="cpu")),

@@ -34,6 +34,14 @@ def main():
         "models.GNN": (ref.gnn.GNN, ["__init__", "forward_model", "fit", "predict", "init_model"]),
         "models.TDSS": (ref.tdss.TDSS, ["__init__", "forward_model", "fit", "predict", "smoothness", "compute_laplacian_loss"]),
         "models.DGSDA": (ref.dgsda.DGSDA, ["__init__", "forward_model", "fit", "predict", "entropy_minimization_loss"]),
+        "models.StruRW": (ref.strurw.StruRW, ["__init__", "forward_model", "forward_model_mixup", "fit", "predict", "init_model",
+                                              "cal_reweight", "cal_edge_prob_sep", "cal_str_dif_rel", "cal_str_diff_ratio",
+                                              "shuffle_data", "id_node"]),
+        "nn.GCN_reweight": (ref.reweight_gnn.GCN_reweight, ["__init__", "forward"]),
+        "nn.GS_reweight": (ref.reweight_gnn.GS_reweight, ["__init__", "forward"]),
+        "nn.ReweightGNN": (ref.reweight_gnn.ReweightGNN, ["__init__", "forward"]),
+        "nn.MixUpGCNConv": (ref.mixup_gcnconv.MixUpGCNConv, ["__init__", "forward"]),
+        "nn.MixupBase": (ref.mixup_base.MixupBase, ["__init__", "forward", "feat_bottleneck", "feat_classifier"]),
         "nn.PropGCNConv": (ref.prop_gcn_conv.PropGCNConv, ["__init__", "forward"]),
         "nn.CachedGCNConv": (ref.cached_gcn_conv.CachedGCNConv, ["__init__", "forward", "norm"]),
         "nn.PPMIConv": (ref.ppmi_conv.PPMIConv, ["__init__", "norm"]),

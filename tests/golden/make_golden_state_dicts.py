@@ -32,6 +32,12 @@ def main():
         "CachedGCNConv": (ref.cached_gcn_conv.CachedGCNConv, dict(in_channels=12, out_channels=8)),
         "PPMIConv": (ref.ppmi_conv.PPMIConv, dict(in_channels=12, out_channels=8, path_len=7)),
         "Attention": (ref.attention.Attention, dict(in_channels=8)),
+        "ReweightGNN/GS": (ref.reweight_gnn.ReweightGNN, dict(input_dim=12, gnn_dim=8, output_dim=3, cls_dim=6, gnn_layers=3, cls_layers=2, backbone="GS")),
+        "ReweightGNN/GCN": (ref.reweight_gnn.ReweightGNN, dict(input_dim=12, gnn_dim=8, output_dim=3, cls_dim=6, gnn_layers=2, cls_layers=3, backbone="GCN", pooling="add")),
+        "GCN_reweight": (ref.reweight_gnn.GCN_reweight, dict(in_channels=12, out_channels=8, aggr="mean")),
+        "GS_reweight": (ref.reweight_gnn.GS_reweight, dict(in_channels=12, out_channels=8, reducer="mean")),
+        "MixUpGCNConv": (ref.mixup_gcnconv.MixUpGCNConv, dict(in_channels=12, out_channels=8)),
+        "MixupBase": (ref.mixup_base.MixupBase, dict(in_dim=12, hid_dim=8, num_classes=3, num_layers=3)),
     }
     out = {}
     for name, (cls, kw) in cases.items():
