@@ -188,7 +188,7 @@ class NeighborLoader:
     reference's own scaling tool and is replaced here by node partitioning
     (DESIGN.md section 6); asking for it raises."""
 
-    def __init__(self, data, num_neighbors, batch_size=None, pin=False, **kw):
+    def __init__(self, data, num_neighbors, batch_size=None, pin=False, prefetch_device=None, **kw):
         n = data.x.shape[0]
         if batch_size is not None and batch_size != n:
             raise NotImplementedError(
@@ -208,10 +208,45 @@ class NeighborLoader:
                            batch=data.batch, num_graphs=data.num_graphs, **extra)
         # the fit loops send this one batch host->device on EVERY step (pygda/models/a2gnn.py:311-312): stage it in
         # pinned memory once (a sparse x row-compressed, Data.pin_memory) instead of paging it through each time
-        if pin and torch.cuda.is_available() and torch.is_tensor(data.x) and not data.x.is_cuda:
+        host = torch.is_tensor(data.x) and not data.x.is_cuda
+        if pin and torch.cuda.is_available() and host:
             self._batch = self._batch.pin_memory()
+        # Opt-in software pipeline for host-resident graphs: the copy of the NEXT epoch's batch is issued on a side
+        # stream when the current one is handed out, so PCIe traffic overlaps the training step instead of preceding
+        # it (the reference's loop copies, then computes: a2gnn.py:311-319).  Same bytes, same values.
+        self._prefetch_device = None
+        if prefetch_device is not None and pin and host and torch.cuda.is_available() \
+                and torch.device(prefetch_device).type == "cuda":
+            self._prefetch_device = torch.device(prefetch_device)
+        self._staged, self._side = None, None
+
+    def _stage(self):
+        dev = self._prefetch_device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(self._side):
+            d = self._batch.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return d, ev
+
+    def _iter_prefetched(self):
+        dev = self._prefetch_device
+        if self._staged is None:
+            self._staged = self._stage()
+        d, ev = self._staged
+        self._staged = self._stage()                     # next epoch's copy starts now
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(ev)
+        for v in d.__dict__.values():                    # allocated on the side stream, consumed on this one
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(main)
+        yield d
 
     def __iter__(self):
+        if self._prefetch_device is not None:
+            yield from self._iter_prefetched()
+            return
         # PyG builds a NEW Data object for every batch: attributes a fit loop sets on the batch it was handed
         # (StruRW's re-weighted ``edge_weight``, pygda/models/strurw.py:487) do not survive into the next epoch.
         # The copy is shallow -- same tensors, so graph / split caches keyed by tensor identity keep hitting.

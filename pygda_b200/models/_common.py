@@ -16,16 +16,22 @@ class TwoDomainLoop:
             self.num_source_nodes, _ = source_data.x.shape
             self.num_target_nodes, _ = target_data.x.shape
             pin = str(self.device).startswith('cuda')       # host-resident graphs: pinned (packed) staging, once
+            # opt-in (``estimator.prefetch = True``): next epoch's host->device copy overlaps the current step
+            pf = self.device if (pin and getattr(self, 'prefetch', False)) else None
             if self.batch_size == 0:
                 self.source_batch_size = source_data.x.shape[0]
                 self.source_loader = NeighborLoader(source_data, self.num_neigh,
-                                                    batch_size=self.source_batch_size, pin=pin)
+                                                    batch_size=self.source_batch_size, pin=pin,
+                                                    prefetch_device=pf)
                 self.target_batch_size = target_data.x.shape[0]
                 self.target_loader = NeighborLoader(target_data, self.num_neigh,
-                                                    batch_size=self.target_batch_size, pin=pin)
+                                                    batch_size=self.target_batch_size, pin=pin,
+                                                    prefetch_device=pf)
             else:
-                self.source_loader = NeighborLoader(source_data, self.num_neigh, batch_size=self.batch_size, pin=pin)
-                self.target_loader = NeighborLoader(target_data, self.num_neigh, batch_size=self.batch_size, pin=pin)
+                self.source_loader = NeighborLoader(source_data, self.num_neigh, batch_size=self.batch_size, pin=pin,
+                                                    prefetch_device=pf)
+                self.target_loader = NeighborLoader(target_data, self.num_neigh, batch_size=self.batch_size, pin=pin,
+                                                    prefetch_device=pf)
         elif self.mode == 'graph':
             # datasets given as sequences of graphs are made resident on the device once and collated there
             dev = self.device if isinstance(source_data, (list, tuple)) and isinstance(target_data, (list, tuple)) \
