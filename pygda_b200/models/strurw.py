@@ -100,33 +100,28 @@ class StruRW(BaseGDA):
         y, ei = source_data.y, source_data.edge_index
         source_data.edge_weight = reweight_matrix[y[ei[1]], y[ei[0]]].float()
 
+    # Diagnostics of the reference (never called by its fit loop; ``calculate_str_diff`` :616-652 refers to a missing
+    # ``cal_str_dif_log`` and cannot run there, so it is not reproduced).  Same values, written with torch.where.
     def cal_str_dif_rel(self, pred_mtx, true_mtx):                                        # :550-582
-        cls1_diff = torch.abs(pred_mtx - true_mtx)
-        cls0_diff = torch.abs((1 - pred_mtx) - (1 - true_mtx))
-        abs_diff = 0.5 * cls0_diff + 0.5 * cls1_diff
-        rel_diff_1 = abs_diff / true_mtx
-        rel_diff_2 = abs_diff / pred_mtx
-        rel_diff = 0.5 * rel_diff_1 + 0.5 * rel_diff_2
-        rel_diff[torch.isinf(rel_diff_1)] = rel_diff_2[torch.isinf(rel_diff_1)]
-        rel_diff[torch.isinf(rel_diff_2)] = rel_diff_1[torch.isinf(rel_diff_2)]
-        rel_diff[torch.isnan(rel_diff)] = 0
-        num = true_mtx.size(0) * true_mtx.size(1)
-        return torch.sum(abs_diff) / num, torch.sum(rel_diff) / num
+        """(mean absolute, mean relative) difference of two [C, C] edge-probability tables."""
+        abs_diff = 0.5 * ((1 - pred_mtx) - (1 - true_mtx)).abs() + 0.5 * (pred_mtx - true_mtx).abs()
+        by_true, by_pred = abs_diff / true_mtx, abs_diff / pred_mtx
+        rel = 0.5 * by_true + 0.5 * by_pred
+        rel = torch.where(torch.isinf(by_true), by_pred, rel)          # a zero in one table: the other ratio alone
+        rel = torch.where(torch.isinf(by_pred), by_true, rel)
+        rel = torch.where(torch.isnan(rel), torch.zeros_like(rel), rel)
+        return abs_diff.sum() / abs_diff.numel(), rel.sum() / abs_diff.numel()
 
     def cal_str_diff_ratio(self, pred_mtx, true_mtx):                                     # :584-614
-        intra_prob_pred = torch.diagonal(pred_mtx, 0).repeat_interleave(pred_mtx.size(1)).view(-1, pred_mtx.size(1))
-        intra_prob_true = torch.diagonal(true_mtx, 0).repeat_interleave(true_mtx.size(1)).view(-1, true_mtx.size(1))
-        pred_ratio = torch.div(pred_mtx, intra_prob_pred)
-        true_ratio = torch.div(true_mtx, intra_prob_true)
-        pred_ratio[torch.isnan(pred_ratio)] = 1
-        true_ratio[torch.isnan(true_ratio)] = 1
-        pred_ratio[torch.isinf(pred_ratio)] = pred_mtx[torch.isinf(pred_ratio)]
-        true_ratio[torch.isinf(true_ratio)] = true_mtx[torch.isinf(true_ratio)]
-        ratio_diff = torch.div(pred_ratio, true_ratio)
-        ratio_diff[torch.isnan(ratio_diff)] = 1
-        ratio_diff[torch.isinf(ratio_diff)] = 1
-        num = true_mtx.size(0) * true_mtx.size(1) - pred_mtx.size(0)
-        return (torch.sum(ratio_diff) - torch.sum(torch.diagonal(ratio_diff))) / num
+        """Mean off-diagonal ratio of the two tables' (inter / intra)-class probability ratios."""
+        def to_intra(m):
+            r = m / m.diagonal().view(-1, 1)                          # row i divided by its intra-class entry
+            r = torch.where(torch.isnan(r), torch.ones_like(r), r)
+            return torch.where(torch.isinf(r), m, r)
+
+        ratio = to_intra(pred_mtx) / to_intra(true_mtx)
+        ratio = torch.where(torch.isnan(ratio) | torch.isinf(ratio), torch.ones_like(ratio), ratio)
+        return (ratio.sum() - ratio.diagonal().sum()) / (ratio.numel() - ratio.size(0))
 
     # ---- objectives ------------------------------------------------------------------------------------------
     def forward_model(self, source_data, target_data, alpha, epoch, mmd_indices=None):    # :189-257

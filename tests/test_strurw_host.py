@@ -155,3 +155,38 @@ def test_reweight_schedule():
             est._epoch = epoch
             est._maybe_reweight(None, None, None, epoch)
         assert fired == expect
+
+
+def test_structure_difference_diagnostics_equal_the_reference_formulas():
+    """cal_str_dif_rel / cal_str_diff_ratio (strurw.py:550-614) restated here op by op, incl. zeros in the tables."""
+    from pygda_b200.models import StruRW
+    est = StruRW(in_dim=5, hid_dim=4, num_classes=3, device="cpu")
+    torch.manual_seed(3)
+    pred, true = torch.rand(4, 4, dtype=torch.float64), torch.rand(4, 4, dtype=torch.float64)
+    pred[0, 1] = 0.0
+    true[2, 3] = 0.0
+    true[1, 1] = 0.0
+    pred[3, 3] = 0.0
+    pred[1, 2] = true[1, 2] = 0.0
+
+    cls1, cls0 = (pred - true).abs(), ((1 - pred) - (1 - true)).abs()
+    abs_diff = 0.5 * cls0 + 0.5 * cls1
+    r1, r2 = abs_diff / true, abs_diff / pred
+    rel = 0.5 * r1 + 0.5 * r2
+    rel[torch.isinf(r1)] = r2[torch.isinf(r1)]
+    rel[torch.isinf(r2)] = r1[torch.isinf(r2)]
+    rel[torch.isnan(rel)] = 0
+    got = est.cal_str_dif_rel(pred, true)
+    assert torch.equal(got[0], abs_diff.sum() / 16) and torch.equal(got[1], rel.sum() / 16)
+
+    def intra(m):
+        d = torch.diagonal(m, 0).repeat_interleave(m.size(1)).view(-1, m.size(1))
+        r = torch.div(m, d)
+        r[torch.isnan(r)] = 1
+        r[torch.isinf(r)] = m[torch.isinf(r)]
+        return r
+    ratio = torch.div(intra(pred), intra(true))
+    ratio[torch.isnan(ratio)] = 1
+    ratio[torch.isinf(ratio)] = 1
+    want = (ratio.sum() - torch.diagonal(ratio).sum()) / (16 - 4)
+    assert torch.equal(est.cal_str_diff_ratio(pred, true), want)
