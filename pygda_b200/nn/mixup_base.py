@@ -1,8 +1,8 @@
 """MixupBase -- drop-in for pygda/nn/mixup_base.py:10-200 (StruRW's 'mixup' mode).
 
-The convolutions are ``MixUpGCNConv`` (libgda GEMM + aggregation).  The node permutation ``x[id_new_value_old]`` and the
-interpolations ``a * lam + b * (1 - lam)`` stay torch expressions: this mode is API surface only -- no benchmark
-script selects it (benchmark/node/strurw.py:39 defaults to 'erm')."""
+The convolutions are ``MixUpGCNConv`` (libgda GEMM + aggregation), the interpolations ``a * lam + b * (1 - lam)``
+``ops.lerp2`` (gda_scale_f32 + gda_axpy_f32); only the node permutation ``x[id_new_value_old]`` is a torch gather (data
+movement).  This mode is API surface -- no benchmark script selects it (benchmark/node/strurw.py:39 defaults to 'erm')."""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -51,19 +51,19 @@ class MixupBase(nn.Module):
         x1 = act_drop(conv(0, x, x, edge_index))                              # :130-132
         x2 = act_drop(conv(1, x1, x1, edge_index))                            # :134-136
         x0_b, x1_b = x[perm], x1[perm]                                        # :138-139
-        x_mix = x * lam + x0_b * (1 - lam)                                    # :141
+        x_mix = ops.lerp2(x, x0_b, lam)                                       # :141
         new_x1 = act(conv(0, x, x_mix, edge_index))                           # :143-146
         new_x1_b = act(conv(0, x0_b, x_mix, edge_index_b))
-        x1_mix = drop(new_x1 * lam + new_x1_b * (1 - lam))                    # :148-149
+        x1_mix = drop(ops.lerp2(new_x1, new_x1_b, lam))                       # :148-149
         new_x2 = act(conv(1, x1, x1_mix, edge_index))                         # :151-154
         new_x2_b = act(conv(1, x1_b, x1_mix, edge_index_b))
-        x_mix = drop(new_x2 * lam + new_x2_b * (1 - lam))                     # :156-157
+        x_mix = drop(ops.lerp2(new_x2, new_x2_b, lam))                        # :156-157
         x = x2
         for i in range(2, len(self.convs)):                                   # :162-176
             x_t = act_drop(conv(i, x, x, edge_index))
             x_b = x[perm]
             new_x = act(conv(i, x, x_mix, edge_index))
             new_x_b = act(conv(i, x_b, x_mix, edge_index_b))
-            x_mix = drop(new_x * lam + new_x_b * (1 - lam))
+            x_mix = drop(ops.lerp2(new_x, new_x_b, lam))
             x = x_t
         return x_mix

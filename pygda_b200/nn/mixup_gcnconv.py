@@ -36,4 +36,4 @@ class MixUpGCNConv(nn.Module):
         if edge_weight is None:
             raise TypeError("MixUpGCNConv needs edge weights (the reference's message calls edge_rw.view, :243)")
         g = message_graph(edge_index, edge_weight, lmda, x.size(0), True, 'add', to_source=False)
-        return ops.graph_conv(x, self.lin.weight, None, g, 1) + ops.linear(x_cen, self.lin_cen.weight, self.bias)
+        return ops.add(ops.graph_conv(x, self.lin.weight, None, g, 1), ops.linear(x_cen, self.lin_cen.weight, self.bias))

@@ -111,8 +111,8 @@ class GS_reweight(nn.Module):
         # agg_lin(cat(aggr_out, x)) (:366-367) without materialising the [N, out + in] concatenation
         # (in = 6775 input features at the first layer): the weight is split instead
         w = self.agg_lin.weight
-        out = ops.linear(aggr_out, w[:, :self.out_channels], self.agg_lin.bias) + \
-            ops.linear(x, w[:, self.out_channels:], None)
+        out = ops.add(ops.linear(aggr_out, w[:, :self.out_channels], self.agg_lin.bias),
+                      ops.linear(x, w[:, self.out_channels:], None))
         out = ops.act_dropout(out, F.relu, 0.0, False)                        # :368
         if self.normalize_emb:                                                # :370-371 (never enabled by ReweightGNN)
             out = F.normalize(out, p=2, dim=-1)

@@ -253,6 +253,42 @@ def scale(x, alpha):
     return y
 
 
+class LinCombFn(torch.autograd.Function):
+    """y = wa * a + wb * b on libgda (gda_scale_f32 + gda_axpy_f32): the sum of two branch outputs
+    (pygda/nn/mixup_gcnconv.py:212) and mixup's interpolation ``a * lam + b * (1 - lam)``
+    (pygda/nn/mixup_base.py:141,148,156)."""
+
+    @staticmethod
+    def forward(ctx, a, b, wa, wb):
+        a, b = _f32c(a), _f32c(b)
+        if a.shape != b.shape:
+            raise ValueError(f"shapes differ: {tuple(a.shape)} vs {tuple(b.shape)}")
+        y = torch.empty_like(a)
+        gda.scale_f32(_p(y), _p(a), a.numel(), float(wa), _stream())
+        gda.axpy_f32(_p(y), _p(b), b.numel(), float(wb), _stream())
+        ctx.w = (float(wa), float(wb))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        wa, wb = ctx.w
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = g if wa == 1.0 else scale(g, wa)
+        if ctx.needs_input_grad[1]:
+            gb = g if wb == 1.0 else scale(g, wb)
+        return ga, gb, None, None
+
+
+def add(a, b):
+    return LinCombFn.apply(a, b, 1.0, 1.0)
+
+
+def lerp2(a, b, lam):
+    """a * lam + b * (1 - lam)."""
+    return LinCombFn.apply(a, b, float(lam), 1.0 - float(lam))
+
+
 class DropoutRng:
     """Seeds for the counter-based dropout masks.
 

@@ -207,3 +207,19 @@ def test_strurw_fit_predict(mode, gnn, capsys):
     assert out.count("Epoch") >= 5 or out.count("epoch") >= 5
     logits, labels = model.predict(tgt)
     assert logits.shape == (1200, 3) and labels.shape == (1200,) and torch.isfinite(logits).all()
+
+
+def test_lincomb_kernels():
+    """ops.add / ops.lerp2 (gda_scale_f32 + gda_axpy_f32) forward and backward against torch."""
+    from pygda_b200 import ops
+    torch.manual_seed(1)
+    a0, b0 = torch.randn(1000, 37), torch.randn(1000, 37)
+    for fn, ref, wa, wb in ((lambda a, b: ops.lerp2(a, b, 0.3), lambda a, b: a * 0.3 + b * (1 - 0.3), 0.3, 0.7),
+                            (ops.add, lambda a, b: a + b, 1.0, 1.0)):
+        a, b = a0.cuda().requires_grad_(True), b0.cuda().requires_grad_(True)
+        y = fn(a, b)
+        go = torch.randn_like(y)
+        y.backward(go)
+        assert_close(y, ref(a0, b0), 1e-6, "value")
+        assert_close(a.grad, wa * go, 1e-6, "grad a")
+        assert_close(b.grad, wb * go, 1e-6, "grad b")
