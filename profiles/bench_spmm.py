@@ -14,7 +14,7 @@ n = int(os.environ.get("N", 100_000)); e = int(os.environ.get("E", 1_000_000))
 cases = ((128, torch.float32), (5, torch.float32), (256, torch.bfloat16), (64, torch.float32))
 if os.environ.get("WIDE_ONLY"):                                # the one-16-byte-slice-per-lane widths only
     cases = ((128, torch.float32), (256, torch.bfloat16))
-print("GDA_SPMM_TASKS =", os.environ.get("GDA_SPMM_TASKS", "(default 4)"))
+print("GDA_SPMM_TASKS =", os.environ.get("GDA_SPMM_TASKS", "(default 4)"), " SAME_X =", os.environ.get("SAME_X", "(ping-pong)"))
 for h, dt in cases:
     ei = powerlaw_edge_index(n, e, seed=2, offset=48.0).cuda()
     g = Graph(ei, n)
@@ -31,9 +31,13 @@ for h, dt in cases:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 50
-    e0.record()
-    for i in range(reps):
-        ops.spmm(g, bufs[i & 1], out=bufs[(i + 1) & 1])
+    same_x = bool(os.environ.get("SAME_X"))                     # A/B for round 2: X read-only (never re-written) vs the
+    e0.record()                                                # ping-pong chain, whose input was just written by the
+    for i in range(reps):                                      # previous launch (home-L2 / cross-die fabric hypothesis)
+        if same_x:
+            ops.spmm(g, bufs[0], out=bufs[1])
+        else:
+            ops.spmm(g, bufs[i & 1], out=bufs[(i + 1) & 1])
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
