@@ -7,13 +7,26 @@ kept and back-propagated into the encoder although only the critic's optimiser s
 (:302) before anyone reads them.  Here the encoder forwards of the critic loop run without a
 tape (same values, same critic updates, 10 encoder backward passes less); the final encoder
 forward + backward is unchanged.  The critic (Linear-ReLU-Dropout-Linear-Sigmoid on [<=3B, hid]
-rows) and its WGAN-GP double backward stay in torch autograd: they need second derivatives and
-are negligible next to the encoder."""
+rows in graph mode) and its WGAN-GP double backward stay in torch autograd by default: they need
+second derivatives and are negligible next to the encoder there.
+
+``analytic_critic = True`` (opt-in; node mode, where the critic sees all [3N, hid] rows ten times per
+step): the only [rows, hid]-sized product -- the critic's first Linear -- runs on libgda
+(``ops.linear``), and the gradient penalty is evaluated in CLOSED FORM instead of by double backward.
+For D(x) = sigmoid(w2 . (relu(W1 x + b1) * m) + b2) with dropout mask m,
+
+    dD/dx = D (1 - D) * (u W1),   u = w2 * 1[W1 x + b1 > 0] * m          (a [rows, adv_dim] matrix)
+    |dD/dx|^2 = (D (1 - D))^2 * rowsum((u W1 W1^T) * u)
+
+so no [rows, hid] gradient tensor is ever formed and first-order autograd over [rows, adv_dim]
+arrays yields the same parameter gradients (relu' and the mask are piecewise constant, exactly as in
+torch's double backward).  Checked against the double-backward form (tests/test_zz_gpu_critic.py)."""
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 from . import BaseGDA
+from .. import ops
 from ..nn.adagcn_base import AdaGCNBase
 from ..optim import Adam
 from ._common import TwoDomainLoop
@@ -31,6 +44,7 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         self.gp_weight = gp_weight
         self.domain_weight = domain_weight
         self.mode = mode
+        self.analytic_critic = False      # opt-in, see the module docstring
 
     def init_model(self, **kwargs):
         return AdaGCNBase(in_dim=self.in_dim, hid_dim=self.hid_dim, num_classes=self.num_classes,
@@ -44,14 +58,44 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         self.c_optimizer = torch.optim.Adam(self.discriminator.parameters(), lr=self.lr,
                                             weight_decay=self.weight_decay)
 
+    # ---- critic evaluation -------------------------------------------------------------------------------
+    def _critic_hidden(self, x):
+        """(z1, u-mask, h) of the critic's first block: z1 = W1 x + b1 on libgda; m = dropout keep mask / (1 - p)
+        in train mode; h = relu(z1) * m."""
+        lin1, drop = self.discriminator[0], self.discriminator[2]
+        z1 = ops.linear(x, lin1.weight, lin1.bias)
+        pos = (z1 > 0).to(z1.dtype)
+        if self.discriminator.training and drop.p > 0:
+            pos = pos * ((torch.rand_like(z1) >= drop.p).to(z1.dtype) / (1.0 - drop.p))
+        return z1, pos, z1 * pos
+
+    def _critic(self, x):
+        """``self.discriminator(x)`` -- through libgda for the [rows, hid] product when ``analytic_critic``."""
+        if not self.analytic_critic:
+            return self.discriminator(x)
+        _, _, h = self._critic_hidden(x)
+        return torch.sigmoid(self.discriminator[3](h))
+
+    def _gradient_penalty_closed_form(self, inputs):
+        lin1, lin2 = self.discriminator[0], self.discriminator[3]
+        _, pos, h = self._critic_hidden(inputs.detach())
+        score = torch.sigmoid(lin2(h)).reshape(-1)                       # D(x)                      [rows]
+        u = pos * lin2.weight.reshape(1, -1)                               # w2 * relu' * dropout      [rows, adv]
+        gram = lin1.weight @ lin1.weight.t()                               # W1 W1^T                   [adv, adv]
+        q = ((u @ gram) * u).sum(dim=1)                                    # |u W1|^2                  [rows]
+        live = q > 0                                                       # norm(0) has gradient 0 in torch
+        root = torch.where(live, q, torch.ones_like(q)).sqrt() * live.to(q.dtype)
+        gradient_norm = (score * (1 - score)).abs() * root
+        return torch.mean((gradient_norm - 1) ** 2)
+
     def forward_model(self, source_data, target_data):
         for _ in range(10):                                                               # :169-183
             with torch.no_grad():                       # see the module docstring
                 encoded_source = self.adagcn(source_data)
                 encoded_target = self.adagcn(target_data)
             gp_loss = self.gradient_penalty(encoded_source, encoded_target)
-            dis_s = torch.mean(self.discriminator(encoded_source).reshape(-1))
-            dis_t = torch.mean(self.discriminator(encoded_target).reshape(-1))
+            dis_s = torch.mean(self._critic(encoded_source).reshape(-1))
+            dis_t = torch.mean(self._critic(encoded_target).reshape(-1))
             dis_loss = - torch.abs(dis_s - dis_t)
             loss = dis_loss + self.gp_weight * gp_loss
             self.c_optimizer.zero_grad()
@@ -61,8 +105,8 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         encoded_target = self.adagcn(target_data)
         source_logits = self.adagcn.cls_model(encoded_source)
         cls_loss = self.adagcn.loss_func(source_logits, source_data.y)
-        dis_s = torch.mean(self.discriminator(encoded_source).reshape(-1))
-        dis_t = torch.mean(self.discriminator(encoded_target).reshape(-1))
+        dis_s = torch.mean(self._critic(encoded_source).reshape(-1))
+        dis_t = torch.mean(self._critic(encoded_target).reshape(-1))
         dis_loss = torch.abs(dis_s - dis_t)
         target_logits = self.adagcn.cls_model(encoded_target)
         loss = cls_loss + dis_loss * self.domain_weight                                   # :196
@@ -89,6 +133,8 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
             alpha = self._rand(num_t)
             interpolates = encoded_target + (alpha * (encoded_source - encoded_target))
         inputs = torch.cat((encoded_source, encoded_target, interpolates), dim=0)
+        if self.analytic_critic:
+            return self._gradient_penalty_closed_form(inputs)
         if not inputs.requires_grad:                    # tape-free encoder outputs: differentiate w.r.t. a leaf
             inputs = inputs.detach().requires_grad_(True)
         scores = self.discriminator(inputs)
