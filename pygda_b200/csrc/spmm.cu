@@ -59,10 +59,30 @@ struct Epilogue {
 
 template <typename T, int VEC> struct VecIO;
 
+// 16-byte gather of a neighbour-row slice.  GDA_GATHER_LOAD selects the cache policy at COMPILE time for A/B builds
+// (`make VARIANT=ldcg|noalloc`, profiles/bench_spmm.py with GDA_LIB_PATH): 0 = ld.global.nc through L1 (the shipped
+// default), 1 = ld.global.cg (L2 only), 2 = ld.global.nc.L1::no_allocate.  L1 hits on the gathers are 2 % at config 2
+// while l1tex is the busiest unit of the kernel (profiles/r1_j_final), so not allocating may be the cheaper path.
+#ifndef GDA_GATHER_LOAD
+#define GDA_GATHER_LOAD 0
+#endif
+static __device__ __forceinline__ uint4 gather16(const void* p) {
+#if GDA_GATHER_LOAD == 1
+  return __ldcg(reinterpret_cast<const uint4*>(p));
+#elif GDA_GATHER_LOAD == 2
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const uint4*>(p));
+#endif
+}
+
 template <> struct VecIO<float, 4> {
   static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    const uint4 v = gather16(p);
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
   }
   static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
@@ -74,7 +94,7 @@ template <> struct VecIO<float, 1> {
 };
 template <> struct VecIO<__nv_bfloat16, 8> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 v = gather16(p);
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
