@@ -1,0 +1,117 @@
+"""DEVELOPER TOOL, not a test and not a product path.
+
+When no GPU is at hand (the build container has none, and GPU minutes are rationed), this module lets the PYTHON GLUE
+of new estimators / layers be exercised on the CPU: importing it monkeypatches the libgda-backed entry points of
+``pygda_b200.ops`` and ``pygda_b200.graph.Graph`` with plain torch expressions inside THIS process only.  It catches
+shape / attribute / autograd-wiring mistakes before a GPU call is spent; it proves nothing about the kernels, is never
+imported by ``pygda_b200`` or by the pytest suites (``tests/devtools`` holds no ``test_*.py``), and no parity claim
+rests on it -- parity is what ``pytest -m gpu`` measures on the B200 against the oracle and the golden vectors.
+Usage: ``bash tests/devtools/desk_check.sh tests/test_zz_gpu_strurw.py``."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.nn.functional as F
+from oracle import pyg_ops as P
+from oracle import mmd as OM
+import pygda_b200
+from pygda_b200 import ops, graph as G
+
+SELF_LOOPS, IMPROVED, NORM_SYM_COL, NORM_SYM_ROW = 1, 2, 4, 8
+
+class FakeGraph:
+    def __init__(self, edge_index, num_nodes, edge_weight=None, flags=SELF_LOOPS | NORM_SYM_COL):
+        self.num_nodes = int(num_nodes)
+        ei, w = edge_index, edge_weight
+        if flags & NORM_SYM_COL:
+            ei, w = P.gcn_norm_by_col(ei, w, num_nodes, bool(flags & IMPROVED), bool(flags & SELF_LOOPS))
+        elif flags & NORM_SYM_ROW:
+            assert not (flags & SELF_LOOPS) and w is None
+            w = torch.ones(ei.size(1))
+            deg = P.scatter_add(w, ei[0], 0, num_nodes)
+            dinv = deg.pow(-0.5); dinv[dinv == float("inf")] = 0
+            w = dinv[ei[0]] * w * dinv[ei[1]]
+        elif flags & SELF_LOOPS:
+            ei, w = P.add_remaining_self_loops(ei, w if w is not None else torch.ones(ei.size(1)), 1.0, num_nodes)
+        elif w is None:
+            w = torch.ones(ei.size(1))
+        self.ei, self.w = ei, w.float()
+        self.nnz = ei.size(1)
+    def coo(self):
+        return self.ei, self.w
+    def csr(self, transpose=False):
+        order = torch.argsort(self.ei[1], stable=True)
+        return None, self.ei[0][order], self.w[order]
+
+G.Graph = FakeGraph
+import pygda_b200.nn.reweight_gnn as RW
+RW.Graph = FakeGraph
+
+def spmm(graph, x, transpose=False, bias=None, relu=False, dropout_p=0.0, **kw):
+    ei = graph.ei.flip(0) if transpose else graph.ei
+    y = P.propagate(ei, x, graph.w, graph.num_nodes)
+    if bias is not None: y = y + bias
+    if relu: y = torch.relu(y)
+    assert dropout_p == 0
+    return y
+def spmm_k(graph, x, k, transpose=False, bias=None, **kw):
+    for i in range(k):
+        x = spmm(graph, x, transpose, bias if i == k - 1 else None)
+    return x
+ops.spmm, ops.spmm_k = spmm, spmm_k
+
+class PropagateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph, k):
+        ctx.graph, ctx.k = graph, k
+        return spmm_k(graph, x, k)
+    @staticmethod
+    def backward(ctx, g):
+        return spmm_k(ctx.graph, g.contiguous(), ctx.k, transpose=True), None, None
+ops.PropagateFn = PropagateFn
+RW.ops = ops
+def graph_conv(x, weight, bias, graph, k, w_in_out=False):
+    h = x @ (weight if w_in_out else weight.t())
+    if k > 0:
+        h = PropagateFn.apply(h, graph, k)
+    return h if bias is None else h + bias
+ops.graph_conv = graph_conv
+ops.linear = lambda x, w, b=None: F.linear(x, w, b)
+def act_dropout(x, act, p, training):
+    if act is not None: x = act(x)
+    return F.dropout(x, p, training) if (training and p > 0) else x
+ops.act_dropout = act_dropout
+ops.softmax_cross_entropy = lambda z, y: F.cross_entropy(z, y)
+def domain_ce(z, split):
+    lab = torch.cat([torch.zeros(split, dtype=torch.long), torch.ones(z.size(0) - split, dtype=torch.long)])
+    return F.cross_entropy(z, lab)
+ops.domain_cross_entropy = domain_ce
+ops.combine = lambda pairs: sum(t * w for t, w in pairs)
+ops.scale = lambda x, a: x * a
+ops.global_mean_pool = lambda x, batch, size=None: P.global_mean_pool(x, batch, size)
+import pygda_b200.utils as U
+import pygda_b200.models.strurw as S
+import pygda_b200.models.adagcn as _A
+_A.ops = ops
+_A.Adam = torch.optim.Adam
+S.MMD = lambda a, b, indices=None: OM.MMD(a, b, indices=indices)
+S.Adam = torch.optim.Adam
+from pygda_b200.metrics import eval_micro_f1
+S.micro_f1_from_logits = lambda y, z: eval_micro_f1(y, z.argmax(1))
+
+# LinCombFn: run its real Python (forward/backward) with the two ABI calls emulated on tensors
+class _FakeGda:
+    @staticmethod
+    def scale_f32(y, x, n, a, st):
+        y.view(-1)[:n].copy_(a * x.reshape(-1)[:n])
+    @staticmethod
+    def axpy_f32(y, x, n, a, st):
+        y.view(-1)[:n].add_(a * x.reshape(-1)[:n])
+ops.gda = _FakeGda
+ops._p = lambda t: t
+ops._f32c = lambda t: t.contiguous()
+ops._stream = lambda: None
+ops.scale = lambda x, a: x * a
+import pygda_b200.nn.mixup_gcnconv as MG, pygda_b200.nn.mixup_base as MB
+MG.ops = ops; MB.ops = ops

@@ -216,7 +216,7 @@ def test_lincomb_kernels():
     a0, b0 = torch.randn(1000, 37), torch.randn(1000, 37)
     for fn, ref, wa, wb in ((lambda a, b: ops.lerp2(a, b, 0.3), lambda a, b: a * 0.3 + b * (1 - 0.3), 0.3, 0.7),
                             (ops.add, lambda a, b: a + b, 1.0, 1.0)):
-        a, b = a0.cuda().requires_grad_(True), b0.cuda().requires_grad_(True)
+        a, b = a0.clone().cuda().requires_grad_(True), b0.clone().cuda().requires_grad_(True)
         y = fn(a, b)
         go = torch.randn_like(y)
         y.backward(go)
