@@ -22,6 +22,7 @@ tail -c 5000 gpurun_out/r2a_bench.json
     fi
   done
 } 2>&1 | tee gpurun_out/r2a_spmm_ab.log
+timeout 600 python profiles/bench_strurw.py 2>&1 | tee gpurun_out/r2a_strurw.jsonl
 if [ -x profiles/probes/gather_probe6 ]; then
   timeout 300 profiles/probes/gather_probe6 2>&1 | tee gpurun_out/r2a_probe6.log
 fi
