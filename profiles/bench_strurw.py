@@ -75,7 +75,7 @@ for gnn in ("GS", "GCN"):
     us = statistics.mean(tm) * 1e3 if tm else float("nan")
     print(json.dumps({"what": "StruRW training step (erm, mean pooling)", "backbone": gnn, "nodes": N, "edges": E,
                       "feat": F_, "hid": H, "ms_per_step": ms_plain, "epochs_per_s": 1e3 / ms_plain,
-                      "ms_per_step_with_reweighting": ms_rw, "ms_cal_reweight": ms_cal, "loss": float(loss),
+                      "ms_per_step_with_reweighting": ms_rw, "ms_cal_reweight": ms_cal, "loss": float(loss.detach()),
                       "aggregation": {"launches_per_step": len(tm) / 3, "us_per_launch": us, "nnz": g.nnz,
                                       "alg_bytes_per_launch": b_alg, "achieved_GBps": b_alg / us / 1e3,
                                       "frac_of_hbm_peak": b_alg / us / 1e3 / peak,
