@@ -107,12 +107,21 @@ class GS_reweight(nn.Module):
 
     def forward(self, x, edge_index, edge_weight, lmda):                      # :281-372
         g = message_graph(edge_index, edge_weight, lmda, x.size(0), False, self.aggr)
-        aggr_out = ops.PropagateFn.apply(self.lin(x), g, 1)
         # agg_lin(cat(aggr_out, x)) (:366-367) without materialising the [N, out + in] concatenation
-        # (in = 6775 input features at the first layer): the weight is split instead
-        w = self.agg_lin.weight
-        out = ops.add(ops.linear(aggr_out, w[:, :self.out_channels], self.agg_lin.bias),
-                      ops.linear(x, w[:, self.out_channels:], None))
+        # (in = 6775 input features at the first layer): the weight is split instead,
+        #     agg_lin(cat(a, x)) = a Wa^T + x Wx^T + b,   Wa = W[:, :out], Wx = W[:, out:]
+        w, o = self.agg_lin.weight, self.out_channels
+        if self.in_channels > o:
+            # wide input: lin(x) and x Wx^T read the same rows of x -- one GEMM on the stacked weight [2 out, in]
+            # streams x ONCE instead of twice (forward, and again for the weight gradients); same dot products
+            fused_w = torch.cat([self.lin.weight, w[:, o:]], dim=0)
+            fused_b = None if self.lin.bias is None else torch.cat([self.lin.bias, torch.zeros_like(self.lin.bias)])
+            z = ops.linear(x, fused_w, fused_b)
+            h, x_part = z[:, :o], z[:, o:]
+        else:
+            h, x_part = self.lin(x), ops.linear(x, w[:, o:], None)
+        aggr_out = ops.PropagateFn.apply(h, g, 1)
+        out = ops.add(ops.linear(aggr_out, w[:, :o], self.agg_lin.bias), x_part)
         out = ops.act_dropout(out, F.relu, 0.0, False)                        # :368
         if self.normalize_emb:                                                # :370-371 (never enabled by ReweightGNN)
             out = F.normalize(out, p=2, dim=-1)
