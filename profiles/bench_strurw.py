@@ -9,7 +9,6 @@ import json
 import os
 import statistics
 import sys
-import time
 
 import torch
 
