@@ -40,12 +40,23 @@ class CachedGCNConv(nn.Module):
         flags = SELF_LOOPS | NORM_SYM_ROW | (IMPROVED if improved else 0)
         return Graph(edge_index, num_nodes, edge_weight, flags).coo()
 
-    def forward(self, x, edge_index, cache_name="default_cache", edge_weight=None):
+    def _graph(self, edge_index, num_nodes, cache_name, edge_weight=None):
         if cache_name not in self.cache_dict:
             flags = SELF_LOOPS | NORM_SYM_ROW | (IMPROVED if self.improved else 0)
-            self.cache_dict[cache_name] = Graph(edge_index, x.size(0), edge_weight, flags)
-        graph = self.cache_dict[cache_name]
+            self.cache_dict[cache_name] = Graph(edge_index, num_nodes, edge_weight, flags)
+        return self.cache_dict[cache_name]
+
+    def forward(self, x, edge_index, cache_name="default_cache", edge_weight=None):
+        graph = self._graph(edge_index, x.size(0), cache_name, edge_weight)
         return ops.graph_conv(x, self.weight, self.bias, graph, 1, w_in_out=True)
+
+    def propagate_product(self, xw, edge_index, cache_name="default_cache", edge_weight=None):
+        """``forward`` given ``xw = x @ self.weight`` computed by the caller: aggregation + bias only.  Lets two
+        layers that share ``weight`` AND input (UDAGCN's adjacency and PPMI views, udagcn_base.py:168-169) share
+        the product -- same values as two ``forward`` calls."""
+        graph = self._graph(edge_index, xw.size(0), cache_name, edge_weight)
+        out = ops.PropagateFn.apply(xw, graph, 1)
+        return out if self.bias is None else ops.BiasAddFn.apply(out, self.bias)
 
     def __repr__(self):
         return '{}({}, {})'.format(self.__class__.__name__, self.in_channels, self.out_channels)

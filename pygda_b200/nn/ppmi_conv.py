@@ -6,7 +6,6 @@ minutes to hours at benchmark scale, once per (layer, cache_name)); here it is b
 (pygda_b200/ppmi.py, csrc/ppmi.cu) in milliseconds.  NumPy's unseeded random stream cannot be reproduced,
 so -- exactly like two runs of the reference -- two builds differ in their walks; everything downstream of
 the visit counts is the reference's arithmetic (tests/test_gpu_ppmi.py)."""
-from .. import ops
 from ..graph import IMPROVED, NORM_SYM_ROW, SELF_LOOPS, Graph
 from ..ppmi import ppmi_edges
 from .cached_gcn_conv import CachedGCNConv
@@ -28,7 +27,7 @@ class PPMIConv(CachedGCNConv):
         ignored there too (it is overwritten at :171)."""
         return self._ppmi_graph(edge_index, num_nodes, improved).coo()
 
-    def forward(self, x, edge_index, cache_name="default_cache", edge_weight=None):
+    def _graph(self, edge_index, num_nodes, cache_name, edge_weight=None):
         if cache_name not in self.cache_dict:                                             # cached_gcn_conv.py:132-136
-            self.cache_dict[cache_name] = self._ppmi_graph(edge_index, x.size(0), self.improved)
-        return ops.graph_conv(x, self.weight, self.bias, self.cache_dict[cache_name], 1, w_in_out=True)
+            self.cache_dict[cache_name] = self._ppmi_graph(edge_index, num_nodes, self.improved)
+        return self.cache_dict[cache_name]

@@ -36,9 +36,13 @@ class GNN(nn.Module):
         for idx in range(1, num_layers):
             self.conv_layers.append(model_cls(hid_dim, hid_dim, weight=weights[idx], bias=biases[idx], **kwargs))
 
-    def forward(self, x, edge_index, cache_name):
+    def forward(self, x, edge_index, cache_name, first_product=None):
+        """``first_product``: ``x @ conv_layers[0].weight`` when the caller already has it (UDAGCNBase.encode)."""
         for i, conv_layer in enumerate(self.conv_layers):
-            x = conv_layer(x, edge_index, cache_name)
+            if i == 0 and first_product is not None:
+                x = conv_layer.propagate_product(first_product, edge_index, cache_name)
+            else:
+                x = conv_layer(x, edge_index, cache_name)
             if i < len(self.conv_layers) - 1:
                 x = ops.act_dropout(x, self.act, self.dropout_p[i], True)   # always "training"
         return x
@@ -52,6 +56,7 @@ class UDAGCNBase(nn.Module):
             raise ValueError("feature_dtype must be torch.float32 or torch.bfloat16")
         self.bf16 = feature_dtype == torch.bfloat16        # bf16 rows through the encoders (BASELINE config 3)
         self.ppmi = ppmi
+        self.share_first_product = False                   # opt-in (unmeasured in round 1), see encode()
         self.encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, gnn_type='gcn', act=act, num_layers=num_layers)
         if self.ppmi:
             self.ppmi_encoder = GNN(in_dim=in_dim, hid_dim=hid_dim, base_model=self.encoder,
@@ -84,6 +89,18 @@ class UDAGCNBase(nn.Module):
         return encoded_output if mask is None else encoded_output[mask]
 
     def encode(self, data, cache_name, mask=None):
+        if self.ppmi and self.share_first_product and not self.bf16:
+            # The two views apply the SAME first-layer weight to the SAME features (the PPMI encoder is built on the
+            # adjacency encoder's parameters, :168-169): x @ W0 -- the product that streams the [N, F] features --
+            # is evaluated once, and so is its weight gradient (autograd sums the two views' gradients first).
+            c0, p0 = self.encoder.conv_layers[0], self.ppmi_encoder.conv_layers[0]
+            if c0.weight is p0.weight:
+                xw = ops.graph_conv(data.x, c0.weight, None, None, 0, w_in_out=True)
+                outs = [self._out(enc(data.x, data.edge_index, cache_name, first_product=xw))
+                        for enc in (self.encoder, self.ppmi_encoder)]
+                if mask is not None:
+                    outs = [o[mask] for o in outs]
+                return self.att_model(outs)
         gcn_output = self.gcn_encode(data, cache_name, mask)
         if self.ppmi:
             return self.att_model([gcn_output, self.ppmi_encode(data, cache_name, mask)])
