@@ -124,3 +124,16 @@ ops._stream = lambda: None
 ops.scale = lambda x, a: x * a
 import pygda_b200.nn.mixup_gcnconv as MG, pygda_b200.nn.mixup_base as MB
 MG.ops = ops; MB.ops = ops
+
+
+def _softmax_entropy(z):
+    p = torch.clamp(F.softmax(z, dim=-1), min=1e-9, max=1.0)          # pygda/models/udagcn.py:193-199
+    return torch.mean(torch.sum(-p * torch.log(p), dim=-1))
+ops.softmax_entropy = _softmax_entropy
+import importlib
+for _name in ("udagcn", "grade", "a2gnn", "gnn", "dgsda", "tdss"):
+    _m = importlib.import_module("pygda_b200.models." + _name)
+    if hasattr(_m, "MMD"):
+        _m.MMD = lambda a, b, indices=None, **kw: OM.MMD(a, b, indices=indices)
+    if hasattr(_m, "Adam"):
+        _m.Adam = torch.optim.Adam
