@@ -44,4 +44,4 @@ def test_fit_with_prefetch_matches_fit_without():
         model.fit(src, tgt)
         logits, _ = model.predict(tgt)
         out.append(logits)
-    assert_close(out[1], out[0], 1e-5, "logits after 4 epochs, prefetch vs plain")
+    assert_close(out[1], out[0], 1e-4, "logits after 4 epochs, prefetch vs plain")
