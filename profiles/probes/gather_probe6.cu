@@ -23,7 +23,21 @@
 
 constexpr int U = 4;
 
-template <bool PAIR, bool WGT, bool TAIL>
+// LD: cache policy of the 16-byte row gathers -- 0 = ld.global.nc (__ldg, what the library ships), 1 = ld.global.cg
+// (L2 only), 2 = ld.global.nc.L1::no_allocate (the `make VARIANT=ldcg|noalloc` builds of libgda)
+template <int LD>
+__device__ __forceinline__ float4 gather16(const float4* p) {
+  if (LD == 1) return __ldcg(p);
+  if (LD == 2) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  }
+  return __ldg(p);
+}
+
+template <bool PAIR, bool WGT, bool TAIL, int LD = 0>
 __global__ void k_probe(const float4* __restrict__ X, const int* __restrict__ rowptr, const int* __restrict__ col,
                         const float* __restrict__ val, const int* __restrict__ order, int n_rows, float4* __restrict__ Y) {
   const int lane = threadIdx.x & 31;
@@ -47,7 +61,7 @@ __global__ void k_probe(const float4* __restrict__ X, const int* __restrict__ ro
           if (u < k) {
             const int c = PAIR ? __shfl_sync(0xffffffffu, myc, j + u) : __ldg(col + base + j + u);
             w[u] = PAIR ? __shfl_sync(0xffffffffu, myv, j + u) : (WGT ? __ldg(val + base + j + u) : 1.f);
-            v[u] = __ldg(X + (long)c * 32 + lane);
+            v[u] = gather16<LD>(X + (long)c * 32 + lane);
           }
         }
 #pragma unroll
@@ -95,14 +109,14 @@ static Graph make_graph(int N, bool real_len, bool plaw, bool sorted, bool pad4)
   return g;
 }
 
-template <bool PAIR, bool WGT, bool TAIL>
+template <bool PAIR, bool WGT, bool TAIL, int LD = 0>
 static float run(const Graph& g, int N, float4* X, float4* Y, int* d_rp, int* d_col, float* d_val, int* d_ord, int ctas) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float4 *a = X, *b = Y;
-  for (int r = 0; r < 4; ++r) { k_probe<PAIR, WGT, TAIL><<<148 * ctas, 128>>>(a, d_rp, d_col, d_val, d_ord, N, b); std::swap(a, b); }
+  for (int r = 0; r < 4; ++r) { k_probe<PAIR, WGT, TAIL, LD><<<148 * ctas, 128>>>(a, d_rp, d_col, d_val, d_ord, N, b); std::swap(a, b); }
   cudaEventRecord(e0);
-  for (int r = 0; r < 20; ++r) { k_probe<PAIR, WGT, TAIL><<<148 * ctas, 128>>>(a, d_rp, d_col, d_val, d_ord, N, b); std::swap(a, b); }
+  for (int r = 0; r < 20; ++r) { k_probe<PAIR, WGT, TAIL, LD><<<148 * ctas, 128>>>(a, d_rp, d_col, d_val, d_ord, N, b); std::swap(a, b); }
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms;
@@ -137,6 +151,19 @@ int main() {
       printf("mask %2d [%s%s%s%s%s%s] nnz=%ld  %d warps/SM: %7.1f us/launch  %6.2f TB/s gathered\n", mask, LEN ? "LEN " : "",
              PAIR ? "PAIR " : "", WGT ? "WGT " : "", SORT ? "SORT " : "", TAIL ? "TAIL " : "", PLAW ? "PLAW" : "", g.nnz,
              ctas * 4, ms * 1e3, (double)g.nnz * 512 / ms / 1e9);
+    }
+    if (mask == 63 || mask == 0) {                       // gather cache policy on the two end points
+      for (int ctas : {10, 16}) {
+        float t[3];
+        if (mask == 63) { t[0] = run<true, true, true, 0>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas);
+                          t[1] = run<true, true, true, 1>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas);
+                          t[2] = run<true, true, true, 2>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas); }
+        else { t[0] = run<false, false, false, 0>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas);
+               t[1] = run<false, false, false, 1>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas);
+               t[2] = run<false, false, false, 2>(g, N, X, Y, d_rp, d_col, d_val, d_ord, ctas); }
+        printf("mask %2d  %d warps/SM  gather policy  nc: %6.1f us  cg: %6.1f us  nc.L1::no_allocate: %6.1f us\n", mask,
+               ctas * 4, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3);
+      }
     }
     cudaFree(d_rp); cudaFree(d_col); cudaFree(d_val); cudaFree(d_ord);
   }
