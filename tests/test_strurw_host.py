@@ -190,3 +190,42 @@ def test_structure_difference_diagnostics_equal_the_reference_formulas():
     ratio[torch.isinf(ratio)] = 1
     want = (ratio.sum() - torch.diagonal(ratio).sum()) / (16 - 4)
     assert torch.equal(est.cal_str_diff_ratio(pred, true), want)
+
+
+def test_reweighting_degenerate_inputs():
+    """No edges at all; a class that occurs in neither graph; a class the target never predicts."""
+    from pygda_b200.data import Data
+    from pygda_b200.models import StruRW
+    est = StruRW(in_dim=3, hid_dim=4, num_classes=4, device="cpu")
+    x = torch.zeros(6, 3)
+    empty = torch.zeros(2, 0, dtype=torch.long)
+    s = Data(x=x, edge_index=empty, y=torch.tensor([0, 0, 1, 1, 2, 2]))
+    t = Data(x=x, edge_index=empty, y=torch.tensor([0, 1, 2, 0, 1, 2]))
+    est.cal_reweight(s, t, torch.tensor([0, 0, 0, 1, 1, 1]))
+    assert s.edge_weight.shape == (0,) and s.edge_weight.dtype == torch.float32
+    ei = torch.tensor([[0, 2, 4, 1, 0], [2, 4, 0, 3, 1]])
+    s = Data(x=x, edge_index=ei, y=torch.tensor([0, 0, 1, 1, 2, 2]))
+    t = Data(x=x, edge_index=ei, y=torch.tensor([0, 1, 2, 0, 1, 2]))
+    src_p, tgt_p, true_p = est.cal_edge_prob_sep(s, t, torch.tensor([0, 0, 1, 1, 1, 1]))
+    assert torch.isnan(src_p[3]).all() and torch.isnan(src_p[:, 3]).all()       # class 3 absent: 0 / 0
+    assert (tgt_p[2] == 0).all() and (tgt_p[3] == 0).all()                       # never predicted: 0 / 1e-12
+    est.cal_reweight(s, t, torch.tensor([0, 0, 1, 1, 1, 1]))
+    assert torch.isfinite(s.edge_weight).all() and s.edge_weight.shape == (5,)
+    # every edge weight is the table entry of its (class of edge_index[1], class of edge_index[0]) pair
+    R = tgt_p / src_p
+    R[torch.isinf(R)] = 1
+    R[torch.isnan(R)] = 1
+    assert torch.equal(s.edge_weight, R[s.y[ei[1]], s.y[ei[0]]].float())
+
+
+def test_message_values_degenerate_inputs():
+    from pygda_b200.nn.reweight_gnn import message_values
+    empty = torch.zeros(2, 0, dtype=torch.long)
+    assert message_values(empty, None, torch.zeros(0), 0.5, 4, "mean").shape == (0,)
+    ei = torch.tensor([[0, 0, 0, 2], [1, 1, 3, 2]])                               # duplicate edge, self loop, isolated node 1/3 rows
+    v = message_values(ei, None, torch.tensor([1., 3., 1., 2.]), 0.5, 4, "mean")
+    assert torch.allclose(v, torch.tensor([1 / 3, 2 / 3, 1 / 3, 1.5]))
+    v = message_values(ei, None, None, 0.5, 4, "add")
+    assert torch.equal(v, torch.ones(4))
+    with pytest.raises(ValueError, match="unsupported aggregation"):
+        message_values(ei, None, None, 0.5, 4, "max")
