@@ -137,3 +137,38 @@ for _name in ("udagcn", "grade", "a2gnn", "gnn", "dgsda", "tdss"):
         _m.MMD = lambda a, b, indices=None, **kw: OM.MMD(a, b, indices=indices)
     if hasattr(_m, "Adam"):
         _m.Adam = torch.optim.Adam
+
+
+# ---- A2GNN family: paired bottleneck evaluations and the two-stream overlap, as plain sequential torch ----
+def _act_dropout_pair(x, p):
+    r = torch.relu(x)
+    return F.dropout(r, p, True), F.dropout(r, p, True)
+
+
+def _graph_conv_act_pair(xa, xb, weight, bias, graph, k, p, relu=True, w_in_out=False):
+    def one(x):
+        y = graph_conv(x, weight, bias, graph, int(k), w_in_out)
+        y = torch.relu(y) if relu else y
+        return F.dropout(y, p, True) if p > 0 else y
+    return one(xa), one(xb)
+
+
+ops.act_dropout_pair = _act_dropout_pair
+ops.graph_conv_act_pair = _graph_conv_act_pair
+import contextlib
+
+
+class _FakeStream:
+    cuda_stream = 0
+    def wait_stream(self, other): pass
+    def wait_event(self, ev): pass
+
+
+if not torch.cuda.is_available():
+    torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+    torch.cuda.Stream = lambda *a, **k: _FakeStream()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.Tensor.record_stream = lambda self, s: None
+import pygda_b200.optim as _O
+_O.Adam = torch.optim.Adam
