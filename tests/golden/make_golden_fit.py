@@ -1,0 +1,77 @@
+"""Training TRAJECTORIES made by running the reference's own ``fit`` / ``predict`` (pygda/models/a2gnn.py:215-411,
+pygda/models/strurw.py:325-444, 669-700) for a few epochs on small graphs -- loaders, alpha schedule, optimiser
+configuration and update rule, epoch loop and predict, end to end:
+
+    python tests/golden/make_golden_fit.py        # build container only (needs /root/reference)
+
+Writes tests/golden/fit.pt: per run the initial state_dict (captured from the ``init_model`` call inside ``fit``), the
+torch CPU RNG state right after it (the MMD indices of the following epochs are drawn from that stream), the final
+state_dict, and ``predict`` on the target (and source) graph.  dropout = 0: the dropout streams cannot be matched."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference, REPO  # noqa: E402
+
+sys.path.insert(0, REPO)
+from make_golden import small_graph  # noqa: E402
+from oracle.data import Data  # noqa: E402
+
+
+def capture_init(est, attr_box):
+    """Wrap est.init_model so that the state it creates inside fit() and the RNG state after it are recorded."""
+    real = est.init_model
+
+    def wrapped(**kw):
+        net = real(**kw)
+        attr_box["state"] = {k: v.clone() for k, v in net.state_dict().items()}
+        attr_box["rng_state"] = torch.get_rng_state().clone()
+        return net
+    est.init_model = wrapped
+
+
+def main():
+    ref = load_reference()
+    src, tgt = small_graph(60, 220, 20, 3, seed=21), small_graph(52, 180, 20, 3, seed=22, with_loops=False)
+    blob = {"source": {"x": src.x, "edge_index": src.edge_index, "y": src.y},
+            "target": {"x": tgt.x, "edge_index": tgt.edge_index, "y": tgt.y}, "runs": {}}
+
+    for name, kw in (("a2gnn_mmd", dict(adv=False, weight=3)), ("a2gnn_adv", dict(adv=True, weight=2))):
+        hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, dropout=0.0, s_pnums=0, t_pnums=4, lr=0.01,
+                  weight_decay=0.005, epoch=4, **kw)
+        torch.manual_seed(71)
+        est = ref.a2gnn.A2GNN(device="cpu", verbose=0, **hp)
+        box = {}
+        capture_init(est, box)
+        est.fit(Data(**blob["source"]), Data(**blob["target"]))
+        t_logits, t_labels = est.predict(Data(**blob["target"]))
+        s_logits, s_labels = est.predict(Data(**blob["source"]), source=True)
+        blob["runs"][name] = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+                              "final_state": {k: v.clone() for k, v in est.a2gnn.state_dict().items()},
+                              "target_logits": t_logits.clone(), "target_labels": t_labels.clone(),
+                              "source_logits": s_logits.clone(), "source_labels": s_labels.clone()}
+
+    # StruRW, GS backbone, 'erm' objective; the edge re-weighting fires in epochs 1 and 3 (and, PyG's loaders building a
+    # new batch object per epoch, lasts for that epoch's source pass only)
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, cls_dim=8, cls_layers=2, dropout=0.0, gnn="GS",
+              pooling="mean", ew_start=2, ew_freq=2, lamb=0.8, mode="erm", lr=0.01, weight_decay=0.001, epoch=4)
+    torch.manual_seed(73)
+    est = ref.strurw.StruRW(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    est.fit(Data(edge_weight=None, **blob["source"]), Data(edge_weight=None, **blob["target"]))   # PyG: missing -> None
+    t = Data(**blob["target"])
+    t.edge_weight = torch.ones(t.edge_index.size(1))
+    t_logits, t_labels = est.predict(t)
+    blob["runs"]["strurw_erm"] = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+                                  "final_state": {k: v.clone() for k, v in est.gnn.state_dict().items()},
+                                  "target_logits": t_logits.clone(), "target_labels": t_labels.clone()}
+    torch.save(blob, os.path.join(HERE, "fit.pt"))
+    print("wrote fit.pt", os.path.getsize(os.path.join(HERE, "fit.pt")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""``fit()`` / ``predict()`` of the estimators on the GPU against the trajectories of the reference's own ``fit``
+(tests/golden/fit.pt): same initial weights (injected into the ``init_model`` call inside ``fit``), same CPU RNG state
+(MMD indices), the reference's number of epochs -> same final weights and predictions.  Tolerance as in
+test_gpu_a2gnn.py::test_train_steps_track_the_oracle: Adam's m / (sqrt(v) + eps) amplifies fp32 noise on entries whose
+gradient is close to eps, so weights are compared at 1e-3 of their largest entry."""
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _inject(est, run):
+    real = est.init_model
+
+    def wrapped(**kw):
+        net = real(**kw)
+        net.load_state_dict(run["init_state"])
+        torch.set_rng_state(run["rng_state"])
+        return net
+    est.init_model = wrapped
+
+
+@pytest.mark.parametrize("name", ["a2gnn_mmd", "a2gnn_adv"])
+def test_a2gnn_fit_reproduces_the_reference_trajectory(name):
+    from pygda_b200.data import Data
+    from pygda_b200.models import A2GNN
+    G = load_golden("fit")
+    r = G["runs"][name]
+    est = A2GNN(device="cuda:0", verbose=0, **r["hparams"])
+    _inject(est, r)
+    src, tgt = Data(**G["source"]), Data(**G["target"])              # host-resident, as a user would pass them
+    est.fit(src, tgt)
+    for k, v in est.a2gnn.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
+    t_logits, t_labels = est.predict(tgt)
+    s_logits, s_labels = est.predict(src, source=True)
+    assert_close(t_logits, r["target_logits"], 1e-3, "predict(target)")
+    assert_close(s_logits, r["source_logits"], 1e-3, "predict(source)")
+    assert torch.equal(t_labels.cpu(), r["target_labels"]) and torch.equal(s_labels.cpu(), r["source_labels"])
+
+
+def test_strurw_fit_reproduces_the_reference_trajectory(capsys):
+    from pygda_b200.data import Data
+    from pygda_b200.models import StruRW
+    G = load_golden("fit")
+    r = G["runs"]["strurw_erm"]
+    est = StruRW(device="cuda:0", verbose=0, **r["hparams"])
+    _inject(est, r)
+    est.fit(Data(**G["source"]), Data(**G["target"]))
+    assert capsys.readouterr().out.count("edge reweight...") == 2
+    for k, v in est.gnn.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
+    logits, labels = est.predict(Data(**G["target"]))
+    assert_close(logits, r["target_logits"], 1e-3, "predict(target)")
+    assert torch.equal(labels.cpu(), r["target_labels"])
