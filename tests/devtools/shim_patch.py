@@ -172,3 +172,28 @@ if not torch.cuda.is_available():
     torch.Tensor.record_stream = lambda self, s: None
 import pygda_b200.optim as _O
 _O.Adam = torch.optim.Adam
+
+
+# ---- TDSS smoothing graph / Laplacian loss, DGSDA's Bernstein propagation: the oracle's forms ----
+import pygda_b200.smooth as _SM
+from oracle.models import TDSS as _OTDSS
+from oracle import nn as _ONN
+
+
+def _khop(edge_index, num_nodes, k):
+    t = _OTDSS(in_dim=1, hid_dim=1, num_classes=2, smooth_mode="K-hop", k=k)
+    return t.smoothness(edge_index, None, num_nodes)[0]
+
+
+_SM.khop_edge_index = _khop
+_SM.laplacian_loss = lambda feats, ei: _OTDSS.compute_laplacian_loss(feats, ei)
+import pygda_b200.nn.dgsda_base as _DB
+
+
+def _bern_forward(self, x, edge_index, edge_weight=None):
+    o = _ONN.BernProp(self.K)
+    o.temp = self.temp
+    return o(x, edge_index, edge_weight)
+
+
+_DB.BernProp.forward = _bern_forward

@@ -21,12 +21,14 @@ from make_golden import small_graph  # noqa: E402
 from oracle.data import Data  # noqa: E402
 
 
-def capture_init(est, attr_box):
+def capture_init(est, attr_box, post=None):
     """Wrap est.init_model so that the state it creates inside fit() and the RNG state after it are recorded."""
     real = est.init_model
 
     def wrapped(**kw):
         net = real(**kw)
+        if post is not None:
+            post(net)
         attr_box["state"] = {k: v.clone() for k, v in net.state_dict().items()}
         attr_box["rng_state"] = torch.get_rng_state().clone()
         return net
@@ -69,6 +71,80 @@ def main():
     blob["runs"]["strurw_erm"] = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
                                   "final_state": {k: v.clone() for k, v in est.gnn.state_dict().items()},
                                   "target_logits": t_logits.clone(), "target_labels": t_labels.clone()}
+    def finish(name, est, net_attr, hp, box, predict_kw=()):
+        net = getattr(est, net_attr)
+        run = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+               "final_state": {k: v.clone() for k, v in net.state_dict().items()}}
+        t_logits, t_labels = est.predict(Data(**blob["target"]))
+        run["target_logits"], run["target_labels"] = t_logits.clone(), t_labels.clone()
+        if "source" in predict_kw:
+            s_logits, s_labels = est.predict(Data(**blob["source"]), source=True)
+            run["source_logits"], run["source_labels"] = s_logits.clone(), s_labels.clone()
+        blob["runs"][name] = run
+
+    # UDAGCN (udagcn.py:203-308), adjacency view only; the encoder's never-registered dropout layers (udagcn_base.py:47)
+    # are switched off by hand, in the network fit() has just built
+    def no_encoder_dropout(net):
+        for d in net.encoder.dropout_layers:
+            d.p = 0.0
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, ppmi=False, adv_dim=8, lr=0.01, weight_decay=0.003,
+              epoch=4)
+    torch.manual_seed(75)
+    est = ref.udagcn.UDAGCN(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box, post=no_encoder_dropout)
+    # domain_model holds an nn.Dropout(0.1) that IS registered and active in train mode: its draws come from the CPU
+    # generator on the reference side and cannot be matched -> p = 0 as well
+    real = est.init_model
+
+    def with_plain_domain_model(**kw):
+        net = real(**kw)
+        for m in net.domain_model:
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        return net
+    est.init_model = with_plain_domain_model
+    est.fit(Data(**blob["source"]), Data(**blob["target"]))
+    finish("udagcn", est, "udagcn", hp, box, ("source",))
+
+    for disc in ("JS", "MMD"):
+        hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, dropout=0.0, disc=disc, weight=0.5, lr=0.01,
+                  weight_decay=0.01, epoch=4)
+        torch.manual_seed(77)
+        est = ref.grade.GRADE(device="cpu", verbose=0, **hp)
+        box = {}
+        capture_init(est, box)
+        est.fit(Data(**blob["source"]), Data(**blob["target"]))
+        finish("grade_" + disc.lower(), est, "grade", hp, box, ("source",))
+
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, dropout=0.0, gnn="gcn", lr=0.02, weight_decay=0.001,
+              epoch=4)
+    torch.manual_seed(79)
+    est = ref.gnn.GNN(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    est.fit(Data(**blob["source"]), Data(**blob["target"]))
+    finish("gnn_gcn", est, "gnn", hp, box)
+
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, mode="node", smooth_mode="K-hop", num_layers=2, dropout=0.0,
+              s_pnums=0, t_pnums=3, k=2, alpha=0.5, beta=0.05, lr=0.01, weight_decay=0.005, epoch=4)
+    torch.manual_seed(81)
+    est = ref.tdss.TDSS(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    tt = Data(edge_attr=None, **blob["target"])
+    est.fit(Data(**blob["source"]), tt)
+    finish("tdss", est, "a2gnn", hp, box, ("source",))
+
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, K=4, alpha=0.05, beta=0.5, gamma=0.05, dropout=0.0, lr=0.01,
+              weight_decay=0.0005, epoch=4)
+    torch.manual_seed(83)
+    est = ref.dgsda.DGSDA(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    est.fit(Data(**blob["source"]), Data(**blob["target"]))
+    finish("dgsda", est, "dgsda", hp, box, ("source",))
+
     torch.save(blob, os.path.join(HERE, "fit.pt"))
     print("wrote fit.pt", os.path.getsize(os.path.join(HERE, "fit.pt")), "bytes")
 

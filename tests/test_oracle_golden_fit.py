@@ -55,3 +55,93 @@ def test_strurw_fit_trajectory(capsys):
     logits, labels = est.predict(t)
     assert_close(logits, r["target_logits"], 1e-5, "predict(target)")
     assert torch.equal(labels, r["target_labels"])
+
+
+def _run_loop(est, net, G, r, step, prepare=None):
+    net.load_state_dict(r["init_state"])
+    torch.set_rng_state(r["rng_state"])
+    s0, t0 = Data(**G["source"]), Data(**G["target"])
+    if prepare is not None:
+        prepare(s0, t0)
+    src_loader, tgt_loader = FullBatchNeighborLoader(s0), FullBatchNeighborLoader(t0)
+    for epoch in range(r["hparams"]["epoch"]):
+        for s, t in zip(src_loader, tgt_loader):
+            step(s, t, epoch)
+    for k, v in net.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-5, "weights after fit: " + k)
+    return next(iter(src_loader)), next(iter(tgt_loader))
+
+
+def test_udagcn_fit_trajectory():
+    from oracle.models import UDAGCN
+    G = load_golden("fit")
+    r = G["runs"]["udagcn"]
+    est = UDAGCN(**r["hparams"])
+    est.udagcn.encoder.dropout_layers = [torch.nn.Identity() for _ in est.udagcn.encoder.dropout_layers]
+    for m in est.udagcn.domain_model:
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    s, t = _run_loop(est, est.udagcn, G, r, lambda a, b, e: est.train_step(a, b, e))
+    for m in est.udagcn.models:
+        m.eval()
+    with torch.no_grad():
+        assert_close(est.udagcn.cls_model(est.udagcn.encode(t, "target")), r["target_logits"], 1e-5, "predict(target)")
+        assert_close(est.udagcn.cls_model(est.udagcn.encode(s, "source")), r["source_logits"], 1e-5, "predict(source)")
+
+
+@pytest.mark.parametrize("disc", ["js", "mmd"])
+def test_grade_fit_trajectory(disc):
+    from oracle.models import GRADE
+    G = load_golden("fit")
+    r = G["runs"]["grade_" + disc]
+    est = GRADE(**r["hparams"])
+    s, t = _run_loop(est, est.grade, G, r, lambda a, b, e: est.train_step(a, b, e))
+    est.grade.eval()
+    with torch.no_grad():
+        assert_close(est.grade(t)[0], r["target_logits"], 1e-5, "predict(target)")
+        assert_close(est.grade(s)[0], r["source_logits"], 1e-5, "predict(source)")
+
+
+def test_gnn_fit_trajectory():
+    from oracle.models import GNN
+    G = load_golden("fit")
+    r = G["runs"]["gnn_gcn"]
+    hp = r["hparams"]
+    est = GNN(**hp)
+    opt = torch.optim.Adam(est.gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])   # gnn.py:195-199
+
+    def step(a, b, e):
+        est.gnn.train()
+        loss, _, _ = est.forward_model(a, b)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    s, t = _run_loop(est, est.gnn, G, r, step)
+    est.gnn.eval()
+    with torch.no_grad():
+        assert_close(est.gnn(t.x, t.edge_index), r["target_logits"], 1e-5, "predict(target)")
+
+
+def test_tdss_fit_trajectory():
+    from oracle.models import TDSS
+    G = load_golden("fit")
+    r = G["runs"]["tdss"]
+    est = TDSS(**r["hparams"])
+
+    def prepare(s0, t0):                                    # tdss.py:497-506: done by fit() before the loaders are built
+        t0.edge_index_smooth, t0.edge_attr_smooth = est.smoothness(t0.edge_index, None, t0.x.shape[0])
+    s, t = _run_loop(est, est.a2gnn, G, r, lambda a, b, e: est.train_step(a, b, e), prepare)
+    assert_close(est.predict(t)[0], r["target_logits"], 1e-5, "predict(target)")
+    assert_close(est.predict(s, source=True)[0], r["source_logits"], 1e-5, "predict(source)")
+
+
+def test_dgsda_fit_trajectory():
+    from oracle.models import DGSDA
+    G = load_golden("fit")
+    r = G["runs"]["dgsda"]
+    est = DGSDA(**r["hparams"])
+    s, t = _run_loop(est, est.dgsda, G, r, lambda a, b, e: est.train_step(a, b))
+    est.dgsda.eval()
+    with torch.no_grad():
+        assert_close(est.dgsda(t, False), r["target_logits"], 1e-5, "predict(target)")
+        assert_close(est.dgsda(s, True), r["source_logits"], 1e-5, "predict(source)")

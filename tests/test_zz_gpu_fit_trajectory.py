@@ -55,3 +55,68 @@ def test_strurw_fit_reproduces_the_reference_trajectory(capsys):
     logits, labels = est.predict(Data(**G["target"]))
     assert_close(logits, r["target_logits"], 1e-3, "predict(target)")
     assert torch.equal(labels.cpu(), r["target_labels"])
+
+
+def _fit_and_compare(est, net_attr, G, r, post=None, source=True, target_needs_edge_attr=False):
+    from pygda_b200.data import Data
+    real = est.init_model
+
+    def wrapped(**kw):
+        net = real(**kw)
+        net.load_state_dict(r["init_state"])
+        if post is not None:
+            post(net)
+        torch.set_rng_state(r["rng_state"])
+        return net
+    est.init_model = wrapped
+    src, tgt = Data(**G["source"]), Data(**G["target"])
+    est.fit(src, tgt)
+    for k, v in getattr(est, net_attr).state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
+    logits, labels = est.predict(tgt)
+    assert_close(logits, r["target_logits"], 1e-3, "predict(target)")
+    assert torch.equal(labels.cpu(), r["target_labels"])
+    if source:
+        logits, labels = est.predict(src, source=True)
+        assert_close(logits, r["source_logits"], 1e-3, "predict(source)")
+        assert torch.equal(labels.cpu(), r["source_labels"])
+
+
+def test_udagcn_fit_reproduces_the_reference_trajectory():
+    from pygda_b200.models import UDAGCN
+    G = load_golden("fit")
+    r = G["runs"]["udagcn"]
+
+    def no_dropout(net):                                    # as on the reference side (make_golden_fit.py)
+        net.encoder.dropout_p = [0.0 for _ in net.encoder.dropout_p]
+        net.domain_model[1].p = 0.0
+    _fit_and_compare(UDAGCN(device="cuda:0", verbose=0, **r["hparams"]), "udagcn", G, r, post=no_dropout)
+
+
+@pytest.mark.parametrize("disc", ["js", "mmd"])
+def test_grade_fit_reproduces_the_reference_trajectory(disc):
+    from pygda_b200.models import GRADE
+    G = load_golden("fit")
+    r = G["runs"]["grade_" + disc]
+    _fit_and_compare(GRADE(device="cuda:0", verbose=0, **r["hparams"]), "grade", G, r)
+
+
+def test_gnn_fit_reproduces_the_reference_trajectory():
+    from pygda_b200.models import GNN
+    G = load_golden("fit")
+    r = G["runs"]["gnn_gcn"]
+    _fit_and_compare(GNN(device="cuda:0", verbose=0, **r["hparams"]), "gnn", G, r, source=False)
+
+
+def test_tdss_fit_reproduces_the_reference_trajectory():
+    from pygda_b200.models import TDSS
+    G = load_golden("fit")
+    r = G["runs"]["tdss"]
+    _fit_and_compare(TDSS(device="cuda:0", verbose=0, **r["hparams"]), "a2gnn", G, r)
+
+
+def test_dgsda_fit_reproduces_the_reference_trajectory():
+    from pygda_b200.models import DGSDA
+    G = load_golden("fit")
+    r = G["runs"]["dgsda"]
+    _fit_and_compare(DGSDA(device="cuda:0", verbose=0, **r["hparams"]), "dgsda", G, r)
