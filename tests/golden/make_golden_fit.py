@@ -145,6 +145,29 @@ def main():
     est.fit(Data(**blob["source"]), Data(**blob["target"]))
     finish("dgsda", est, "dgsda", hp, box, ("source",))
 
+    # AdaGCN (adagcn.py:200-319), node level: 10 critic iterations with WGAN-GP per step.  The critic is created inside
+    # fit() right after init_model (:264-276) from the same CPU generator, so the recorded RNG state reproduces its
+    # initial weights too; its nn.Dropout(0.1) -- and the encoder's own nn.Dropout(0.1), adagcn_base.py:59 -- draw from that
+    # generator in train mode and are built with p = 0 here.
+    hp = dict(in_dim=20, hid_dim=12, num_classes=3, mode="node", num_layers=2, dropout=0.0, adv_dim=8, gp_weight=5,
+              domain_weight=0.5, lr=0.01, weight_decay=0.001, epoch=3)
+    real_dropout = torch.nn.Dropout
+
+    class NoDropout(real_dropout):
+        def __init__(self, p=0.5, inplace=False):
+            super().__init__(0.0, inplace)
+    torch.manual_seed(85)
+    est = ref.adagcn.AdaGCN(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    torch.nn.Dropout = NoDropout
+    try:
+        est.fit(Data(**blob["source"]), Data(**blob["target"]))
+    finally:
+        torch.nn.Dropout = real_dropout
+    finish("adagcn_node", est, "adagcn", hp, box, ("source",))
+    blob["runs"]["adagcn_node"]["critic_final_state"] = {k: v.clone() for k, v in est.discriminator.state_dict().items()}
+
     torch.save(blob, os.path.join(HERE, "fit.pt"))
     print("wrote fit.pt", os.path.getsize(os.path.join(HERE, "fit.pt")), "bytes")
 

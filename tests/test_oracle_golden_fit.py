@@ -145,3 +145,39 @@ def test_dgsda_fit_trajectory():
     with torch.no_grad():
         assert_close(est.dgsda(t, False), r["target_logits"], 1e-5, "predict(target)")
         assert_close(est.dgsda(s, True), r["source_logits"], 1e-5, "predict(source)")
+
+
+def _critic_from_the_stream(hid, adv):
+    """The reference builds its critic inside fit() right after init_model (adagcn.py:264-270): the same constructor
+    calls on the same generator state give the same initial weights."""
+    return torch.nn.Sequential(torch.nn.Linear(hid, adv), torch.nn.ReLU(), torch.nn.Dropout(0.0),
+                               torch.nn.Linear(adv, 1), torch.nn.Sigmoid())
+
+
+def test_adagcn_fit_trajectory():
+    from oracle.models import AdaGCN
+    G = load_golden("fit")
+    r = G["runs"]["adagcn_node"]
+    hp = r["hparams"]
+    est = AdaGCN(**hp)
+    est.adagcn.load_state_dict(r["init_state"])
+    est.adagcn.encoder.dropout.p = 0.0                     # the encoder keeps its own Dropout(0.1) (adagcn_base.py:59,84):
+    torch.set_rng_state(r["rng_state"])                    # built with p = 0 on the reference side too
+    est.discriminator = _critic_from_the_stream(hp["hid_dim"], hp["adv_dim"])
+    est.c_optimizer = torch.optim.Adam(est.discriminator.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    src_loader, tgt_loader = FullBatchNeighborLoader(Data(**G["source"])), FullBatchNeighborLoader(Data(**G["target"]))
+    for epoch in range(hp["epoch"]):
+        for s, t in zip(src_loader, tgt_loader):
+            est.adagcn.train()
+            loss, _, _ = est.forward_model(s, t)
+            est.optimizer.zero_grad()                      # clears what the critic loop left on the encoder (:302)
+            loss.backward()
+            est.optimizer.step()
+    for k, v in est.adagcn.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-5, "encoder after fit: " + k)
+    for k, v in est.discriminator.state_dict().items():
+        assert_close(v, r["critic_final_state"][k], 1e-5, "critic after fit: " + k)
+    est.adagcn.eval()
+    with torch.no_grad():
+        t = next(iter(tgt_loader))
+        assert_close(est.adagcn.cls_model(est.adagcn(t)), r["target_logits"], 1e-5, "predict(target)")

@@ -120,3 +120,26 @@ def test_dgsda_fit_reproduces_the_reference_trajectory():
     G = load_golden("fit")
     r = G["runs"]["dgsda"]
     _fit_and_compare(DGSDA(device="cuda:0", verbose=0, **r["hparams"]), "dgsda", G, r)
+
+
+@pytest.mark.parametrize("analytic", [False, True])
+def test_adagcn_fit_reproduces_the_reference_trajectory(analytic):
+    """Three epochs x (10 critic iterations + 1 encoder step); the critic is created inside fit() from the recorded
+    generator state, exactly as the reference creates it.  Also with the closed-form critic."""
+    from pygda_b200.models import AdaGCN
+    G = load_golden("fit")
+    r = G["runs"]["adagcn_node"]
+    est = AdaGCN(device="cuda:0", verbose=0, **r["hparams"])
+    est.analytic_critic = analytic
+    real_critic = est.init_critic
+
+    def critic_without_dropout():                          # as on the reference side (make_golden_fit.py)
+        real_critic()
+        est.discriminator[2].p = 0.0
+    est.init_critic = critic_without_dropout
+
+    def encoder_without_dropout(net):                      # the encoder keeps its own Dropout(0.1) (adagcn_base.py:59,84)
+        net.encoder.dropout.p = 0.0
+    _fit_and_compare(est, "adagcn", G, r, post=encoder_without_dropout)
+    for k, v in est.discriminator.state_dict().items():
+        assert_close(v, r["critic_final_state"][k], 2e-3, "critic after fit: " + k)
