@@ -77,8 +77,10 @@ def collate_graphs(graphs):
 
 
 class GraphDataLoader:
-    """``DataLoader(dataset, batch_size, shuffle=True)`` over a list of graphs;
-    shuffle order from the global torch RNG."""
+    """``DataLoader(dataset, batch_size, shuffle=True)`` over a list of graphs.  PyG's DataLoader IS
+    ``torch.utils.data.DataLoader`` with a graph collate function, so the index batches (and the draws they take from
+    the global CPU generator: the iterator's base seed, then the RandomSampler's seed) come from torch's own sampler
+    machinery here as well."""
 
     def __init__(self, dataset, batch_size, shuffle=True):
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
@@ -87,7 +89,8 @@ class GraphDataLoader:
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        n = len(self.dataset)
-        order = torch.randperm(n).tolist() if self.shuffle else list(range(n))
-        for s in range(0, n, self.batch_size):
-            yield collate_graphs([self.dataset[i] for i in order[s:s + self.batch_size]])
+        import torch.utils.data as tud
+        index_batches = tud.DataLoader(range(len(self.dataset)), batch_size=self.batch_size, shuffle=self.shuffle,
+                                       collate_fn=list)
+        for ids in index_batches:
+            yield collate_graphs([self.dataset[i] for i in ids])

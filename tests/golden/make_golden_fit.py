@@ -168,6 +168,37 @@ def main():
     finish("adagcn_node", est, "adagcn", hp, box, ("source",))
     blob["runs"]["adagcn_node"]["critic_final_state"] = {k: v.clone() for k, v in est.discriminator.state_dict().items()}
 
+    # Graph-level mode with shuffled mini-batches (a2gnn.py:266-286, grade.py:214-252): DataLoader(batch_size=8,
+    # shuffle=True) over lists of small graphs -- the batch order comes from torch's sampler on the CPU generator.
+    from pygda_b200.synthetic import graph_dataset
+    gs = [Data(x=d.x, edge_index=d.edge_index, y=d.y) for d in graph_dataset(21, 9, 2.0, 6, 3, seed=7)]
+    gt = [Data(x=d.x, edge_index=d.edge_index, y=d.y) for d in graph_dataset(19, 11, 3.0, 6, 3, seed=8)]
+    blob["graph_source"] = [{"x": d.x, "edge_index": d.edge_index, "y": d.y} for d in gs]
+    blob["graph_target"] = [{"x": d.x, "edge_index": d.edge_index, "y": d.y} for d in gt]
+
+    def finish_graph(name, est, net_attr, hp, box):
+        net = getattr(est, net_attr)
+        blob["runs"][name] = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+                              "final_state": {k: v.clone() for k, v in net.state_dict().items()}}
+
+    hp = dict(in_dim=6, hid_dim=12, num_classes=3, mode="graph", num_layers=2, dropout=0.0, s_pnums=0, t_pnums=2,
+              adv=False, weight=2.0, lr=0.01, weight_decay=0.005, epoch=3, batch_size=8)
+    torch.manual_seed(87)
+    est = ref.a2gnn.A2GNN(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    est.fit(gs, gt)
+    finish_graph("a2gnn_graph", est, "a2gnn", hp, box)
+
+    hp = dict(in_dim=6, hid_dim=12, num_classes=3, mode="graph", num_layers=2, dropout=0.0, disc="JS", weight=0.5,
+              lr=0.01, weight_decay=0.01, epoch=3, batch_size=8)
+    torch.manual_seed(89)
+    est = ref.grade.GRADE(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box)
+    est.fit(gs, gt)
+    finish_graph("grade_graph", est, "grade", hp, box)
+
     torch.save(blob, os.path.join(HERE, "fit.pt"))
     print("wrote fit.pt", os.path.getsize(os.path.join(HERE, "fit.pt")), "bytes")
 

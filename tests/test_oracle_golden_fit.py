@@ -181,3 +181,27 @@ def test_adagcn_fit_trajectory():
     with torch.no_grad():
         t = next(iter(tgt_loader))
         assert_close(est.adagcn.cls_model(est.adagcn(t)), r["target_logits"], 1e-5, "predict(target)")
+
+
+@pytest.mark.parametrize("name", ["a2gnn_graph", "grade_graph"])
+def test_graph_mode_minibatch_fit_trajectory(name):
+    """Shuffled mini-batches of graphs: the batch order comes from torch's own sampler machinery on the CPU generator
+    (PyG's DataLoader is torch's), the zip of the two loaders stops with the shorter one."""
+    from oracle.data import GraphDataLoader
+    from oracle.models import GRADE
+    G = load_golden("fit")
+    r = G["runs"][name]
+    hp = dict(r["hparams"])
+    bs = hp.pop("batch_size")
+    est, net = (A2GNN(**hp), None) if name.startswith("a2gnn") else (GRADE(**hp), None)
+    net = est.a2gnn if name.startswith("a2gnn") else est.grade
+    net.load_state_dict(r["init_state"])
+    torch.set_rng_state(r["rng_state"])
+    gs = [Data(**d) for d in G["graph_source"]]
+    gt = [Data(**d) for d in G["graph_target"]]
+    src_loader, tgt_loader = GraphDataLoader(gs, bs, shuffle=True), GraphDataLoader(gt, bs, shuffle=True)
+    for epoch in range(hp["epoch"]):
+        for s, t in zip(src_loader, tgt_loader):
+            est.train_step(s, t, epoch)
+    for k, v in net.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-5, "weights after fit: " + k)

@@ -143,3 +143,26 @@ def test_adagcn_fit_reproduces_the_reference_trajectory(analytic):
     _fit_and_compare(est, "adagcn", G, r, post=encoder_without_dropout)
     for k, v in est.discriminator.state_dict().items():
         assert_close(v, r["critic_final_state"][k], 2e-3, "critic after fit: " + k)
+
+
+@pytest.mark.parametrize("name", ["a2gnn_graph", "grade_graph"])
+def test_graph_mode_minibatch_fit_reproduces_the_reference_trajectory(name):
+    """Graph-level mode, DataLoader(batch_size=8, shuffle=True): resident dataset collated on the GPU, batch order from
+    torch's sampler on the CPU generator."""
+    from pygda_b200.data import Data
+    from pygda_b200.models import A2GNN, GRADE
+    G = load_golden("fit")
+    r = G["runs"][name]
+    cls, attr = (A2GNN, "a2gnn") if name.startswith("a2gnn") else (GRADE, "grade")
+    est = cls(device="cuda:0", verbose=0, **r["hparams"])
+    real = est.init_model
+
+    def wrapped(**kw):
+        net = real(**kw)
+        net.load_state_dict(r["init_state"])
+        torch.set_rng_state(r["rng_state"])
+        return net
+    est.init_model = wrapped
+    est.fit([Data(**d) for d in G["graph_source"]], [Data(**d) for d in G["graph_target"]])
+    for k, v in getattr(est, attr).state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
