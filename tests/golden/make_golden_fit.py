@@ -168,6 +168,25 @@ def main():
     finish("adagcn_node", est, "adagcn", hp, box, ("source",))
     blob["runs"]["adagcn_node"]["critic_final_state"] = {k: v.clone() for k, v in est.discriminator.state_dict().items()}
 
+    # StruRW with the adversarial objective (GS backbone) and with MMD on the GCN backbone
+    for name, extra in (("strurw_adv", dict(gnn="GS", mode="adv")), ("strurw_mmd", dict(gnn="GCN", mode="mmd"))):
+        hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, cls_dim=8, cls_layers=2, dropout=0.0,
+                  pooling="mean", ew_start=2, ew_freq=2, lamb=0.8, lr=0.01, weight_decay=0.001, epoch=4, **extra)
+        torch.manual_seed(91)
+        est = ref.strurw.StruRW(device="cpu", verbose=0, **hp)
+        box = {}
+        capture_init(est, box)
+        est.fit(Data(edge_weight=None, **blob["source"]), Data(edge_weight=None, **blob["target"]))
+        t = Data(**blob["target"])
+        t.edge_weight = torch.ones(t.edge_index.size(1))
+        t_logits, t_labels = est.predict(t)
+        run = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+               "final_state": {k: v.clone() for k, v in est.gnn.state_dict().items()},
+               "target_logits": t_logits.clone(), "target_labels": t_labels.clone()}
+        if extra["mode"] == "adv":
+            run["disc_final_state"] = {k: v.clone() for k, v in est.domain_discriminator.state_dict().items()}
+        blob["runs"][name] = run
+
     # Graph-level mode with shuffled mini-batches (a2gnn.py:266-286, grade.py:214-252): DataLoader(batch_size=8,
     # shuffle=True) over lists of small graphs -- the batch order comes from torch's sampler on the CPU generator.
     from pygda_b200.synthetic import graph_dataset

@@ -31,13 +31,18 @@ def test_a2gnn_fit_trajectory(name):
     assert torch.equal(t_labels, r["target_labels"]) and torch.equal(s_labels, r["source_labels"])
 
 
-def test_strurw_fit_trajectory(capsys):
+@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd"])
+def test_strurw_fit_trajectory(name, capsys):
     G = load_golden("fit")
-    r = G["runs"]["strurw_erm"]
+    r = G["runs"][name]
     hp = r["hparams"]
     est = StruRW(**hp)
     est.gnn.load_state_dict(r["init_state"])
     torch.set_rng_state(r["rng_state"])
+    if hp["mode"] == "adv":                                 # created inside fit() after init_model (strurw.py:364-372)
+        est.domain_discriminator = torch.nn.Linear(hp["hid_dim"], 2)
+        est.optimizer = torch.optim.Adam(list(est.gnn.parameters()) + list(est.domain_discriminator.parameters()),
+                                         lr=hp["lr"], weight_decay=hp["weight_decay"])
     s0, t0 = Data(**G["source"]), Data(**G["target"])
     s0.edge_weight = torch.ones(s0.edge_index.size(1))
     t0.edge_weight = torch.ones(t0.edge_index.size(1))
@@ -55,6 +60,9 @@ def test_strurw_fit_trajectory(capsys):
     logits, labels = est.predict(t)
     assert_close(logits, r["target_logits"], 1e-5, "predict(target)")
     assert torch.equal(labels, r["target_labels"])
+    if hp["mode"] == "adv":
+        for k, v in est.domain_discriminator.state_dict().items():
+            assert_close(v, r["disc_final_state"][k], 1e-5, "discriminator after fit: " + k)
 
 
 def _run_loop(est, net, G, r, step, prepare=None):

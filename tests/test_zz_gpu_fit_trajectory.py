@@ -41,11 +41,12 @@ def test_a2gnn_fit_reproduces_the_reference_trajectory(name):
     assert torch.equal(t_labels.cpu(), r["target_labels"]) and torch.equal(s_labels.cpu(), r["source_labels"])
 
 
-def test_strurw_fit_reproduces_the_reference_trajectory(capsys):
+@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd"])
+def test_strurw_fit_reproduces_the_reference_trajectory(name, capsys):
     from pygda_b200.data import Data
     from pygda_b200.models import StruRW
     G = load_golden("fit")
-    r = G["runs"]["strurw_erm"]
+    r = G["runs"][name]
     est = StruRW(device="cuda:0", verbose=0, **r["hparams"])
     _inject(est, r)
     est.fit(Data(**G["source"]), Data(**G["target"]))
@@ -55,6 +56,9 @@ def test_strurw_fit_reproduces_the_reference_trajectory(capsys):
     logits, labels = est.predict(Data(**G["target"]))
     assert_close(logits, r["target_logits"], 1e-3, "predict(target)")
     assert torch.equal(labels.cpu(), r["target_labels"])
+    if r["hparams"]["mode"] == "adv":
+        for k, v in est.domain_discriminator.state_dict().items():
+            assert_close(v, r["disc_final_state"][k], 1e-3, "discriminator after fit: " + k)
 
 
 def _fit_and_compare(est, net_attr, G, r, post=None, source=True, tol=1e-3):
