@@ -169,18 +169,21 @@ def main():
     blob["runs"]["adagcn_node"]["critic_final_state"] = {k: v.clone() for k, v in est.discriminator.state_dict().items()}
 
     # StruRW with the adversarial objective (GS backbone) and with MMD on the GCN backbone
-    for name, extra in (("strurw_adv", dict(gnn="GS", mode="adv")), ("strurw_mmd", dict(gnn="GCN", mode="mmd"))):
+    for name, extra in (("strurw_adv", dict(gnn="GS", mode="adv")), ("strurw_mmd", dict(gnn="GCN", mode="mmd")),
+                        ("strurw_mixup", dict(mode="mixup"))):
         hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, cls_dim=8, cls_layers=2, dropout=0.0,
                   pooling="mean", ew_start=2, ew_freq=2, lamb=0.8, lr=0.01, weight_decay=0.001, epoch=4, **extra)
         torch.manual_seed(91)
         est = ref.strurw.StruRW(device="cpu", verbose=0, **hp)
         box = {}
         capture_init(est, box)
+        import numpy as np
+        np.random.seed(95)                                   # mixup: beta draw + node shuffle per step (strurw.py:301,723)
         est.fit(Data(edge_weight=None, **blob["source"]), Data(edge_weight=None, **blob["target"]))
         t = Data(**blob["target"])
         t.edge_weight = torch.ones(t.edge_index.size(1))
         t_logits, t_labels = est.predict(t)
-        run = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
+        run = {"np_seed": 95, "hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
                "final_state": {k: v.clone() for k, v in est.gnn.state_dict().items()},
                "target_logits": t_logits.clone(), "target_labels": t_labels.clone()}
         if extra["mode"] == "adv":

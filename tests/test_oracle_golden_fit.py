@@ -31,7 +31,7 @@ def test_a2gnn_fit_trajectory(name):
     assert torch.equal(t_labels, r["target_labels"]) and torch.equal(s_labels, r["source_labels"])
 
 
-@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd"])
+@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd", "strurw_mixup"])
 def test_strurw_fit_trajectory(name, capsys):
     G = load_golden("fit")
     r = G["runs"][name]
@@ -47,6 +47,8 @@ def test_strurw_fit_trajectory(name, capsys):
     s0.edge_weight = torch.ones(s0.edge_index.size(1))
     t0.edge_weight = torch.ones(t0.edge_index.size(1))
     src_loader, tgt_loader = FullBatchNeighborLoader(s0), FullBatchNeighborLoader(t0)
+    import numpy as np
+    np.random.seed(r.get("np_seed", 0))
     fired = 0
     for epoch in range(hp["epoch"]):
         for s, t in zip(src_loader, tgt_loader):

@@ -41,7 +41,7 @@ def test_a2gnn_fit_reproduces_the_reference_trajectory(name):
     assert torch.equal(t_labels.cpu(), r["target_labels"]) and torch.equal(s_labels.cpu(), r["source_labels"])
 
 
-@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd"])
+@pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd", "strurw_mixup"])
 def test_strurw_fit_reproduces_the_reference_trajectory(name, capsys):
     from pygda_b200.data import Data
     from pygda_b200.models import StruRW
@@ -49,6 +49,8 @@ def test_strurw_fit_reproduces_the_reference_trajectory(name, capsys):
     r = G["runs"][name]
     est = StruRW(device="cuda:0", verbose=0, **r["hparams"])
     _inject(est, r)
+    import numpy as np
+    np.random.seed(r.get("np_seed", 0))                     # mixup: beta draw + node shuffle per step
     est.fit(Data(**G["source"]), Data(**G["target"]))
     assert capsys.readouterr().out.count("edge reweight...") == 2
     for k, v in est.gnn.state_dict().items():
