@@ -117,14 +117,15 @@ def main():
         est.fit(Data(**blob["source"]), Data(**blob["target"]))
         finish("grade_" + disc.lower(), est, "grade", hp, box, ("source",))
 
-    hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, dropout=0.0, gnn="gcn", lr=0.02, weight_decay=0.001,
-              epoch=4)
-    torch.manual_seed(79)
-    est = ref.gnn.GNN(device="cpu", verbose=0, **hp)
-    box = {}
-    capture_init(est, box)
-    est.fit(Data(**blob["source"]), Data(**blob["target"]))
-    finish("gnn_gcn", est, "gnn", hp, box)
+    for backbone in ("gcn", "gat"):
+        hp = dict(in_dim=20, hid_dim=12, num_classes=3, num_layers=2, dropout=0.0, gnn=backbone, lr=0.02,
+                  weight_decay=0.001, epoch=4)
+        torch.manual_seed(79)
+        est = ref.gnn.GNN(device="cpu", verbose=0, **hp)
+        box = {}
+        capture_init(est, box)
+        est.fit(Data(**blob["source"]), Data(**blob["target"]))
+        finish("gnn_" + backbone, est, "gnn", hp, box)
 
     hp = dict(in_dim=20, hid_dim=12, num_classes=3, mode="node", smooth_mode="K-hop", num_layers=2, dropout=0.0,
               s_pnums=0, t_pnums=3, k=2, alpha=0.5, beta=0.05, lr=0.01, weight_decay=0.005, epoch=4)

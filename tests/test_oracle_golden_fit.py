@@ -112,10 +112,11 @@ def test_grade_fit_trajectory(disc):
         assert_close(est.grade(s)[0], r["source_logits"], 1e-5, "predict(source)")
 
 
-def test_gnn_fit_trajectory():
+@pytest.mark.parametrize("backbone", ["gcn", "gat"])
+def test_gnn_fit_trajectory(backbone):
     from oracle.models import GNN
     G = load_golden("fit")
-    r = G["runs"]["gnn_gcn"]
+    r = G["runs"]["gnn_" + backbone]
     hp = r["hparams"]
     est = GNN(**hp)
     opt = torch.optim.Adam(est.gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])   # gnn.py:195-199

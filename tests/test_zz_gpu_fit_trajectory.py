@@ -107,10 +107,11 @@ def test_grade_fit_reproduces_the_reference_trajectory(disc):
     _fit_and_compare(GRADE(device="cuda:0", verbose=0, **r["hparams"]), "grade", G, r)
 
 
-def test_gnn_fit_reproduces_the_reference_trajectory():
+@pytest.mark.parametrize("backbone", ["gcn", "gat"])
+def test_gnn_fit_reproduces_the_reference_trajectory(backbone):
     from pygda_b200.models import GNN
     G = load_golden("fit")
-    r = G["runs"]["gnn_gcn"]
+    r = G["runs"]["gnn_" + backbone]
     _fit_and_compare(GNN(device="cuda:0", verbose=0, **r["hparams"]), "gnn", G, r, source=False)
 
 
