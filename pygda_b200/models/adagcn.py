@@ -20,7 +20,7 @@ For D(x) = sigmoid(w2 . (relu(W1 x + b1) * m) + b2) with dropout mask m,
 
 so no [rows, hid] gradient tensor is ever formed and first-order autograd over [rows, adv_dim]
 arrays yields the same parameter gradients (relu' and the mask are piecewise constant, exactly as in
-torch's double backward).  Checked against the double-backward form (tests/test_zz_gpu_critic.py)."""
+torch's double backward).  Checked against the double-backward form (tests/test_zz3_gpu_critic.py)."""
 import torch
 import torch.nn.functional as F
 from torch import nn

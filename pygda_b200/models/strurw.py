@@ -9,7 +9,7 @@ Edge re-weighting (:446-548).  The reference densifies both adjacencies (``to_de
 100 k nodes), multiplies them with one-hot label matrices in scipy on the host and then loops over the C^2 class pairs
 with ``np.in1d`` over the edge list.  The same numbers are, exactly: class-pair edge COUNTS (a bincount over
 ``C * y[row] + y[col]``), class sizes, two float64 divisions and a [C, C] table lookup per edge -- done here on the
-device with the same float64 arithmetic, bit-identical to the reference (tests/test_strurw_host.py on the CPU, tests/test_zz_gpu_strurw.py on the GPU).  This is index
+device with the same float64 arithmetic, bit-identical to the reference (tests/test_strurw_host.py on the CPU, tests/test_zz2_gpu_strurw.py on the GPU).  This is index
 plumbing that runs every ``ew_freq`` epochs, not per step, so it stays a handful of torch integer ops."""
 import copy
 import itertools

@@ -1,7 +1,7 @@
 #!/bin/bash
 # DEVELOPER TOOL (see shim_patch.py): run the Python side of a GPU test file on the CPU with the libgda calls replaced by
 # torch expressions.  The file is copied to a scratch directory with "cuda" -> "cpu" substitutions; nothing here is
-# collected by the repo's pytest runs.   bash tests/devtools/desk_check.sh tests/test_zz_gpu_strurw.py [-k expr]
+# collected by the repo's pytest runs.   bash tests/devtools/desk_check.sh tests/test_zz2_gpu_strurw.py [-k expr]
 set -e
 here=$(cd "$(dirname "$0")" && pwd)
 root=$(cd "$here/../.." && pwd)

@@ -6,7 +6,7 @@ of new estimators / layers be exercised on the CPU: importing it monkeypatches t
 shape / attribute / autograd-wiring mistakes before a GPU call is spent; it proves nothing about the kernels, is never
 imported by ``pygda_b200`` or by the pytest suites (``tests/devtools`` holds no ``test_*.py``), and no parity claim
 rests on it -- parity is what ``pytest -m gpu`` measures on the B200 against the oracle and the golden vectors.
-Usage: ``bash tests/devtools/desk_check.sh tests/test_zz_gpu_strurw.py``."""
+Usage: ``bash tests/devtools/desk_check.sh tests/test_zz2_gpu_strurw.py``."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
