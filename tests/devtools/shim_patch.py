@@ -104,7 +104,7 @@ import pygda_b200.models.strurw as S
 import pygda_b200.models.adagcn as _A
 _A.ops = ops
 _A.Adam = torch.optim.Adam
-S.MMD = lambda a, b, indices=None: OM.MMD(a, b, indices=indices)
+S.MMD = lambda a, b, indices=None: OM.MMD(a, b, indices=indices, sqdist=lambda z: OM.pairwise_sqdist_blocked(z, 250))
 S.Adam = torch.optim.Adam
 from pygda_b200.metrics import eval_micro_f1
 S.micro_f1_from_logits = lambda y, z: eval_micro_f1(y, z.argmax(1))
@@ -134,7 +134,7 @@ import importlib
 for _name in ("udagcn", "grade", "a2gnn", "gnn", "dgsda", "tdss"):
     _m = importlib.import_module("pygda_b200.models." + _name)
     if hasattr(_m, "MMD"):
-        _m.MMD = lambda a, b, indices=None, **kw: OM.MMD(a, b, indices=indices)
+        _m.MMD = lambda a, b, indices=None, **kw: OM.MMD(a, b, indices=indices, sqdist=lambda z: OM.pairwise_sqdist_blocked(z, 250))
     if hasattr(_m, "Adam"):
         _m.Adam = torch.optim.Adam
 
