@@ -222,6 +222,27 @@ def main():
     est.fit(gs, gt)
     finish_graph("grade_graph", est, "grade", hp, box)
 
+    # UDAGCN in graph mode, batch_size=0 (one shuffled batch of ALL graphs per epoch).  Pins the CachedGCNConv quirk end to
+    # end: the normalised graph is cached per cache_name at the FIRST batch (cached_gcn_conv.py:132-136) and silently
+    # re-used for the differently shuffled batches of the later epochs.
+    hp = dict(in_dim=6, hid_dim=12, num_classes=3, mode="graph", num_layers=2, ppmi=False, adv_dim=8, lr=0.01,
+              weight_decay=0.003, epoch=3, batch_size=0)
+    torch.manual_seed(93)
+    est = ref.udagcn.UDAGCN(device="cpu", verbose=0, **hp)
+    box = {}
+    capture_init(est, box, post=no_encoder_dropout)
+    real_u = est.init_model
+
+    def plain_domain_model_u(**kw):
+        net = real_u(**kw)
+        for m in net.domain_model:
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        return net
+    est.init_model = plain_domain_model_u
+    est.fit(gs, gt)
+    finish_graph("udagcn_graph", est, "udagcn", hp, box)
+
     torch.save(blob, os.path.join(HERE, "fit.pt"))
     print("wrote fit.pt", os.path.getsize(os.path.join(HERE, "fit.pt")), "bytes")
 

@@ -216,3 +216,32 @@ def test_graph_mode_minibatch_fit_trajectory(name):
             est.train_step(s, t, epoch)
     for k, v in net.state_dict().items():
         assert_close(v, r["final_state"][k], 1e-5, "weights after fit: " + k)
+
+
+def test_udagcn_graph_mode_fit_trajectory_with_the_stale_graph_cache():
+    """One shuffled batch of all graphs per epoch: the conv layers keep the normalised graph of the FIRST batch
+    (cached_gcn_conv.py:132-136) and apply it to the differently ordered later batches -- as the reference does."""
+    from oracle.data import GraphDataLoader
+    from oracle.models import UDAGCN
+    G = load_golden("fit")
+    r = G["runs"]["udagcn_graph"]
+    hp = dict(r["hparams"])
+    hp.pop("batch_size")
+    est = UDAGCN(**hp)
+    est.udagcn.load_state_dict(r["init_state"])
+    est.udagcn.encoder.dropout_layers = [torch.nn.Identity() for _ in est.udagcn.encoder.dropout_layers]
+    for m in est.udagcn.domain_model:
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    torch.set_rng_state(r["rng_state"])
+    gs = [Data(**d) for d in G["graph_source"]]
+    gt = [Data(**d) for d in G["graph_target"]]
+    src_loader, tgt_loader = GraphDataLoader(gs, len(gs), shuffle=True), GraphDataLoader(gt, len(gt), shuffle=True)
+    orders = []
+    for epoch in range(hp["epoch"]):
+        for s, t in zip(src_loader, tgt_loader):
+            orders.append(s.y.tolist())
+            est.train_step(s, t, epoch)
+    assert orders[0] != orders[1]                          # the batches really are ordered differently
+    for k, v in est.udagcn.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-5, "weights after fit: " + k)

@@ -174,3 +174,27 @@ def test_graph_mode_minibatch_fit_reproduces_the_reference_trajectory(name):
     est.fit([Data(**d) for d in G["graph_source"]], [Data(**d) for d in G["graph_target"]])
     for k, v in getattr(est, attr).state_dict().items():
         assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
+
+
+def test_udagcn_graph_mode_fit_keeps_the_first_batchs_graph_like_the_reference():
+    """mode='graph', batch_size=0: one shuffled batch of all graphs per epoch; the conv layers cache the normalised graph
+    of the first batch per cache_name and re-use it for the later, differently ordered batches
+    (cached_gcn_conv.py:132-136).  The reference's trajectory contains that quirk; so must ours."""
+    from pygda_b200.data import Data
+    from pygda_b200.models import UDAGCN
+    G = load_golden("fit")
+    r = G["runs"]["udagcn_graph"]
+    est = UDAGCN(device="cuda:0", verbose=0, **r["hparams"])
+    real = est.init_model
+
+    def wrapped(**kw):
+        net = real(**kw)
+        net.load_state_dict(r["init_state"])
+        net.encoder.dropout_p = [0.0 for _ in net.encoder.dropout_p]
+        net.domain_model[1].p = 0.0
+        torch.set_rng_state(r["rng_state"])
+        return net
+    est.init_model = wrapped
+    est.fit([Data(**d) for d in G["graph_source"]], [Data(**d) for d in G["graph_target"]])
+    for k, v in est.udagcn.state_dict().items():
+        assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
