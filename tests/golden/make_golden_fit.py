@@ -51,10 +51,14 @@ def main():
         est.fit(Data(**blob["source"]), Data(**blob["target"]))
         t_logits, t_labels = est.predict(Data(**blob["target"]))
         s_logits, s_labels = est.predict(Data(**blob["source"]), source=True)
+        # predict() ignores its ``data`` argument and re-iterates the loaders stored by fit()
+        other_logits, other_labels = est.predict(Data(**blob["source"]))          # source graph, source=False
         blob["runs"][name] = {"hparams": hp, "init_state": box["state"], "rng_state": box["rng_state"],
                               "final_state": {k: v.clone() for k, v in est.a2gnn.state_dict().items()},
                               "target_logits": t_logits.clone(), "target_labels": t_labels.clone(),
-                              "source_logits": s_logits.clone(), "source_labels": s_labels.clone()}
+                              "source_logits": s_logits.clone(), "source_labels": s_labels.clone(),
+                              "predict_ignores_data": bool(torch.equal(other_logits, t_logits) and
+                                                           torch.equal(other_labels, t_labels))}
 
     # StruRW, GS backbone, 'erm' objective; the edge re-weighting fires in epochs 1 and 3 (and, PyG's loaders building a
     # new batch object per epoch, lasts for that epoch's source pass only)

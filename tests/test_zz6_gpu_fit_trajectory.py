@@ -39,6 +39,10 @@ def test_a2gnn_fit_reproduces_the_reference_trajectory(name):
     assert_close(t_logits, r["target_logits"], 1e-3, "predict(target)")
     assert_close(s_logits, r["source_logits"], 1e-3, "predict(source)")
     assert torch.equal(t_labels.cpu(), r["target_labels"]) and torch.equal(s_labels.cpu(), r["source_labels"])
+    # the reference's predict() ignores its ``data`` argument (it re-iterates the loaders fit() stored): so does ours
+    assert r["predict_ignores_data"] is True
+    other_logits, other_labels = est.predict(src)                     # the SOURCE graph with source=False
+    assert torch.equal(other_logits, t_logits) and torch.equal(other_labels, t_labels)
 
 
 @pytest.mark.parametrize("name", ["strurw_erm", "strurw_adv", "strurw_mmd", "strurw_mixup"])
