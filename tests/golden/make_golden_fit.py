@@ -195,6 +195,31 @@ def main():
             run["disc_final_state"] = {k: v.clone() for k, v in est.domain_discriminator.state_dict().items()}
         blob["runs"][name] = run
 
+    # What fit() PRINTS with verbose=2 (utils/utility.py): per epoch the summed loss and the micro-F1 of the source
+    # predictions -- A2GNN scores the TRAINING-mode logits of the step (a2gnn.py:321-329), GNN and StruRW re-predict in eval
+    # mode after every step (gnn.py:219-226, strurw.py:423-431).  Same seeds as the runs above, so the same trajectories.
+    import contextlib
+    import io
+    import re
+
+    def logged(make_est, seed, fit_args):
+        torch.manual_seed(seed)
+        est = make_est()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            est.fit(*fit_args())
+        rows = re.findall(r"Epoch (\d+): loss ([-0-9.]+), source acc ([0-9.]+)", buf.getvalue())
+        return [(int(e), float(l), float(a)) for e, l, a in rows]
+
+    plain = lambda: (Data(**blob["source"]), Data(**blob["target"]))                                   # noqa: E731
+    weighted = lambda: (Data(edge_weight=None, **blob["source"]), Data(edge_weight=None, **blob["target"]))   # noqa: E731
+    blob["runs"]["a2gnn_mmd"]["log"] = logged(
+        lambda: ref.a2gnn.A2GNN(device="cpu", verbose=2, **blob["runs"]["a2gnn_mmd"]["hparams"]), 71, plain)
+    blob["runs"]["gnn_gcn"]["log"] = logged(
+        lambda: ref.gnn.GNN(device="cpu", verbose=2, **blob["runs"]["gnn_gcn"]["hparams"]), 79, plain)
+    blob["runs"]["strurw_erm"]["log"] = logged(
+        lambda: ref.strurw.StruRW(device="cpu", verbose=2, **blob["runs"]["strurw_erm"]["hparams"]), 73, weighted)
+
     # Graph-level mode with shuffled mini-batches (a2gnn.py:266-286, grade.py:214-252): DataLoader(batch_size=8,
     # shuffle=True) over lists of small graphs -- the batch order comes from torch's sampler on the CPU generator.
     from pygda_b200.synthetic import graph_dataset

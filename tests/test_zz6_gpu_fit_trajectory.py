@@ -202,3 +202,26 @@ def test_udagcn_graph_mode_fit_keeps_the_first_batchs_graph_like_the_reference()
     est.fit([Data(**d) for d in G["graph_source"]], [Data(**d) for d in G["graph_target"]])
     for k, v in est.udagcn.state_dict().items():
         assert_close(v, r["final_state"][k], 1e-3, "weights after fit: " + k)
+
+
+@pytest.mark.parametrize("name", ["a2gnn_mmd", "gnn_gcn", "strurw_erm"])
+def test_fit_prints_the_reference_epoch_lines(name, capsys):
+    """verbose=2: 'Epoch NNNN: loss x, source acc y, time z' per epoch -- the summed loss and the micro-F1 of the source
+    predictions (training-mode logits for A2GNN, an eval-mode re-prediction after every step for GNN and StruRW), as the
+    reference printed them for the same run.  Loss to 1e-3 absolute (printed with four decimals), accuracy exact up to
+    one sample of 60."""
+    import re
+    from pygda_b200.data import Data
+    from pygda_b200 import models as M
+    G = load_golden("fit")
+    r = G["runs"][name]
+    cls = {"a2gnn_mmd": M.A2GNN, "gnn_gcn": M.GNN, "strurw_erm": M.StruRW}[name]
+    est = cls(device="cuda:0", verbose=2, **r["hparams"])
+    _inject(est, r)
+    est.fit(Data(**G["source"]), Data(**G["target"]))
+    rows = re.findall(r"Epoch (\d+): loss ([-0-9.]+), source acc ([0-9.]+), time", capsys.readouterr().out)
+    got = [(int(e), float(l), float(a)) for e, l, a in rows]
+    assert [e for e, _, _ in got] == [e for e, _, _ in r["log"]]
+    for (_, loss, acc), (_, rloss, racc) in zip(got, r["log"]):
+        assert abs(loss - rloss) <= 1e-3 * max(1.0, abs(rloss)), (got, r["log"])
+        assert abs(acc - racc) <= 1.0 / 60 + 1e-4, (got, r["log"])
