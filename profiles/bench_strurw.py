@@ -4,7 +4,7 @@
 benchmark/node/strurw.py:37-46), lr 0.003 / wd 0.01 / dropout 0.2 / lamb 0.8 (benchmark/node/run_citation.sh:6).
 CUDA-event time per training step with and without a re-weighting in the step, the edge re-weighting alone
 (reference: dense N x N adjacencies on the host, 40 GB each at this size), per-launch aggregation time and B_alg GB/s on
-the folded re-weighted CSR (empty rows possible -> generic walker) .  One JSON object per line on stdout."""
+the folded re-weighted CSR (isolated nodes get an explicit zero-weight entry, so the lean kernels apply).  One JSON object per line on stdout."""
 import json
 import os
 import statistics

@@ -229,3 +229,20 @@ def test_message_values_degenerate_inputs():
     assert torch.equal(v, torch.ones(4))
     with pytest.raises(ValueError, match="unsupported aggregation"):
         message_values(ei, None, None, 0.5, 4, "max")
+
+
+def test_fill_empty_rows_keeps_the_matrix_and_leaves_no_row_or_column_empty():
+    from pygda_b200.nn.reweight_gnn import fill_empty_rows
+    n = 7
+    ei = torch.tensor([[0, 0, 2, 4], [1, 2, 0, 4]])           # 3, 5, 6 isolated; 1 has no out-edge; 4 only a loop
+    val = torch.tensor([0.5, 1.5, 2.0, 3.0])
+    ei2, val2 = fill_empty_rows(ei, val, n)
+    dense = torch.zeros(n, n).index_put_((ei[0], ei[1]), val, accumulate=True)
+    dense2 = torch.zeros(n, n).index_put_((ei2[0], ei2[1]), val2, accumulate=True)
+    assert torch.equal(dense, dense2)                          # zero-weight entries only
+    assert torch.equal(ei2[:, :4], ei) and torch.equal(val2[:4], val)
+    for r in (0, 1):
+        assert torch.bincount(ei2[r], minlength=n).min() >= 1
+    assert sorted(ei2[0, 4:].tolist()) == [1, 3, 5, 6] and torch.equal(ei2[0, 4:], ei2[1, 4:])
+    same = fill_empty_rows(ei2, val2, n)
+    assert same[0] is ei2 and same[1] is val2                  # nothing to add the second time
