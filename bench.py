@@ -56,8 +56,32 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.thread, self.gpu = [], None, None, str(gpu_index)
+        self.nvml_rows, self.nvml_thread, self.nvml_stop = [], None, threading.Event()
+
+    def _nvml_pump(self):
+        """Polls NVML every ~10 ms: the timed region of the default run is ~120 ms, which `nvidia-smi -lms 100` sees
+        once.  Any failure simply ends this thread; the nvidia-smi rows remain."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(self.gpu))
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.nvml_stop.is_set():
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:                                       # noqa: BLE001
+                    power = 0.0
+                self.nvml_rows.append((sm, smax, power, int(get_reasons(h))))
+                time.sleep(0.01)
+        except Exception:                                               # noqa: BLE001
+            return
 
     def start(self):
+        self.nvml_thread = threading.Thread(target=self._nvml_pump, daemon=True)
+        self.nvml_thread.start()
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100",
@@ -71,7 +95,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    # NVML clocks-event-reason bits (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+    NVML_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+                 ("hw_thermal_slowdown", 0x40))
+
     def stop(self):
+        self.nvml_stop.set()
+        if self.nvml_thread is not None:
+            self.nvml_thread.join(timeout=2)
+        smi = self._stop_smi()
+        rows = list(self.nvml_rows)
+        if len(rows) < 2:
+            return smi
+        reasons = set(r for r in smi.get("reasons", []) if r in dict(self.NVML_BITS))
+        for _, _, _, bits in rows:
+            reasons.update(name for name, bit in self.NVML_BITS if bits & bit)
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": max(r[1] for r in rows),
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows), "source": "nvml, 10 ms period",
+                "reasons": sorted(reasons)}
+
+    def _stop_smi(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
