@@ -70,8 +70,12 @@ def test_reweight_gnn_golden(name):
     for k, v in got.items():
         if name == "gs_bn" and k == "mlp_classify.0.bias":
             # a bias in front of a BatchNorm has an analytically ZERO gradient (the batch mean is subtracted):
-            # both sides hold rounding noise there, so it is bounded against the weight gradient's scale
-            assert float(v.abs().max()) <= 1e-4 * float(c["grads"]["mlp_classify.0.weight"].abs().max())
+            # both sides hold only rounding noise there (the reference's CPU run: 1.2e-4; torch's cuDNN BatchNorm
+            # backward on the B200: 8.8e-4, GPUTEST_r01), i.e. the noise of a sum of N terms that cancel.  It is
+            # bounded by 1e-3 of the scale of the gradient that flows through the same rows (the weight gradient).
+            scale = float(c["grads"]["mlp_classify.0.weight"].abs().max())
+            assert float(c["grads"][k].abs().max()) <= 1e-3 * scale          # the golden is noise as well
+            assert float(v.abs().max()) <= 1e-3 * scale, float(v.abs().max())
             continue
         assert_close(v, c["grads"][k], 1e-4, "grad " + k)
 
