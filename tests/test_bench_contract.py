@@ -34,8 +34,8 @@ def test_committed_gpu_line_has_the_contract_keys():
 
 
 def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--ref-scale", "50"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -46,6 +46,11 @@ def test_reference_arm_prints_one_contract_line():
                            "d2h_bytes_per_step": 0}
     c = line["cpu_baseline"]
     assert c["value"] == line["value"] and c["kind"] == "port" and c["cores"] >= 1 and c["sample"]
+    # measured, and says what was run: the requested counts, honestly (the full-scale run is what the driver times;
+    # this test uses the reduced-size knob and the line must say so)
+    assert line["steps"] == 2 and line["warmup"] == 1 and c["estimated"] is False
+    assert "REDUCED 1/50 scale" in c["sample"] and c["small_scale_estimate"]["estimated"] is True
+    assert abs(line["ms_per_step"] * 1e-3 * line["value"] - 1.0) < 1e-9
 
 
 def test_reference_arm_is_silent_on_other_ranks():
