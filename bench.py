@@ -339,11 +339,15 @@ def run_gpu_arm(args, rank, world, local_rank):
               adv=False, weight=CFG["weight"], weight_decay=CFG["weight_decay"], lr=CFG["lr"],
               epoch=CFG["epochs"], device=str(dev), verbose=0)
     torch.manual_seed(0)
+    run_epoch = None
     if not distributed:
         src, tgt = domain_pair(CFG["nodes"], CFG["edges"], CFG["feats"], CFG["classes"], seed=0, device=dev)
         model = A2GNN(**hp)
-        model._build_loaders(src, tgt)
-        model.a2gnn = model.init_model()
+        if args.no_cuda_graph:
+            model.cuda_graph = False
+        # exactly what fit() does before its epoch loop (pygda_b200/models/a2gnn.py: prepare_fit): loaders, model,
+        # optimiser and -- the default for full-batch node mode -- the CUDA-graph step; epoch 0 ran eagerly inside
+        run_epoch = model.prepare_fit(src, tgt)
         s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
         parallelism = "single GPU"
     else:
@@ -366,10 +370,11 @@ def run_gpu_arm(args, rank, world, local_rank):
         parallelism = ("1-D node partition: %d communities of %dk nodes (one per GPU, 5%% cross-partition edges), "
                        "NVLink peer gathers in the aggregation kernel, NCCL gradient all-reduce; value counts "
                        "config-2-sized graph-epochs per second" % (world, CFG["nodes"] // 1000))
-    params = list(model.a2gnn.parameters())
-    opt = Adam(params, lr=CFG["lr"], weight_decay=CFG["weight_decay"])
-    sopt = opt
-    step_no = [0]
+    if run_epoch is not None or not distributed:
+        sopt = model.optimizer
+    else:
+        sopt = Adam(list(model.a2gnn.parameters()), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    step_no = [1]
 
     def one_step(sb, tb):
         alpha = model.alpha_at(step_no[0] % CFG["epochs"], CFG["epochs"])
@@ -378,31 +383,23 @@ def run_gpu_arm(args, rank, world, local_rank):
         return loss
 
     # ---------------- device-resident throughput (`value`) ----------------
+    # Single GPU: fit()'s default path -- the loop body replayed from a CUDA graph (pygda_b200/models/graphed.py),
+    # the same kernels on the same resident buffers, MMD indices still drawn on the CPU generator and staged in
+    # before every replay.  `--no-cuda-graph` / N > 1: every kernel issued eagerly.
+    def timed_step(sb, tb):
+        if run_epoch is not None:
+            e = step_no[0]
+            step_no[0] += 1
+            return run_epoch(e % CFG["epochs"] or 1)[0]
+        return one_step(sb, tb)
+
     warm = args.warmup if args.skip_e2e else max(args.warmup, 3)      # profiling runs may use fewer
     for _ in range(warm):
-        one_step(s_batch, t_batch)
+        timed_step(s_batch, t_batch)
     barrier()
-    # Single GPU: the timed steps replay the loop body from a CUDA graph (pygda_b200/models/graphed.py) --
-    # the same kernels on the same resident buffers, MMD indices still drawn on the CPU generator and
-    # staged in before every replay.  Falls back to eager issue if the capture is refused.
-    gstep, graph_note = None, "eager launches"
-    if not distributed and not args.no_cuda_graph:
-        try:
-            from pygda_b200.models.graphed import GraphedStep
-            gstep = GraphedStep(model, s_batch, t_batch, sopt, warmup=1)
-            for _ in range(2):
-                gstep()
-            torch.cuda.synchronize()
-            graph_note = "CUDA graph replay (%d kernels per step)" % gstep.launches_per_replay
-        except Exception as exc:                      # noqa: BLE001 -- report and measure the eager path
-            gstep, graph_note = None, "eager launches (graph capture failed: %s)" % str(exc)[:200]
-            torch.cuda.synchronize()
-    eager_step = one_step
-
-    def timed_step(sb, tb):
-        if gstep is not None:
-            return gstep()[0]
-        return eager_step(sb, tb)
+    gstep = getattr(model, "graphed_step", None) if run_epoch is not None else None
+    graph_note = ("CUDA graph replay (%d kernels per step), fit()'s default" % gstep.launches_per_replay
+                  if gstep is not None else "eager launches")
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -493,85 +490,88 @@ def run_gpu_arm(args, rank, world, local_rank):
                               "host_issue_ms_per_step": host_issue_ms, "gpu_launches": int(launches),
                               "issue": graph_note, "roofline": roofline, "note": "profiling run"}), flush=True)
         return
-    # Host copies of the step's inputs.  Two pinned staging forms are timed: (a) `Data.pin_memory()` as the package
-    # ships it -- a sparse fp32 x (bag-of-words: ~7 % non-zero here) is kept ROW-COMPRESSED in pinned memory, only the
-    # non-zeros cross PCIe and the dense matrix is rebuilt on the GPU bit for bit (gda_unpack_rows_f32); (b) the
-    # plain dense pinned copy (pack=False).  Both copy every input of the step host->device inside the timed region.
+    # Host copies of the step's inputs; every timed step copies x / edge_index / y of both graphs host->device and
+    # reads the loss back.  `Data.pin_memory()` (what fit()'s loaders do) keeps a sparse fp32 x ROW-COMPRESSED in pinned
+    # memory: only the non-zeros cross PCIe, the dense matrix is rebuilt on the GPU bit for bit (gda_unpack_rows_f32).
+    #   e2e.value          fit()'s DEFAULT path (A2GNN.prepare_fit on the host graphs): CUDA-graph replay, the copy of
+    #                      epoch e+1 double-buffered behind the replay of epoch e (models/graphed.py: StagedBatch)
+    #   e2e.eager_serial   the reference's schedule: copy, then compute, every kernel issued from Python
+    #                      (cuda_graph = False, prefetch = False) -- round 1's e2e.value
+    #   e2e.dense_staging  eager_serial with the plain dense pinned copy (pack=False)
     src_h, tgt_h = src.to("cpu"), tgt.to("cpu")
-    if distributed:
-        sb_h, tb_h = src_h, tgt_h
-    else:
-        model._build_loaders(src_h, tgt_h)
-        sb_h, tb_h = next(iter(model.source_loader)), next(iter(model.target_loader))
-    del src, tgt, s_batch, t_batch, gstep
+    del src, tgt, s_batch, t_batch, gstep, run_epoch
+    if hasattr(model, "graphed_step"):
+        del model.graphed_step
     torch.cuda.empty_cache()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
 
-    def e2e_run(sb, tb):
-        for _ in range(3):
-            one_step(sb, tb).item()
+    def timed_loop(step_fn, n):
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(e2e_steps):
-            one_step(sb, tb).item()              # host->device copies + loss read-back every step
+        for i in range(n):
+            step_fn(i).item()                          # loss read-back every step
         t1.record()
         barrier()
         t = torch.tensor([t0.elapsed_time(t1)], device=dev)
         if distributed:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * e2e_steps / (float(t.item()) / 1e3)
+        return world * n / (float(t.item()) / 1e3)
 
-    # (the loaders built above already hold the pinned form -- what `fit()` sends every step; re-pinning is a no-op copy)
-    sb_p = sb_h if "_packed_x" in sb_h.__dict__ or sb_h.x.is_pinned() else sb_h.pin_memory()
-    tb_p = tb_h if "_packed_x" in tb_h.__dict__ or tb_h.x.is_pinned() else tb_h.pin_memory()
-    h2d = sb_p.h2d_nbytes() + tb_p.h2d_nbytes()
-    packed = "_packed_x" in sb_p.__dict__
-    e2e_value = e2e_run(sb_p, tb_p)
-    del sb_p, tb_p
-    sb_d = Data(x=sb_h.x, edge_index=sb_h.edge_index, y=sb_h.y).pin_memory(pack=False)
-    tb_d = Data(x=tb_h.x, edge_index=tb_h.edge_index, y=tb_h.y).pin_memory(pack=False)
-    for a, b in ((sb_d, sb_h), (tb_d, tb_h)):            # same graph-cache identity as the packed form
-        for attr in ("_gda_partition", "_gda_key", "_gda_keepalive"):
-            if hasattr(b.edge_index, attr):
-                setattr(a.edge_index, attr, getattr(b.edge_index, attr))
-        for k, v in b.__dict__.items():
-            if k not in a.__dict__ and k != "_packed_x":
-                a.__dict__[k] = v
-    h2d_dense = sb_d.h2d_nbytes() + tb_d.h2d_nbytes()
-    e2e_dense = e2e_run(sb_d, tb_d)
-    del sb_d, tb_d
-
-    # (c) reported next to the two above, never instead of them: the same packed staging with the loaders' opt-in
-    # software pipeline (`estimator.prefetch = True`, pygda_b200/data.py) -- the copy of the next epoch's batch is
-    # issued on a side stream while the current step runs.  Exactly the loop of fit(): one batch per loader per
-    # epoch; every epoch's inputs still cross PCIe inside the timed region (steady state: the copy consumed by the
-    # first timed step was issued during the last warm-up step, the last timed step issues one more).
-    e2e_prefetch = None
+    e2e_note, e2e_eager, e2e_dense, h2d_dense = "eager launches, copy then compute", None, None, None
     if not distributed:
-        try:
-            model.prefetch = True
-            model._build_loaders(src_h, tgt_h)
+        model.cuda_graph = not args.no_cuda_graph
+        run_h = model.prepare_fit(src_h, tgt_h)        # pins (row-compresses) the host graphs like fit() does
+        sopt = model.optimizer
+        sb_p, tb_p = next(iter(model.source_loader)), next(iter(model.target_loader))
+        h2d = sb_p.h2d_nbytes() + tb_p.h2d_nbytes()
+        packed = "_packed_x" in sb_p.__dict__
+        if run_h is not None:
+            gs = model.graphed_step
+            h2d = gs.h2d_bytes_per_step                 # counted from the tensors StagedBatch copies every epoch
+            e2e_note = ("fit() default: CUDA-graph replay, next epoch's host->device copy double-buffered behind it "
+                        "(+%d staging kernels per step)" % (gs.restage_launches if hasattr(gs, "restage_launches") else 0))
+            ep = [1]
 
-            def pf_epochs(n):
-                for _ in range(n):
-                    for sb, tb in zip(model.source_loader, model.target_loader):
-                        one_step(sb, tb).item()
-
-            pf_epochs(3)
-            barrier()
-            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-            t0.record()
-            pf_epochs(e2e_steps)
-            t1.record()
-            barrier()
-            e2e_prefetch = {"value": e2e_steps / (t0.elapsed_time(t1) / 1e3), "unit": UNIT,
-                            "h2d_bytes_per_step": h2d, "steps": e2e_steps,
-                            "how": "NeighborLoader(prefetch_device=...): next epoch's H2D on a side stream"}
-        except Exception as exc:                                        # an experiment: never takes the line down
-            e2e_prefetch = {"error": repr(exc)[:300]}
-        finally:
-            model.prefetch = False
+            def graphed_h(i):
+                ep[0] += 1
+                return run_h(ep[0] % CFG["epochs"] or 1)[0]
+            for i in range(3):
+                graphed_h(i).item()
+            e2e_value = timed_loop(graphed_h, e2e_steps)
+            del run_h, gs
+            del model.graphed_step
+            torch.cuda.empty_cache()
+        else:
+            for i in range(3):
+                one_step(sb_p, tb_p).item()
+            e2e_value = timed_loop(lambda i: one_step(sb_p, tb_p), e2e_steps)
+        # the reference's serial schedule on the same pinned batches (side keys)
+        n_side = max(3, min(args.steps, 10))
+        for i in range(3):
+            one_step(sb_p, tb_p).item()
+        e2e_eager = timed_loop(lambda i: one_step(sb_p, tb_p), n_side)
+        sb_d = Data(x=sb_p.x, edge_index=sb_p.edge_index, y=sb_p.y).pin_memory(pack=False)
+        tb_d = Data(x=tb_p.x, edge_index=tb_p.edge_index, y=tb_p.y).pin_memory(pack=False)
+        for a_, b_ in ((sb_d, sb_p), (tb_d, tb_p)):          # same graph-cache identity as the packed form
+            for attr in ("_gda_partition", "_gda_key", "_gda_keepalive"):
+                if hasattr(b_.edge_index, attr):
+                    setattr(a_.edge_index, attr, getattr(b_.edge_index, attr))
+        del sb_p, tb_p
+        h2d_dense = sb_d.h2d_nbytes() + tb_d.h2d_nbytes()
+        for i in range(2):
+            one_step(sb_d, tb_d).item()
+        e2e_dense = timed_loop(lambda i: one_step(sb_d, tb_d), max(3, n_side // 2))
+        del sb_d, tb_d
+    else:
+        sb_p = src_h if "_packed_x" in src_h.__dict__ or src_h.x.is_pinned() else src_h.pin_memory()
+        tb_p = tgt_h if "_packed_x" in tgt_h.__dict__ or tgt_h.x.is_pinned() else tgt_h.pin_memory()
+        h2d = sb_p.h2d_nbytes() + tb_p.h2d_nbytes()
+        packed = "_packed_x" in sb_p.__dict__
+        for i in range(3):
+            one_step(sb_p, tb_p).item()
+        e2e_value = timed_loop(lambda i: one_step(sb_p, tb_p), e2e_steps)
+        del sb_p, tb_p
 
     if rank != 0:
         return
@@ -587,11 +587,14 @@ def run_gpu_arm(args, rank, world, local_rank):
                                     "no explicit flush",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "how": e2e_note,
                     "staging": ("pinned host inputs, x row-compressed (lossless; only its non-zeros cross PCIe, dense "
                                 "matrix rebuilt on the GPU)" if packed else "pinned host inputs, dense"),
-                    "dense_staging": {"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_dense},
-                    "prefetch": e2e_prefetch},
+                    "eager_serial": ({"value": e2e_eager, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                      "how": "cuda_graph=False, prefetch=False: copy, then compute (round 1's e2e.value)"}
+                                     if e2e_eager is not None else None),
+                    "dense_staging": ({"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_dense}
+                                      if e2e_dense is not None else None)},
             "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "roofline": roofline,
             "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:

@@ -102,6 +102,13 @@ class Data:
             part = getattr(src, "_gda_partition", None)      # row-partitioned multi-GPU graph tag
             if part is not None:
                 ei._gda_partition = part
+        xd, xsrc = out.__dict__.get("x"), self.__dict__.get("x")
+        if torch.is_tensor(xd) and xd is not xsrc and torch.is_tensor(xsrc) and dev.type == "cuda":
+            # same for the input features: their derived operand forms (split-bf16 pair / bf16 copy, ops.ConstCache)
+            # are keyed by the host tensor, so re-sending it every step refills ONE set of buffers
+            xd._gda_key = getattr(xsrc, "_gda_key", None) or (
+                "src", xsrc.data_ptr(), xsrc._version, tuple(xsrc.shape), str(xsrc.device))
+            xd._gda_keepalive = getattr(xsrc, "_gda_keepalive", xsrc)
         ew, wsrc = out.__dict__.get("edge_weight"), self.__dict__.get("edge_weight")
         if torch.is_tensor(ew) and ew is not wsrc:
             # same for per-edge weights (StruRW): the re-weighted CSR is keyed by the host tensor they came from

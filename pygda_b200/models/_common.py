@@ -11,13 +11,17 @@ from ..utils import logger
 
 
 class TwoDomainLoop:
-    def _build_loaders(self, source_data, target_data):
+    # node-mode fit() on host-resident graphs: the loaders issue the NEXT epoch's host->device copy on a side stream
+    # while the current step runs (data.NeighborLoader); same bytes, same values (tests/test_zz5_gpu_prefetch.py)
+    prefetch = True
+
+    def _build_loaders(self, source_data, target_data, prefetch=None):
         if self.mode == 'node':
             self.num_source_nodes, _ = source_data.x.shape
             self.num_target_nodes, _ = target_data.x.shape
             pin = str(self.device).startswith('cuda')       # host-resident graphs: pinned (packed) staging, once
-            # opt-in (``estimator.prefetch = True``): next epoch's host->device copy overlaps the current step
-            pf = self.device if (pin and getattr(self, 'prefetch', False)) else None
+            want = getattr(self, 'prefetch', False) if prefetch is None else prefetch
+            pf = self.device if (pin and want) else None
             if self.batch_size == 0:
                 self.source_batch_size = source_data.x.shape[0]
                 self.source_loader = NeighborLoader(source_data, self.num_neigh,

@@ -33,8 +33,9 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         self.mode = mode
         self.overlap_streams = True
         self._side = None
-        # opt-in: capture the full-batch node-level step as a CUDA graph (models/graphed.py)
-        self.cuda_graph = False
+        # full-batch node-level fit() replays the loop body from a CUDA graph, with the per-epoch host->device copy
+        # of a host-resident graph double-buffered behind it (models/graphed.py); False: issue every kernel eagerly
+        self.cuda_graph = True
 
     def _side_stream(self):
         if self._side is None:
@@ -118,13 +119,42 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         optimizer.step()
         return loss, source_logits, target_logits, source_data
 
-    def fit(self, source_data, target_data):
-        self._build_loaders(source_data, target_data)
+    def prepare_fit(self, source_data, target_data):
+        """Everything ``fit`` does before its epoch loop (loaders :254-288, model :290, optimiser :292-296); returns
+        ``run_epoch(epoch, last=False) -> (loss tensor, source logits, source labels)`` for the full-batch node-level
+        CUDA-graph path, or None when the eager loop over the loaders applies (graph mode, ``cuda_graph = False``)."""
+        graphed = bool(self.cuda_graph) and self.mode == 'node' and self.epoch > 1 and self.batch_size == 0 \
+            and str(self.device).startswith('cuda')
+        # the graphed step stages the next epoch's copy itself; the loaders' own prefetch is for the eager loop
+        self._build_loaders(source_data, target_data, prefetch=False if graphed else None)
         self.a2gnn = self.init_model(**self.kwargs)
         optimizer = Adam(self.a2gnn.parameters(), lr=self.lr, weight_decay=self.weight_decay)
         self.optimizer = optimizer
-        if self.cuda_graph and self.mode == 'node' and self.epoch > 1:
-            return self._fit_graphed(optimizer)
+        if not graphed:
+            return None
+        # The loop body replayed from a CUDA graph: epoch 0 runs eagerly inside GraphedStep (it warms the caches the
+        # capture must not allocate), epochs 1.. are replays; a host-resident graph is re-sent every epoch, the copy
+        # of epoch e+1 overlapping the replay of epoch e (models/graphed.py).
+        from .graphed import GraphedStep
+        source_batch = next(iter(self.source_loader))
+        target_batch = next(iter(self.target_loader))
+        step = GraphedStep(self, source_batch, target_batch, optimizer, warmup=1,
+                           alpha_fn=lambda i: self.alpha_at(i, self.epoch))
+        self.graphed_step = step
+
+        def run_epoch(epoch, last=False):
+            if epoch == 0:
+                loss, source_logits, _ = step.warmup_results[0]
+            else:
+                loss, source_logits, _ = step(self.alpha_at(epoch, self.epoch), last=last)
+            return loss, source_logits, step.src.y
+        return run_epoch
+
+    def fit(self, source_data, target_data):
+        run_epoch = self.prepare_fit(source_data, target_data)
+        if run_epoch is not None:
+            return self._fit_graphed(run_epoch)
+        optimizer = self.optimizer
 
         def step(epoch, sampled_source_data, sampled_target_data):
             alpha = self.alpha_at(epoch, self.epoch)
@@ -134,28 +164,18 @@ class A2GNN(TwoDomainLoop, BaseGDA):
 
         self._fit_loop(step)
 
-    def _fit_graphed(self, optimizer):
-        """fit() with the loop body replayed from a CUDA graph: epoch 0 runs eagerly (and warms the
-        caches), epochs 1.. are replays.  Logging as in _fit_loop."""
+    def _fit_graphed(self, run_epoch):
+        """The epoch loop of fit() (:300-336) over the graphed step.  Logging as in _fit_loop."""
         import time
         from ..metrics import micro_f1_from_logits
         from ..utils import logger
-        from .graphed import GraphedStep
         start_time = time.time()
-        source_batch = next(iter(self.source_loader))
-        target_batch = next(iter(self.target_loader))
-        step = GraphedStep(self, source_batch, target_batch, optimizer, warmup=1,
-                           alpha_fn=lambda i: self.alpha_at(i, self.epoch))
-        self.graphed_step = step
         for epoch in range(self.epoch):
-            if epoch == 0:
-                loss, source_logits, _ = step.warmup_results[0]
-            else:
-                loss, source_logits, _ = step(self.alpha_at(epoch, self.epoch))
+            loss, source_logits, source_labels = run_epoch(epoch, last=epoch == self.epoch - 1)
             epoch_loss = loss.item()
             micro_f1_score = None
             if self.verbose > 1:
-                micro_f1_score = micro_f1_from_logits(step.src.y, source_logits)
+                micro_f1_score = micro_f1_from_logits(source_labels, source_logits)
             logger(epoch=epoch, loss=epoch_loss, source_train_acc=micro_f1_score,
                    time=time.time() - start_time, verbose=self.verbose, train=True)
 

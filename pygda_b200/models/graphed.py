@@ -22,6 +22,67 @@ from .._lib import load
 from ..utils import mmd as mmd_utils
 
 
+class StagedBatch:
+    """Per-epoch host->device staging of ONE pinned host batch into the FIXED device tensors a captured step reads.
+
+    The reference's loop copies the batch to the device at the top of every step (pygda/models/a2gnn.py:311-312) and
+    only then computes.  Here the copy of epoch e+1 is issued on a copy stream into one of two device staging slots
+    while epoch e's graph runs; at the top of epoch e+1 the slot is consumed on the compute stream: a row-compressed
+    ``x`` is rebuilt densely into the static ``x`` buffer (``gda_unpack_rows_f32``, bit for bit), the other tensors
+    are copied device-to-device, and the cached split-bf16 operand pair of ``x`` is recomputed from it
+    (``ops.ConstCache.refresh``) -- every epoch's data crosses PCIe and is consumed; nothing is re-allocated."""
+
+    def __init__(self, host_batch, device):
+        self.dev = torch.device(device)
+        self.static = host_batch.to(self.dev)            # epoch 0's copy; allocates the static device tensors
+        self.packed = host_batch.__dict__.get("_packed_x")
+        self.fields = {}
+        if self.packed is not None:
+            self.fields.update(_vals=self.packed.vals, _cols=self.packed.cols, _rowptr=self.packed.rowptr)
+        for k, v in host_batch.__dict__.items():
+            if torch.is_tensor(v) and not v.is_cuda and not (k == "x" and self.packed is not None):
+                self.fields[k] = v if v.is_pinned() else v.pin_memory()
+        self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in self.fields.items()}
+                      for _ in range(2)]
+        self.copied, self.consumed = [None, None], [None, None]
+        self.stream = torch.cuda.Stream(self.dev)
+        self.nbytes = sum(v.numel() * v.element_size() for v in self.fields.values())
+
+    def issue(self, slot):
+        """Queue the host->device copy of the whole batch into ``slot`` on the copy stream."""
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])
+            for k, v in self.fields.items():
+                self.slots[slot][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.copied[slot] = ev
+
+    def consume(self, slot):
+        """On the current stream: wait for the slot's copy and move it into the static tensors."""
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(self.copied[slot])
+        s = self.slots[slot]
+        if self.packed is not None:
+            n, f = self.packed.shape
+            x = self.static.x
+            ops.gda.unpack_rows_f32(ops._p(s["_vals"]), ops._p(s["_cols"]), self.packed.col_bytes, ops._p(s["_rowptr"]),
+                                    n, f, ops._p(x), f, ops._stream())
+        for k, v in s.items():
+            if not k.startswith("_"):
+                getattr(self.static, k).copy_(v, non_blocking=True)
+        ops.split_cache.refresh(self.static.x)
+        ops.bf16_cache.refresh(self.static.x)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.consumed[slot] = ev
+
+
+def _on_device(data, dev):
+    return all((not torch.is_tensor(v)) or v.device == dev for v in data.__dict__.values())
+
+
 class GraphedStep:
     def __init__(self, est, source_data, target_data, optimizer, warmup=2, sampling_num=1000, times=5,
                  alpha_fn=None):
@@ -32,7 +93,12 @@ class GraphedStep:
             raise ValueError("GraphedStep captures the full-batch node-level step only")
         dev = torch.device(est.device)
         self.est, self.opt = est, optimizer
-        self.src, self.tgt = source_data.to(dev), target_data.to(dev)
+        # host-resident batches are re-sent every epoch like the reference does (a2gnn.py:311-312), double-buffered
+        self.staged = [StagedBatch(d, dev) if not _on_device(d, dev) else None for d in (source_data, target_data)]
+        self.src = self.staged[0].static if self.staged[0] is not None else source_data
+        self.tgt = self.staged[1].static if self.staged[1] is not None else target_data
+        self.h2d_bytes_per_step = sum(sb.nbytes for sb in self.staged if sb is not None)
+        self._slot = 0
         self.ns, self.nt = self.src.x.shape[0], self.tgt.x.shape[0]
         self.sampling_num, self.times = sampling_num, times
         self.s_idx = torch.zeros(times, sampling_num, dtype=torch.int64, device=dev)
@@ -61,6 +127,9 @@ class GraphedStep:
             self.loss, self.source_logits, self.target_logits = self._body()
         self.launches_per_replay = int(lib.gda_launch_count() - n0)
         self.replays = 0
+        for sb in self.staged:                           # the first replay's inputs start crossing PCIe now
+            if sb is not None:
+                sb.issue(self._slot)
 
     def _body(self):
         est = self.est
@@ -83,9 +152,23 @@ class GraphedStep:
         else:
             ops.gda.fill_f32(ops._p(self.alpha), 1, float(alpha), ops._stream())
 
-    def __call__(self, alpha=0.0, mmd_indices=None):
+    def _restage(self, prefetch_next=True):
+        """Consume this epoch's staged inputs, then start the next epoch's copy (it overlaps the replay)."""
+        n0 = load().gda_launch_count()
+        for sb in self.staged:
+            if sb is not None:
+                sb.consume(self._slot)
+        self.restage_launches = int(load().gda_launch_count() - n0)
+        self._slot ^= 1
+        if prefetch_next:
+            for sb in self.staged:
+                if sb is not None:
+                    sb.issue(self._slot)
+
+    def __call__(self, alpha=0.0, mmd_indices=None, last=False):
         """One training step; returns (loss, source_logits, target_logits) -- static tensors that the
-        next call overwrites."""
+        next call overwrites.  ``last``: no further step follows (do not start another host->device copy)."""
+        self._restage(prefetch_next=not last)
         self._stage(alpha, mmd_indices)
         self.graph.replay()
         self.replays += 1

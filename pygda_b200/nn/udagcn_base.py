@@ -74,7 +74,7 @@ class UDAGCNBase(nn.Module):
 
     def _x(self, data):
         # the input features are constant: their bf16 copy is made once per tensor (ops.bf16_cache)
-        return ops.bf16_cache.get(data.x) if self.bf16 else data.x
+        return ops.bf16_cache.get(data.x) if (self.bf16 and data.x.dtype != torch.bfloat16) else data.x
 
     def _out(self, enc):
         # heads, attention and losses run in fp32: one cast at the encoder boundary (its backward casts back)

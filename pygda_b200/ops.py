@@ -154,30 +154,74 @@ class Split:
         self.ld = (self.cols + 7) // 8 * 8
         self.hi = torch.empty(self.rows, self.ld, dtype=torch.bfloat16, device=x.device)
         self.lo = torch.empty(self.rows, self.ld, dtype=torch.bfloat16, device=x.device)
+        self.fill(x)
+
+    def fill(self, x):
+        """(Re)compute the pair from ``x`` into the existing buffers."""
+        x = _f32c(x)
         gda.split_bf16(_p(x), self.rows, self.cols, x.stride(0), _p(self.hi), _p(self.lo), self.ld, _stream())
 
+    @property
+    def nbytes(self):
+        return 2 * self.hi.numel() * 2
 
-class SplitCache:
-    """Splits of CONSTANT operands (the input features ``data.x``), keyed like the graph
-    cache: a tensor that does not require grad and keeps its identity/version is split once
-    and re-used by every forward and backward pass."""
 
-    def __init__(self, capacity=8):
-        self.capacity, self._d = capacity, {}
+class ConstCache:
+    """Derived forms (split-bf16 pair, bf16 copy) of CONSTANT operands -- the input features ``data.x``.
+
+    Key: the HOST tensor a device copy was made from when ``Data.to`` attached one (``_gda_key``, as for
+    ``edge_index``): the fit loops re-send the same host graph every step (pygda/models/a2gnn.py:311-312), each time
+    to a fresh device tensor -- such a copy maps to ONE entry whose buffers are refilled in place from the new copy
+    (the step's data is consumed, nothing is re-allocated, nothing stale is kept alive).  Tensors without a host key
+    are keyed by (data_ptr, version) and kept alive so that the pointer cannot be recycled.
+    Only grad-mode forward passes insert: under ``torch.no_grad()`` (predict) every activation has
+    ``requires_grad == False`` and must not evict the real constants -- there the cache is lookup-only.
+    Bounded by entries and by bytes."""
+
+    def __init__(self, make, fill, nbytes, capacity=8, max_bytes=48 << 30):
+        self._make, self._fill, self._nbytes = make, fill, nbytes
+        self.capacity, self.max_bytes, self._d = capacity, max_bytes, {}
+
+    @staticmethod
+    def _key(x):
+        k = getattr(x, "_gda_key", None)
+        if k is not None:
+            return ("host", k, tuple(x.shape), str(x.device))
+        return ("dev", x.data_ptr(), x._version, tuple(x.shape), str(x.device))
 
     def get(self, x):
-        key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
+        key = self._key(x)
         hit = self._d.get(key)
         if hit is not None:
+            if hit[2] != x.data_ptr():                   # a new device copy of the same host tensor: refill in place
+                self._fill(hit[0], x)
+                hit[2] = x.data_ptr()
             return hit[0]
-        sp = Split(x)
-        if len(self._d) >= self.capacity:
+        val = self._make(x)
+        if not torch.is_grad_enabled():
+            return val
+        while self._d and (len(self._d) >= self.capacity or
+                           sum(self._nbytes(v[0]) for v in self._d.values()) + self._nbytes(val) > self.max_bytes):
             self._d.pop(next(iter(self._d)))
-        self._d[key] = (sp, x)          # keeps x alive so the data_ptr cannot be recycled
-        return sp
+        # host-keyed entries keep the HOST tensor alive (its address is the key), not a stale device copy
+        keep = getattr(x, "_gda_keepalive", x) if key[0] == "host" else x
+        self._d[key] = [val, keep, x.data_ptr()]
+        return val
+
+    def refresh(self, x):
+        """``x`` was re-written in place (a staged copy landed in its buffer): recompute the cached form."""
+        hit = self._d.get(self._key(x))
+        if hit is not None:
+            self._fill(hit[0], x)
+            hit[2] = x.data_ptr()
+        return hit is not None
 
     def clear(self):
         self._d.clear()
+
+
+def SplitCache(capacity=8):
+    return ConstCache(Split, lambda sp, x: sp.fill(x), lambda sp: sp.nbytes, capacity)
 
 
 split_cache = SplitCache()
@@ -614,24 +658,15 @@ class CastFn(torch.autograd.Function):
         return (to_f32(g) if ctx.to_half else to_bf16(g)), None
 
 
-class Bf16Cache:
+def _bf16_fill(y, x):
+    x = _f32c(x)
+    gda.cast_f32_bf16(_p(x), _p(y), x.numel(), _stream())
+
+
+def Bf16Cache(capacity=8):
     """bf16 copies of CONSTANT fp32 tensors (the input features), keyed like SplitCache."""
-
-    def __init__(self, capacity=8):
-        self.capacity, self._d = capacity, {}
-
-    def get(self, x):
-        if x.dtype == torch.bfloat16:
-            return x
-        key = (x.data_ptr(), x._version, tuple(x.shape), str(x.device))
-        hit = self._d.get(key)
-        if hit is not None:
-            return hit[0]
-        y = to_bf16(x)
-        if len(self._d) >= self.capacity:
-            self._d.pop(next(iter(self._d)))
-        self._d[key] = (y, x)
-        return y
+    return ConstCache(to_bf16, _bf16_fill,
+                      lambda y: y.numel() * 2, capacity)
 
 
 bf16_cache = Bf16Cache()
