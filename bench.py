@@ -444,7 +444,18 @@ def run_gpu_arm(args, rank, world, local_rank):
         nnz = tg.nnz
     n_nodes, H = CFG["nodes"], CFG["hid"]
     b_alg = 4 * (n_nodes + 1) + 8 * nnz + 2 * 4 * n_nodes * H
-    times = [a.elapsed_time(b) for (a, b, meta) in recs if meta == (n_nodes, H, "float32")]
+    def launches_of(nb_):
+        by_kind = {}
+        for (a, b, meta) in recs:
+            if meta[:4] == (n_nodes, H, "float32", nb_):
+                by_kind.setdefault(meta[4], []).append(a.elapsed_time(b))
+        if not by_kind:
+            return None, []
+        kind = max(by_kind, key=lambda k_: len(by_kind[k_]))        # the kernel that carries the step
+        return kind, by_kind[kind]
+
+    n_prof = max(min(args.steps, 5), 1)
+    kind1, times = launches_of(1)
     spmm_ms = statistics.mean(times) if times else float("nan")
     peaks = {}
     try:
@@ -452,36 +463,48 @@ def run_gpu_arm(args, rank, world, local_rank):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = b_alg / (spmm_ms * 1e-3) / 1e9
     traffic = None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json")))
     except Exception:
         pass
-    per_step_spmm = len(times) / max(min(args.steps, 5), 1)
-    # layer >= 2 of the two bottleneck evaluations per domain runs as ONE launch over the stacked pair
-    # (gda_spmm_nb_f32, nb = 2): same index bytes, twice the feature bytes
-    times2 = [a.elapsed_time(b) for (a, b, meta) in recs if meta == (n_nodes, H, "float32", 2)]
+    # The factored (unit-weight) kernel reads no edge weights: 4 bytes per non-zero fewer, + the dinv vector.
+    def alg_bytes(kind, nb_):
+        idx = 4 * (n_nodes + 1) + (4 * nnz + 4 * n_nodes if kind == "unit-weight" else 8 * nnz)
+        return idx + nb_ * 2 * 4 * n_nodes * H
+    kname = {"unit-weight": "k_spmm_unw<4,16,...> (factored D S D form: no per-edge weights)",
+             "weighted": "k_spmm_tasks<float,4,4,...>"}
+    b_alg = alg_bytes(kind1, 1)
+    achieved = b_alg / (spmm_ms * 1e-3) / 1e9
+    per_step_spmm = len(times) / n_prof
+    # layer >= 2 of the two bottleneck evaluations per domain runs as ONE launch over the stacked pair (nb = 2):
+    # same index bytes, twice the feature bytes
+    kind2, times2 = launches_of(2)
     batched = None
     if times2:
         ms2 = statistics.mean(times2)
-        b_alg2 = 4 * (n_nodes + 1) + 8 * nnz + 2 * 2 * 4 * n_nodes * H
-        batched = {"kernel": "k_spmm_tasks<float,4,4,...,NB=2> (two stacked [N,128] matrices per launch)",
+        b_alg2 = alg_bytes(kind2, 2)
+        batched = {"kernel": "%s, NB=2 (two stacked [N,128] matrices per launch)" % kname.get(kind2, kind2),
                    "alg_bytes_per_launch": b_alg2, "us_per_launch": ms2 * 1e3,
                    "achieved": b_alg2 / (ms2 * 1e-3) / 1e9, "frac": b_alg2 / (ms2 * 1e-3) / 1e9 / peak,
-                   "launches_per_step": len(times2) / max(min(args.steps, 5), 1)}
-    roofline = {"bound": "hbm", "kernel": "k_spmm_tasks<float,4,4,...> (A_hat x, H=128, N=100k, nnz=%d)" % nnz,
+                   "launches_per_step": len(times2) / n_prof}
+    gather_bytes = 4 * (n_nodes + 1) + (4 if kind1 == "unit-weight" else 8) * nnz + 4 * nnz * H + 4 * n_nodes * H
+    roofline = {"bound": "hbm", "kernel": "%s (A_hat x, H=128, N=100k, nnz=%d)" % (kname.get(kind1, kind1), nnz),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic["bytes_per_launch"] if traffic else None,
-                "traffic_source": traffic["source"] if traffic else None,
-                "gather_bytes_per_launch": 4 * (n_nodes + 1) + 8 * nnz + 4 * nnz * H + 4 * n_nodes * H,
+                "traffic": ((traffic or {}).get(kind1) or {}).get("bytes_per_launch"),
+                "traffic_source": ((traffic or {}).get(kind1) or {}).get("source"),
+                "gather_bytes_per_launch": gather_bytes, "gathered_GBps": gather_bytes / (spmm_ms * 1e-3) / 1e9,
+                "l2_gather_ceiling_GBps": 15000.0,
+                "l2_gather_ceiling_source": "profiles/probes/gather_probe6 (regular 12-gather rows, 64 warps/SM: 14.9-15.3 "
+                                            "TB/s of gathered rows on this GPU; the feature matrix is L2-resident, so the "
+                                            "kernel is bounded by the L2 gather path, not by HBM)",
                 "alg_bytes_per_launch": b_alg, "us_per_launch": spmm_ms * 1e3,
                 "launches_per_step": per_step_spmm,
                 "share_of_step": (per_step_spmm * spmm_ms + (batched["launches_per_step"] * batched["us_per_launch"] * 1e-3
                                                               if batched else 0.0)) / (ms_total / args.steps),
                 "batched": batched,
-                "how": "CUDA events around each gda_spmm_f32 launch in an instrumented repeat of the timed steps"}
+                "how": "CUDA events around each aggregation launch in an instrumented repeat of the timed steps"}
 
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
     if args.skip_e2e:
@@ -529,8 +552,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         if run_h is not None:
             gs = model.graphed_step
             h2d = gs.h2d_bytes_per_step                 # counted from the tensors StagedBatch copies every epoch
-            e2e_note = ("fit() default: CUDA-graph replay, next epoch's host->device copy double-buffered behind it "
-                        "(+%d staging kernels per step)" % (gs.restage_launches if hasattr(gs, "restage_launches") else 0))
+            e2e_note = ("fit() default: CUDA-graph replay (%d kernels), next epoch's host->device copy "
+                        "double-buffered behind it, consumed by unpack + operand-split kernels before each replay"
+                        % gs.launches_per_replay)
             ep = [1]
 
             def graphed_h(i):

@@ -120,6 +120,20 @@ int gda_spmm_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* X,
                     int64_t x_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, int H,
                     const float* bias, int epi_flags, float dropout_p, uint64_t seed,
                     const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+/* The factored form for UNIT-weight symmetric normalisation (gcn_norm with edge_weight=None,
+ * pygda/nn/prop_gcn_conv.py:67-81: w_e = dinv[src] * 1 * dinv[dst]):  A_hat = D (A + I) D, so
+ * A_hat^k x = D S (D^2 S)^(k-1) D x with S = A + I.  gda_row_scale_f32 computes z = D x once,
+ * gda_spmm_unw_nb_f32 one step out[r] = scale[r] * sum_{c in row r} z[c] (scale = dinv^2, or dinv when
+ * `last`), with the epilogue of gda_spmm_f32 -- no per-edge weight is read or multiplied.  Values equal
+ * the weighted kernel's up to fp32 rounding.  gda_graph_unit_weights: 1 when the graph / width / nb
+ * qualify (H = 128 fp32, nb 1 or 2).  gda_spmm_k_nb_f32 takes this route by itself for k >= 3. */
+int gda_graph_unit_weights(const gda_graph_t* g, int transpose, int H, int nb);
+int gda_row_scale_f32(const gda_graph_t* g, int nb, const float* X, int64_t ldx, int64_t x_batch_stride, float* Z,
+                      int64_t ldz, int64_t z_batch_stride, int H, gda_stream_t stream);
+int gda_spmm_unw_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride,
+                        float* Y, int64_t ldy, int64_t y_batch_stride, int H, int last, const float* bias, int epi_flags,
+                        float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                        int64_t workspace_bytes, gda_stream_t stream);
 int gda_spmm_k_nb_f32(const gda_graph_t* g, int transpose, int k, int nb, const float* X, int64_t ldx,
                       int64_t x_batch_stride, float* Y, int64_t ldy, int64_t y_batch_stride, float* T0, float* T1,
                       int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,

@@ -34,6 +34,9 @@ SIGNATURES = {
     "gda_spmm_f32": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_k_f32": (i32, [vp, i32, i32, vp, i64, vp, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_nb_f32": (i32, [vp, i32, i32, vp, i64, i64, vp, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_graph_unit_weights": (i32, [vp, i32, i32, i32]),
+    "gda_row_scale_f32": (i32, [vp, i32, vp, i64, i64, vp, i64, i64, i32, vp]),
+    "gda_spmm_unw_nb_f32": (i32, [vp, i32, i32, vp, i64, i64, vp, i64, i64, i32, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_k_nb_f32": (i32, [vp, i32, i32, i32, vp, i64, i64, vp, i64, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp,
                                 i64, vp]),
     "gda_spmm_peer_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
@@ -104,7 +107,7 @@ SIGNATURES = {
 }
 
 # calls whose int return is a status code to check
-_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is i32 and k not in ("gda_version", "gda_sm_arch", "gda_gemm_bf16x3_supported")}
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is i32 and k not in ("gda_version", "gda_sm_arch", "gda_gemm_bf16x3_supported", "gda_graph_unit_weights")}
 
 
 def load():

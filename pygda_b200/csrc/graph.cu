@@ -397,6 +397,7 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
     GDA_CUDA(cudaMemcpyAsync(g->csr_t.vals, raw_s, sizeof(float) * nnz, cudaMemcpyDeviceToDevice, st));
   }
 
+  g->unit_weights = norm && w == nullptr && !(flags & GDA_IMPROVED);
   g->csr.may_have_empty_rows = g->csr_t.may_have_empty_rows = !loops;   // a self loop in every row
   if (!loops && N > 0) {
     // graphs given with their loops already in place (TDSS's smoothing graph, tdss.py:376-385) have no empty

@@ -40,6 +40,9 @@ struct gda_graph {
   int32_t* coo_dst = nullptr;
   float*   coo_w = nullptr;
   float*   dinv = nullptr;     // [N] deg^-1/2
+  // every raw edge weight is 1 and the normalisation is symmetric: vals[e] == dinv[src] * dinv[dst], so the
+  // aggregation factors as D (A + I) D and chains can run on the weight-free kernel (spmm.cu: k_spmm_unw)
+  bool     unit_weights = false;
   gda::Csr csr;                // rows = targets: Y = A_hat X
   gda::Csr csr_t;              // rows = sources: Y = A_hat^T X
   // row-block partition of a larger graph (peer path): colidx = owner << 28 | local row

@@ -774,6 +774,151 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Factored work-list kernel for UNIT-weight symmetric normalisation -- every GCN-normalised graph built from a plain
+// edge_index (gcn_norm with edge_weight=None, prop_gcn_conv.py:67-81): w_e = dinv[src] * 1 * dinv[dst], so
+//     A_hat = D S D,   S = A + I (0/1 entries, multi-edges repeated),  D = diag(dinv)
+// and a chain  A_hat^k x = D S (D^2 S)^(k-1) D x :  one row scaling of the input, then k steps of
+//     out[r] = scale[r] * sum_{c in row r} z[c],    scale = dinv^2 (intermediate steps) or dinv (last step).
+// What this removes from the inner loop (profiles/probes/gather_probe6, B200): the per-edge weight -- its 4 bytes,
+// its shuffle / load, the FFMA dependence on it (probe: +10 us of 51 at 40 warps/SM) -- and the lane-coalesced
+// (colidx, weight) staging with two shuffles per non-zero (+5 us); indices are read with warp-uniform loads (one L1
+// transaction, broadcast), the kernel keeps 4 + 16 + 4 live registers of payload and fits 16 CTAs (64 warps) per SM,
+// the occupancy at which the regular gather probe peaks (41 us vs 51 us at 40 warps/SM).
+// Summation order inside a row is unchanged (CSR = COO order, segments reduced in segment order); values differ from
+// the weighted kernel by fp32 rounding only (scale applied once per row instead of once per edge).
+template <int K, int NB>
+__device__ __forceinline__ void gather_sum(float (&acc)[NB][4], const int* __restrict__ ci, const char* __restrict__ Xc,
+                                           unsigned ldxb, uint64_t xbsb) {
+  unsigned cj[K];
+#pragma unroll
+  for (int u = 0; u < K; ++u) cj[u] = static_cast<unsigned>(__ldg(ci + u));
+  uint4 xv[K][NB];
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    const char* src = Xc + static_cast<uint64_t>(cj[u]) * ldxb;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) xv[u][b] = gather16(src + b * xbsb);
+  }
+#pragma unroll
+  for (int u = 0; u < K; ++u)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      acc[b][0] += __uint_as_float(xv[u][b].x); acc[b][1] += __uint_as_float(xv[u][b].y);
+      acc[b][2] += __uint_as_float(xv[u][b].z); acc[b][3] += __uint_as_float(xv[u][b].w);
+    }
+}
+
+template <int U, int CTAS, bool EPI, int NB>
+__global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
+k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
+           const float* __restrict__ dinv, int last, const int* __restrict__ long_rows,
+           const int* __restrict__ long_seg_ptr, const int* __restrict__ seg_long, int* __restrict__ counters,
+           const float* __restrict__ X, unsigned ldxb, float* __restrict__ Y, unsigned ldyb, int H,
+           Epilogue epi, float* __restrict__ partial, uint64_t xbsb, uint64_t ybsb, int nrows) {
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= num_tasks) return;
+  uint2 cur = __ldg(tasks + i);
+  while (true) {
+    const int inext = i + nwarps;
+    const bool has_next = inext < num_tasks;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (has_next) nxt = __ldg(tasks + inext);
+
+    const int* __restrict__ ci = colidx + cur.x;
+    int left = static_cast<int>((cur.y >> 25) & 63u) + 1;
+    float acc[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[b][v] = 0.f;
+    for (; left >= U; left -= U, ci += U) gather_sum<U, NB>(acc, ci, Xc, ldxb, xbsb);
+    switch (left) {                                      // warp-uniform: exact tails, no padding gathers
+      case 1: gather_sum<1, NB>(acc, ci, Xc, ldxb, xbsb); break;
+      case 2: gather_sum<2, NB>(acc, ci, Xc, ldxb, xbsb); break;
+      case 3: gather_sum<3, NB>(acc, ci, Xc, ldxb, xbsb); break;
+      default: break;
+    }
+
+    if (!(cur.y & 0x80000000u)) {
+      const unsigned row = cur.y & 0x01FFFFFFu;
+      const float d = __ldg(dinv + row);
+      const float sc = last ? d : d * d;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[b][v] *= sc;
+        if (EPI) apply_epilogue<4>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
+        VecIO<float, 4>::store(reinterpret_cast<float*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+      }
+    } else {                                             // segment of a long row: ordered reduction by the last arrival
+      const int sgid = static_cast<int>(cur.y & 0x01FFFFFFu);
+      const int L = __ldg(seg_long + sgid);
+      float* dst = partial + static_cast<int64_t>(sgid) * (NB * H) + c0;
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) __stcg(dst + b * H + v, acc[b][v]);
+      __threadfence();
+      __syncwarp();
+      int old = 0;
+      const int first = __ldg(long_seg_ptr + L), nseg = __ldg(long_seg_ptr + L + 1) - first;
+      if (lane == 0) old = atomicAdd(counters + L, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == nseg - 1) {
+        __threadfence();
+        const int row = __ldg(long_rows + L);
+        const float d = __ldg(dinv + row);
+        const float sc = last ? d : d * d;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[b][v] = 0.f;
+          for (int sgi = 0; sgi < nseg; ++sgi) {
+            const float* srcp = partial + static_cast<int64_t>(first + sgi) * (NB * H) + b * H + c0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[b][v] += __ldcg(srcp + v);
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[b][v] *= sc;
+          if (EPI) apply_epilogue<4>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
+          VecIO<float, 4>::store(reinterpret_cast<float*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+        }
+        if (lane == 0) counters[L] = 0;
+      }
+    }
+    if (!has_next) break;
+    cur = nxt;
+    i = inext;
+  }
+}
+
+// z[b][r, :] = dinv[r] * x[b][r, :]   (the D x of the factored chain; one float4 per thread)
+__global__ void __launch_bounds__(256)
+k_row_scale(const float* __restrict__ X, int64_t ldx, int64_t xbs, float* __restrict__ Z, int64_t ldz, int64_t zbs,
+            const float* __restrict__ dinv, int64_t N, int H4, int nb) {
+  const int64_t total = static_cast<int64_t>(nb) * N * H4;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(t % H4);
+    const int64_t rr = t / H4;
+    const int64_t r = rr % N, b = rr / N;
+    const float d = __ldg(dinv + r);
+    float4 v = __ldg(reinterpret_cast<const float4*>(X + b * xbs + r * ldx) + c);
+    v.x *= d; v.y *= d; v.z *= d; v.w *= d;
+    reinterpret_cast<float4*>(Z + b * zbs + r * ldz)[c] = v;
+  }
+}
+
+inline int unw_mode() {         // experiments: GDA_SPMM_UNW=0 disables the factored chain, =12 / =16 pick CTAs per SM
+  static const int m = [] { const char* e = std::getenv("GDA_SPMM_UNW"); return e ? std::atoi(e) : 16; }();
+  return m;
+}
+
 inline int tasks_mode() {       // experiments: GDA_SPMM_TASKS=0 keeps k_spmm_rows, =8 the 8-deep variant, =12 12 CTAs/SM
   static const int m = [] { const char* e = std::getenv("GDA_SPMM_TASKS"); return e ? std::atoi(e) : 4; }();
   return m;
@@ -961,10 +1106,89 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   return GDA_OK;
 }
 
+// true when the factored (weight-free) kernel can take a step over this graph at this width
+bool unw_path(const gda_graph* g, const Csr& c, int H, int64_t ldx, int64_t ldy, const float* X, const float* Y, int nb,
+              int64_t xbs, int64_t ybs) {
+  bool wide_ok = (H == 128) && (ldx % 4 == 0) && (ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
+                 (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
+  if (nb > 1) wide_ok = wide_ok && (xbs % 4 == 0) && (ybs % 4 == 0);
+  return g->unit_weights && !g->peer_packed && g->dinv != nullptr && (nb == 1 || nb == 2) && unw_mode() != 0 &&
+         tasks_path<float, 4>(c, H, wide_ok);
+}
+
+int spmm_unw(const gda_graph* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t zbs, float* Y, int64_t ldy,
+             int64_t ybs, int H, int last, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+             const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const Csr& c = transpose ? g->csr_t : g->csr;
+  GDA_REQUIRE(Z && Y && Z != Y, "gda_spmm_unw: bad feature pointers");
+  GDA_REQUIRE(g->N * ldz < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32), "gda_spmm_unw: N * ld must be below 2^32");
+  GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm_unw: dropout_p outside [0,1)");
+  GDA_REQUIRE(unw_path(g, c, H, ldz, ldy, Z, Y, nb, zbs, ybs), "gda_spmm_unw: graph / shape not eligible (gda_graph_unit_weights)");
+  const int64_t need = static_cast<int64_t>(c.num_segs) * H * nb * sizeof(float);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need))
+    return fail(GDA_E_WORKSPACE, "gda_spmm_unw: workspace smaller than gda_spmm_workspace_bytes(H * nb)");
+  Epilogue epi;
+  epi.bias = bias; epi.flags = epi_flags; epi.thresh = dropout_threshold(dropout_p);
+  epi.scale = 1.0f / (1.0f - dropout_p); epi.seed = seed; epi.seed_offset = seed_offset;
+  const bool has_epi = bias != nullptr || epi_flags != 0;
+  float* partial = static_cast<float*>(workspace);
+  const unsigned ldzb = static_cast<unsigned>(ldz * sizeof(float)), ldyb = static_cast<unsigned>(ldy * sizeof(float));
+  const uint64_t zb = static_cast<uint64_t>(zbs) * sizeof(float), yb = static_cast<uint64_t>(ybs) * sizeof(float);
+  const int per_sm = nb == 2 ? 10 : (unw_mode() == 12 ? 12 : 16);
+  int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
+  if (tb > static_cast<int64_t>(kNumSMs) * per_sm) tb = static_cast<int64_t>(kNumSMs) * per_sm;
+#define GDA_UNW_LAUNCH(CC, E, B)                                                                              \
+  k_spmm_unw<4, CC, E, B><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(                              \
+      c.tasks, c.num_tasks, c.colidx, g->dinv, last, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, Z, ldzb, Y, \
+      ldyb, H, epi, partial, zb, yb, static_cast<int>(g->N))
+  if (nb == 2) { if (has_epi) GDA_UNW_LAUNCH(10, true, 2); else GDA_UNW_LAUNCH(10, false, 2); }
+  else if (per_sm == 12) { if (has_epi) GDA_UNW_LAUNCH(12, true, 1); else GDA_UNW_LAUNCH(12, false, 1); }
+  else { if (has_epi) GDA_UNW_LAUNCH(16, true, 1); else GDA_UNW_LAUNCH(16, false, 1); }
+#undef GDA_UNW_LAUNCH
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
 }  // namespace
 }  // namespace gda
 
 extern "C" {
+
+int gda_graph_unit_weights(const gda_graph_t* g, int transpose, int H, int nb) {
+  if (!g || H != 128) return 0;
+  const gda::Csr& c = transpose ? g->csr_t : g->csr;
+  return gda::unw_path(g, c, H, H, H, nullptr, nullptr, nb, static_cast<int64_t>(g->N) * H,
+                       static_cast<int64_t>(g->N) * H) ? 1 : 0;
+}
+
+int gda_row_scale_f32(const gda_graph_t* g, int nb, const float* X, int64_t ldx, int64_t x_batch_stride, float* Z,
+                      int64_t ldz, int64_t z_batch_stride, int H, gda_stream_t stream) {
+  GDA_REQUIRE(g && g->dinv, "gda_row_scale_f32: graph without a normalisation vector");
+  GDA_REQUIRE(nb >= 1 && H > 0 && H % 4 == 0 && ldx % 4 == 0 && ldz % 4 == 0 && x_batch_stride % 4 == 0 &&
+                  z_batch_stride % 4 == 0,
+              "gda_row_scale_f32: H, leading dimensions and batch strides must be multiples of 4");
+  GDA_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(Z) % 16 == 0,
+              "gda_row_scale_f32: pointers must be 16-byte aligned");
+  if (g->N == 0) return GDA_OK;
+  GDA_REQUIRE(X && Z, "gda_row_scale_f32: NULL pointer");
+  const int64_t total = static_cast<int64_t>(nb) * g->N * (H / 4);
+  int64_t blocks = gda::ceil_div(total, 256);
+  if (blocks > gda::kNumSMs * 16) blocks = gda::kNumSMs * 16;
+  gda::k_row_scale<<<static_cast<unsigned>(blocks), 256, 0, gda::as_stream(stream)>>>(
+      X, ldx, x_batch_stride, Z, ldz, z_batch_stride, g->dinv, g->N, H / 4, nb);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_spmm_unw_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride,
+                        float* Y, int64_t ldy, int64_t y_batch_stride, int H, int last, const float* bias, int epi_flags,
+                        float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                        int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(g != nullptr, "gda_spmm_unw: graph is NULL");
+  if (g->N == 0) return GDA_OK;
+  return gda::spmm_unw(g, transpose, nb, Z, ldz, z_batch_stride, Y, ldy, y_batch_stride, H, last, bias, epi_flags,
+                       dropout_p, seed, seed_offset, workspace, workspace_bytes, gda::as_stream(stream));
+}
 
 int64_t gda_spmm_workspace_bytes(const gda_graph_t* g, int transpose, int H) {
   if (!g || H <= 0) return 0;
@@ -1023,6 +1247,28 @@ int gda_spmm_k_nb_f32(const gda_graph_t* g, int transpose, int k, int nb, const 
   GDA_REQUIRE(k >= 1, "gda_spmm_k: k must be >= 1");
   GDA_REQUIRE(k < 2 || T0, "gda_spmm_k: T0 scratch needed for k >= 2");
   GDA_REQUIRE(k < 3 || T1, "gda_spmm_k: T1 scratch needed for k >= 3");
+  {
+    // unit-weight graphs, k >= 3: D S (D^2 S)^(k-1) D x on the weight-free kernel (one row scaling + k lean steps)
+    const gda::Csr& c = transpose ? g->csr_t : g->csr;
+    const int64_t nh = g->N * static_cast<int64_t>(H);
+    if (k >= 3 && g->N > 0 && gda::unw_path(g, c, H, H, ldy, T0, Y, nb, nh, y_batch_stride) &&
+        reinterpret_cast<uintptr_t>(T1) % 16 == 0 && ldx % 4 == 0 && x_batch_stride % 4 == 0 &&
+        reinterpret_cast<uintptr_t>(X) % 16 == 0) {
+      int rc = gda_row_scale_f32(g, nb, X, ldx, x_batch_stride, T0, H, nh, H, stream);
+      if (rc) return rc;
+      const float* zsrc = T0;
+      for (int i = 0; i < k; ++i) {
+        const bool last = i == k - 1;
+        float* dst = last ? Y : ((i & 1) ? T0 : T1);
+        rc = gda_spmm_unw_nb_f32(g, transpose, nb, zsrc, H, nh, dst, last ? ldy : H, last ? y_batch_stride : nh, H,
+                                 last ? 1 : 0, last ? bias : nullptr, last ? epi_flags : 0, last ? dropout_p : 0.f, seed,
+                                 seed_offset, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        zsrc = dst;
+      }
+      return GDA_OK;
+    }
+  }
   const float* src = X;
   int64_t ld_src = ldx, bs_src = x_batch_stride;
   for (int i = 0; i < k; ++i) {

@@ -202,6 +202,8 @@ class NeighborLoader:
                 "pygda_b200 runs node-level models full-batch (batch_size=0); "
                 "neighbour-sampled mini-batches are not part of the accelerated path")
         self.data = data
+        if torch.is_tensor(data.x) and data.x.is_cuda:
+            data.x._gda_const = True            # resident input features: operand forms are cached (ops.ConstCache)
         ei = data.edge_index
         order = torch.argsort(ei[1], stable=True)
         extra = {k: v for k, v in data.__dict__.items()

@@ -239,6 +239,8 @@ def attach_partition(data, group):
     if (lo, hi) != (data.row_lo, data.row_hi):
         raise ValueError("data block does not match this rank's row range")
     data.edge_index._gda_partition = _PartitionTag(group, data.num_nodes_global)
+    if torch.is_tensor(data.x) and data.x.is_cuda:
+        data.x._gda_const = True                # resident block of input features (ops.ConstCache)
     return data
 
 
@@ -250,6 +252,7 @@ def partition_data(data, group):
     ei = data.edge_index.to(group.device)
     ei._gda_partition = _PartitionTag(group, n)
     out = Data(x=data.x[lo:hi].to(group.device), edge_index=ei, y=data.y[lo:hi].to(group.device))
+    out.x._gda_const = True
     out.num_nodes_global, out.row_lo, out.row_hi = n, lo, hi
     return out
 

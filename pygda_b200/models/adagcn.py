@@ -6,21 +6,22 @@ kept and back-propagated into the encoder although only the critic's optimiser s
 (:169-183) -- the encoder gradients produced there are cleared by ``optimizer.zero_grad()``
 (:302) before anyone reads them.  Here the encoder forwards of the critic loop run without a
 tape (same values, same critic updates, 10 encoder backward passes less); the final encoder
-forward + backward is unchanged.  The critic (Linear-ReLU-Dropout-Linear-Sigmoid on [<=3B, hid]
-rows in graph mode) and its WGAN-GP double backward stay in torch autograd by default: they need
-second derivatives and are negligible next to the encoder there.
+forward + backward is unchanged.
 
-``analytic_critic = True`` (opt-in; node mode, where the critic sees all [3N, hid] rows ten times per
-step): the only [rows, hid]-sized product -- the critic's first Linear -- runs on libgda
-(``ops.linear``), and the gradient penalty is evaluated in CLOSED FORM instead of by double backward.
-For D(x) = sigmoid(w2 . (relu(W1 x + b1) * m) + b2) with dropout mask m,
+The critic (Linear-ReLU-Dropout-Linear-Sigmoid on [3N, hid] rows in node mode, [<= 3B, hid] in graph mode) runs on
+libgda by default (``analytic_critic = True``): both of its Linear layers through ``ops.linear``, its Adam through
+``pygda_b200.optim.Adam``, and the WGAN-GP gradient penalty (:387-454) in CLOSED FORM instead of by
+``autograd.grad(create_graph=True)``.  For D(x) = sigmoid(w2 . (relu(W1 x + b1) * m) + b2) with dropout mask m,
 
     dD/dx = D (1 - D) * (u W1),   u = w2 * 1[W1 x + b1 > 0] * m          (a [rows, adv_dim] matrix)
     |dD/dx|^2 = (D (1 - D))^2 * rowsum((u W1 W1^T) * u)
 
 so no [rows, hid] gradient tensor is ever formed and first-order autograd over [rows, adv_dim]
 arrays yields the same parameter gradients (relu' and the mask are piecewise constant, exactly as in
-torch's double backward).  Checked against the double-backward form (tests/test_zz3_gpu_critic.py)."""
+torch's double backward); the two dense products W1 W1^T and u (W1 W1^T) go through ``ops.matmul``.  What is left to
+torch are elementwise expressions over [rows, adv_dim] / [rows] arrays.  ``analytic_critic = False`` keeps the
+reference's literal form (``torch.nn`` critic, double backward) for comparison (tests/test_zz3_gpu_critic.py: same
+values and gradients as torch's double backward).  Checked against the double-backward form (tests/test_zz3_gpu_critic.py)."""
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -44,7 +45,7 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         self.gp_weight = gp_weight
         self.domain_weight = domain_weight
         self.mode = mode
-        self.analytic_critic = False      # opt-in, see the module docstring
+        self.analytic_critic = True       # closed-form penalty, critic on libgda; see the module docstring
 
     def init_model(self, **kwargs):
         return AdaGCNBase(in_dim=self.in_dim, hid_dim=self.hid_dim, num_classes=self.num_classes,
@@ -55,8 +56,7 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         """The critic and its optimiser, created inside ``fit`` by the reference (:264-276)."""
         self.discriminator = nn.Sequential(nn.Linear(self.hid_dim, self.adv_dim), nn.ReLU(), nn.Dropout(0.1),
                                            nn.Linear(self.adv_dim, 1), nn.Sigmoid()).to(self.device)
-        self.c_optimizer = torch.optim.Adam(self.discriminator.parameters(), lr=self.lr,
-                                            weight_decay=self.weight_decay)
+        self.c_optimizer = Adam(self.discriminator.parameters(), lr=self.lr, weight_decay=self.weight_decay)
 
     # ---- critic evaluation -------------------------------------------------------------------------------
     def _critic_hidden(self, x):
@@ -74,15 +74,16 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         if not self.analytic_critic:
             return self.discriminator(x)
         _, _, h = self._critic_hidden(x)
-        return torch.sigmoid(self.discriminator[3](h))
+        lin2 = self.discriminator[3]
+        return torch.sigmoid(ops.linear(h, lin2.weight, lin2.bias))
 
     def _gradient_penalty_closed_form(self, inputs):
         lin1, lin2 = self.discriminator[0], self.discriminator[3]
         _, pos, h = self._critic_hidden(inputs.detach())
-        score = torch.sigmoid(lin2(h)).reshape(-1)                       # D(x)                      [rows]
+        score = torch.sigmoid(ops.linear(h, lin2.weight, lin2.bias)).reshape(-1)   # D(x)            [rows]
         u = pos * lin2.weight.reshape(1, -1)                               # w2 * relu' * dropout      [rows, adv]
-        gram = lin1.weight @ lin1.weight.t()                               # W1 W1^T                   [adv, adv]
-        q = ((u @ gram) * u).sum(dim=1)                                    # |u W1|^2                  [rows]
+        gram = ops.matmul(lin1.weight, lin1.weight, trans_b=True)          # W1 W1^T                   [adv, adv]
+        q = (ops.matmul(u, gram) * u).sum(dim=1)                           # |u W1|^2                  [rows]
         live = q > 0                                                       # norm(0) has gradient 0 in torch
         root = torch.where(live, q, torch.ones_like(q)).sqrt() * live.to(q.dtype)
         gradient_norm = (score * (1 - score)).abs() * root
@@ -113,7 +114,10 @@ class AdaGCN(TwoDomainLoop, BaseGDA):
         return loss, source_logits, target_logits
 
     def _rand(self, n):
-        return torch.rand((n, 1)).to(self.device)         # CPU generator, like the reference (:420,:429,:434)
+        # CPU generator, like the reference (:420,:429,:434); through pinned memory so that the copy does not stall
+        # the host behind everything queued on the GPU
+        from ..utils.mmd import to_device_async
+        return to_device_async(torch.rand((n, 1)), torch.device(self.device))
 
     def gradient_penalty(self, encoded_source, encoded_target):
         num_s, num_t = encoded_source.shape[0], encoded_target.shape[0]                   # :387-454

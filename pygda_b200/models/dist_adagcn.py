@@ -59,8 +59,8 @@ class DistAdaGCN(AdaGCN):
                 encoded_source = self._encode_all(source_data)
                 encoded_target = self._encode_all(target_data)
             gp_loss = self.gradient_penalty(encoded_source, encoded_target)
-            dis_s = torch.mean(self.discriminator(encoded_source).reshape(-1))
-            dis_t = torch.mean(self.discriminator(encoded_target).reshape(-1))
+            dis_s = torch.mean(self._critic(encoded_source).reshape(-1))
+            dis_t = torch.mean(self._critic(encoded_target).reshape(-1))
             loss = - torch.abs(dis_s - dis_t) + self.gp_weight * gp_loss
             self.c_optimizer.zero_grad()
             loss.backward()
@@ -73,8 +73,8 @@ class DistAdaGCN(AdaGCN):
         g_s = encoded_source.shape[0]
         ce_local = self.adagcn.loss_func(source_logits, source_data.y)                    # local mean
         cls_loss = AllReduceSum.apply(ops.combine([(ce_local, local_source.shape[0] / float(g_s))]), self.pg)
-        dis_s = torch.mean(self.discriminator(encoded_source).reshape(-1))
-        dis_t = torch.mean(self.discriminator(encoded_target).reshape(-1))
+        dis_s = torch.mean(self._critic(encoded_source).reshape(-1))
+        dis_t = torch.mean(self._critic(encoded_target).reshape(-1))
         dis_loss = torch.abs(dis_s - dis_t)
         target_logits = self.adagcn.cls_model(local_target)
         loss = cls_loss + dis_loss * self.domain_weight                                   # :196

@@ -86,7 +86,38 @@ def spmm(graph, x, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0
     if prof is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        prof.append((e0, e1, (n, h, str(x.dtype).replace("torch.", "")) + ((nb,) if nb > 1 else ())))
+        prof.append((e0, e1, (n, h, str(x.dtype).replace("torch.", ""), nb, "weighted")))
+    return out
+
+
+def unit_weight_chain(graph, transpose, h, nb, k):
+    """True when A_hat^k on this graph runs as the factored chain D S (D^2 S)^(k-1) D (gda_spmm_unw_nb_f32)."""
+    return k >= 3 and not hasattr(graph, "spmm_k") and \
+        load().gda_graph_unit_weights(graph.handle, int(bool(transpose)), int(h), int(nb)) == 1
+
+
+def _spmm_k_unw_profiled(graph, x, k, transpose, bias, relu, dropout_p, seed, seed_offset, nb):
+    """bench.py's instrumented form of the factored chain: the same calls gda_spmm_k_nb_f32 makes, one ABI call
+    per step so that each launch can be bracketed by CUDA events."""
+    rows, h = x.shape
+    n = rows // nb
+    bufs = [torch.empty_like(x), torch.empty_like(x)]
+    out = torch.empty_like(x)
+    ws = graph.workspace(transpose, h * nb)
+    gda.row_scale_f32(graph.handle, nb, _p(x), h, n * h, _p(bufs[0]), h, n * h, h, _stream())
+    flags = (EPI_RELU if relu else 0) | (EPI_DROPOUT if dropout_p > 0 else 0)
+    src = bufs[0]
+    for i in range(k):
+        last = i == k - 1
+        dst = out if last else bufs[(i + 1) & 1]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gda.spmm_unw_nb_f32(graph.handle, int(bool(transpose)), nb, _p(src), h, n * h, _p(dst), h, n * h, h, int(last),
+                            _p(bias) if last else _NULL, flags if last else 0, float(dropout_p) if last else 0.0,
+                            int(seed) & _M64, _p(seed_offset), _p(ws), ws.numel(), _stream())
+        e1.record()
+        PROFILE.append((e0, e1, (n, h, "float32", nb, "unit-weight")))
+        src = dst
     return out
 
 
@@ -100,6 +131,9 @@ def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, s
             raise NotImplementedError("the peer path aggregates one matrix per call")
         return graph.spmm_k(x, k, transpose=transpose, bias=bias, relu=relu, dropout_p=dropout_p, seed=seed,
                             seed_offset=seed_offset)
+    if x.dtype == torch.float32 and PROFILE is not None and x.is_contiguous() and \
+            unit_weight_chain(graph, transpose, x.shape[1], nb, k):
+        return _spmm_k_unw_profiled(graph, x, k, transpose, bias, relu, dropout_p, seed, seed_offset, nb)
     if x.dtype != torch.float32 or PROFILE is not None:
         # bf16 features, or bench.py timing each launch: one ABI call per step
         cur, bufs = x, [None, None]
@@ -174,9 +208,10 @@ class ConstCache:
     to a fresh device tensor -- such a copy maps to ONE entry whose buffers are refilled in place from the new copy
     (the step's data is consumed, nothing is re-allocated, nothing stale is kept alive).  Tensors without a host key
     are keyed by (data_ptr, version) and kept alive so that the pointer cannot be recycled.
-    Only grad-mode forward passes insert: under ``torch.no_grad()`` (predict) every activation has
-    ``requires_grad == False`` and must not evict the real constants -- there the cache is lookup-only.
-    Bounded by entries and by bytes."""
+    Only tensors MARKED constant are inserted -- a host key from ``Data.to``, or ``mark_constant`` (the loaders mark
+    the device-resident ``data.x`` they hand out): "does not require grad" is not enough, under ``torch.no_grad()``
+    (predict) every activation looks like that and would evict the real constants.  Anything else is computed
+    uncached.  Bounded by entries and by bytes."""
 
     def __init__(self, make, fill, nbytes, capacity=8, max_bytes=48 << 30):
         self._make, self._fill, self._nbytes = make, fill, nbytes
@@ -198,7 +233,7 @@ class ConstCache:
                 hit[2] = x.data_ptr()
             return hit[0]
         val = self._make(x)
-        if not torch.is_grad_enabled():
+        if key[0] != "host" and not getattr(x, "_gda_const", False):
             return val
         while self._d and (len(self._d) >= self.capacity or
                            sum(self._nbytes(v[0]) for v in self._d.values()) + self._nbytes(val) > self.max_bytes):
@@ -218,6 +253,14 @@ class ConstCache:
 
     def clear(self):
         self._d.clear()
+
+
+def mark_constant(t):
+    """Declare ``t`` (a device tensor that is not re-written between steps, e.g. the input features of a full-batch
+    loader) eligible for the operand caches."""
+    if torch.is_tensor(t):
+        t._gda_const = True
+    return t
 
 
 def SplitCache(capacity=8):
@@ -955,6 +998,33 @@ def graph_conv(x, weight, bias, graph, k, w_in_out=False):
 
 def linear(x, weight, bias=None):
     return LinearFn.apply(x, weight, bias)
+
+
+class MatmulFn(torch.autograd.Function):
+    """a @ b (or a @ b^T) on libgda, differentiable in both operands: the small dense products of AdaGCN's
+    closed-form WGAN-GP penalty (W1 W1^T and u (W1 W1^T), pygda_b200/models/adagcn.py)."""
+
+    @staticmethod
+    def forward(ctx, a, b, trans_b):
+        a, b = _f32c(a), _f32c(b)
+        ctx.save_for_backward(a, b)
+        ctx.trans_b = trans_b
+        return mm(a, b, trans_b=trans_b)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = _f32c(g)
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = mm(g, b, trans_b=not ctx.trans_b)[0]                    # g b^T  |  g b
+        if ctx.needs_input_grad[1]:
+            gb = mm(g, a, trans_a=True)[0] if ctx.trans_b else mm(a, g, trans_a=True)[0]   # g^T a  |  a^T g
+        return ga, gb, None
+
+
+def matmul(a, b, trans_b=False):
+    return MatmulFn.apply(a, b, bool(trans_b))
 
 
 def softmax_cross_entropy(logits, labels):

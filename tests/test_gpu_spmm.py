@@ -113,3 +113,69 @@ def test_autograd_propagate():
     (yg * coef.cuda()).sum().backward()
     assert_close(yg, out, 1e-4, "fwd")
     assert_close(xg.grad, xr.grad, 1e-4, "bwd")
+
+
+# ---- factored chain for unit-weight graphs (spmm.cu: k_spmm_unw; A_hat^k = D S (D^2 S)^(k-1) D, no per-edge weights) ----
+@pytest.mark.parametrize("k", [3, 4, 10])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_unit_weight_chain_matches_the_oracle_and_the_weighted_kernel(k, transpose):
+    from pygda_b200 import ops
+    n = 6000
+    gr, ref_ei, ref_w = _setup(n, 90000, 7, directed=True)          # directed: A_hat != A_hat^T
+    assert ops.unit_weight_chain(gr, transpose, 128, 1, k)
+    x = torch.randn(n, 128)
+    ei = ref_ei.flip(0) if transpose else ref_ei
+    ref = x
+    for _ in range(k):
+        ref = P.propagate(ei, ref, ref_w)
+    y = ops.spmm_k(gr, x.cuda(), k, transpose=transpose)
+    assert_close(y, ref, 2e-5, f"factored A^{k} x vs the oracle")
+    w = x.cuda()
+    for _ in range(k):
+        w = ops.spmm(gr, w, transpose=transpose)                    # one step at a time: the weighted kernel
+    assert_close(y, w, 1e-5, "factored vs weighted kernel")
+    assert torch.equal(y, ops.spmm_k(gr, x.cuda(), k, transpose=transpose))      # deterministic
+
+
+def test_unit_weight_chain_hub_rows_epilogue_and_pairs():
+    from pygda_b200 import ops
+    n, h, k = 20000, 128, 5
+    gr, ref_ei, ref_w = _setup(n, 400000, 2)
+    assert gr.num_long_rows > 0 and ops.unit_weight_chain(gr, False, h, 2, k)
+    x, b = torch.randn(2 * n, h), torch.randn(h)
+    refs = []
+    for half in (x[:n], x[n:]):
+        r = half
+        for _ in range(k):
+            r = P.propagate(ref_ei, r, ref_w)
+        refs.append(torch.relu(r + b))
+    y = ops.spmm_k(gr, x.cuda(), k, bias=b.cuda(), relu=True, nb=2)
+    assert_close(y[:n], refs[0], 2e-5, "stacked pair, first half")
+    assert_close(y[n:], refs[1], 2e-5, "stacked pair, second half")
+    y1 = ops.spmm_k(gr, x[:n].cuda().contiguous(), k, bias=b.cuda(), relu=True)
+    assert torch.equal(y1, y[:n])                                   # nb = 2 == two nb = 1 chains, bit for bit
+    # dropout mask of the last step: that of the weighted kernel for the same seed
+    yd = ops.spmm_k(gr, x[:n].cuda().contiguous(), k, bias=b.cuda(), relu=True, dropout_p=0.5, seed=99)
+    wd = x[:n].cuda()
+    for i in range(k):
+        last = i == k - 1
+        wd = ops.spmm(gr, wd, bias=b.cuda() if last else None, relu=last, dropout_p=0.5 if last else 0.0, seed=99)
+    assert_close(yd, wd, 1e-5, "dropout epilogue")
+
+
+def test_weighted_and_improved_graphs_do_not_take_the_factored_chain():
+    from pygda_b200 import ops
+    from pygda_b200.graph import Graph, SELF_LOOPS, NORM_SYM_COL, IMPROVED
+    n = 3000
+    ei = powerlaw(n, 30000, 5).cuda()
+    w = torch.rand(ei.size(1), device="cuda") + 0.5
+    assert not ops.unit_weight_chain(Graph(ei, n, w), False, 128, 1, 10)
+    assert not ops.unit_weight_chain(Graph(ei, n, None, SELF_LOOPS | NORM_SYM_COL | IMPROVED), False, 128, 1, 10)
+    assert ops.unit_weight_chain(Graph(ei, n), False, 128, 1, 10)
+    assert not ops.unit_weight_chain(Graph(ei, n), False, 64, 1, 10)        # other widths: weighted kernels
+    x = torch.randn(n, 128)
+    ref_ei, ref_w = P.gcn_norm_by_col(ei.cpu(), w.cpu(), n)
+    ref = x
+    for _ in range(4):
+        ref = P.propagate(ref_ei, ref, ref_w)
+    assert_close(ops.spmm_k(Graph(ei, n, w), x.cuda(), 4), ref, 2e-5, "weighted chain")
