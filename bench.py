@@ -365,15 +365,30 @@ def run_gpu_arm(args, rank, world, local_rank):
                               feature_shift=1.4, degree_offset=48.0, device=dev)
         src, tgt = attach_partition(src, group), attach_partition(tgt, group)
         model = DistA2GNN(group=group, **hp)
-        model.a2gnn = model.init_model()
-        s_batch, t_batch = src, tgt
+        if args.no_cuda_graph:
+            model.cuda_graph = False
+        graph_error = None
+        try:
+            # the same prepare_fit as on one GPU: the partitioned step (peer aggregations with their device-side
+            # barriers, NCCL all-reduces) captured as ONE CUDA graph per rank and replayed
+            run_epoch = model.prepare_fit(src, tgt)
+            s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
+        except Exception as exc:                      # noqa: BLE001 -- measure the eager path and say why
+            graph_error = repr(exc)[:300]
+            ok = torch.tensor([0], device=dev)
+        else:
+            ok = torch.tensor([1 if (run_epoch is not None or args.no_cuda_graph) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # every rank takes the same path
+        if int(ok.item()) == 0 or run_epoch is None:
+            run_epoch = None
+            model.cuda_graph = False
+            if not hasattr(model, "optimizer") or graph_error is not None:
+                model.prepare_fit(src, tgt)
+            s_batch, t_batch = next(iter(model.source_loader)), next(iter(model.target_loader))
         parallelism = ("1-D node partition: %d communities of %dk nodes (one per GPU, 5%% cross-partition edges), "
                        "NVLink peer gathers in the aggregation kernel, NCCL gradient all-reduce; value counts "
                        "config-2-sized graph-epochs per second" % (world, CFG["nodes"] // 1000))
-    if run_epoch is not None or not distributed:
-        sopt = model.optimizer
-    else:
-        sopt = Adam(list(model.a2gnn.parameters()), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    sopt = model.optimizer
     step_no = [1]
 
     def one_step(sb, tb):
@@ -400,6 +415,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     gstep = getattr(model, "graphed_step", None) if run_epoch is not None else None
     graph_note = ("CUDA graph replay (%d kernels per step), fit()'s default" % gstep.launches_per_replay
                   if gstep is not None else "eager launches")
+    if distributed and gstep is None and locals().get("graph_error"):
+        graph_note += " (graph capture failed: %s)" % graph_error
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

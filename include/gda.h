@@ -170,6 +170,16 @@ int gda_spmm_peer_k_f32(const gda_graph_t* part, int transpose, int k, const flo
                         float* Y, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
                         const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
                         uint64_t* const* peer_flags, uint64_t epoch0, int* error_flag, gda_stream_t stream);
+/* The same with the barrier epoch kept in DEVICE memory (*epoch_dev, a uint64 owned by the rank, advanced by
+ * the barrier kernel itself): no launch argument depends on host state, so the partitioned training step can be
+ * captured in a CUDA graph and replayed.  gda_peer_barrier_dev is the barrier alone. */
+int gda_spmm_peer_k_dev_f32(const gda_graph_t* part, int transpose, int k, const float* x_local,
+                            const void* const* sym0, const void* const* sym1, int num_peers, int my_rank,
+                            float* Y, int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                            const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
+                            uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag, gda_stream_t stream);
+int gda_peer_barrier_dev(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t* epoch_dev,
+                         int* error_flag, gda_stream_t stream);
 int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
 int gda_sym_open(const unsigned char* handle /* 64 bytes */, void** ptr);
 int gda_sym_close(void* ptr);

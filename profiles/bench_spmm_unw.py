@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A_hat^10 on the config-2 target graph (100k nodes / 1.1M nnz, H = 128 fp32): the factored unit-weight chain
-(k_spmm_unw, GDA_SPMM_UNW = 16 default / 12 / 0 = weighted k_spmm_tasks) timed per step with CUDA events, checked
+(k_spmm_unw, GDA_SPMM_UNW = 12 default / 16 / 0 = weighted k_spmm_tasks) timed per step with CUDA events, checked
 against the weighted chain.  N / E / NB environment variables change the size / stack two matrices."""
 import os
 import sys

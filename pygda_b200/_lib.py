@@ -41,6 +41,9 @@ SIGNATURES = {
                                 i64, vp]),
     "gda_spmm_peer_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
                                   vp, u64, vp, vp]),
+    "gda_spmm_peer_k_dev_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
+                                      vp, vp, vp, vp]),
+    "gda_peer_barrier_dev": (i32, [vp, i32, i32, vp, vp, vp]),
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_graph_partition": (i32, [vp, i64, i64, i64, vp, C.POINTER(vp)]),
     "gda_spmm_peer_f32": (i32, [vp, i32, vp, i32, i32, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),

@@ -224,11 +224,44 @@ __global__ void k_softmax_ce(const float* __restrict__ logits, int64_t rows, int
 #pragma unroll 8
     for (int c = 0; c < C; ++c) s += expf(v[c] - m);
     const float lse = m + logf(s);
-    const int y = labels ? static_cast<int>(labels[r]) : (r >= split ? 1 : 0);
+    int y = labels ? static_cast<int>(labels[r]) : (r >= split ? 1 : 0);
+    y = min(max(y, 0), C - 1);                           // never index outside v[]; range is validated by the caller
     local += lse - v[y];
     if (dlogits) {
       float* g = dlogits + r * C;
       for (int c = 0; c < C; ++c) g[c] = (expf(v[c] - lse) - (c == y ? 1.f : 0.f)) * inv_rows;
+    }
+  }
+  const float tot = block_sum(local);
+  if (threadIdx.x == 0) atomicAdd(loss_out, tot * inv_rows);
+}
+
+// Any number of classes: one warp per row, the lanes stride over the classes (max, sum of exponentials, gradient: three
+// passes over the row, which stays in L1).  Used above kMaxC classes; same values as k_softmax_ce.
+__global__ void k_softmax_ce_wide(const float* __restrict__ logits, int64_t rows, int C, int64_t ld,
+                                  const int64_t* __restrict__ labels, int64_t split, float* __restrict__ loss_out,
+                                  float* __restrict__ dlogits, float inv_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float local = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* z = logits + r * ld;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, z[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(z[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+    int y = labels ? static_cast<int>(labels[r]) : (r >= split ? 1 : 0);
+    y = min(max(y, 0), C - 1);                           // range is validated on the host side (ops.SoftmaxCEFn)
+    if (lane == 0) local += lse - z[y];
+    if (dlogits) {
+      float* g = dlogits + r * C;
+      for (int c = lane; c < C; c += 32) g[c] = (expf(z[c] - lse) - (c == y ? 1.f : 0.f)) * inv_rows;
     }
   }
   const float tot = block_sum(local);
@@ -452,13 +485,17 @@ int gda_bias_act_dropout_bwd(const float* gy, const float* y, float* gx, float* 
 
 int gda_softmax_ce_fwd_bwd(const float* logits, int64_t rows, int C, int64_t ld, const int64_t* labels,
                            int64_t split, float* loss_out, float* dlogits, gda_stream_t stream) {
-  GDA_REQUIRE(rows > 0 && C > 0 && C <= kMaxC && ld >= C, "gda_softmax_ce_fwd_bwd: bad shape (need 0 < C <= 64)");
+  GDA_REQUIRE(rows > 0 && C > 0 && ld >= C, "gda_softmax_ce_fwd_bwd: bad shape");
   GDA_REQUIRE(logits && loss_out, "gda_softmax_ce_fwd_bwd: NULL pointer");
   GDA_REQUIRE(labels || C >= 2, "gda_softmax_ce_fwd_bwd: implicit domain labels need C >= 2");
   cudaStream_t st = as_stream(stream);
   GDA_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-  k_softmax_ce<<<grid_for(rows), kThreads, 0, st>>>(logits, rows, C, ld, labels, split, loss_out, dlogits,
-                                                     1.0f / static_cast<float>(rows));
+  if (C <= kMaxC)
+    k_softmax_ce<<<grid_for(rows), kThreads, 0, st>>>(logits, rows, C, ld, labels, split, loss_out, dlogits,
+                                                       1.0f / static_cast<float>(rows));
+  else
+    k_softmax_ce_wide<<<grid_for(rows * 32), kThreads, 0, st>>>(logits, rows, C, ld, labels, split, loss_out, dlogits,
+                                                                 1.0f / static_cast<float>(rows));
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

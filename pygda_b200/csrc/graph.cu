@@ -6,6 +6,7 @@
 // (rows = sources) for the aggregation kernels.  Radix sort / scans come from CUB
 // (header library in the CUDA toolkit): this is one-time preparation, not the
 // per-step path.
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "graph.cuh"
@@ -189,7 +190,9 @@ __global__ void k_export_coo(const int* __restrict__ src, const int* __restrict_
 template <typename T>
 int dev_alloc(T** p, int64_t n) {
   *p = nullptr;
-  GDA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * static_cast<size_t>(n > 0 ? n : 1)));
+  // + 64 bytes of slack: the aggregation kernels prefetch the next batch's column indices with unconditional loads
+  // that may run up to 3 entries past the last non-zero (spmm.cu: k_spmm_unw)
+  GDA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * static_cast<size_t>(n > 0 ? n : 1) + 64));
   return GDA_OK;
 }
 
@@ -312,6 +315,10 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
 
   std::unique_ptr<gda_graph> g(new gda_graph());
   g->N = N; g->E = E; g->flags = flags; g->seg = kLongRowSegment;
+  if (const char* e = std::getenv("GDA_SEG")) {           // experiments: segment length of split long rows (8..64)
+    const int v = std::atoi(e);
+    if (v >= 8 && v <= 64 && v % 4 == 0) g->seg = v;
+  }
   GDA_CUDA(cudaGetDevice(&g->device));
   const bool loops = flags & GDA_SELF_LOOPS;
   Scratch sc;

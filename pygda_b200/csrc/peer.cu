@@ -35,6 +35,35 @@ __global__ void k_peer_barrier(FlagPtrs flags, int rank, int num_peers, uint64_t
   }
 }
 
+// The same barrier with the epoch kept in DEVICE memory: thread 0 advances the rank's own counter and the block
+// uses the new value.  Nothing about the launch depends on host state, so a captured CUDA graph can replay it
+// (every rank replays the same sequence of barriers on a channel, so the counters stay in step).
+__global__ void k_peer_barrier_dev(FlagPtrs flags, int rank, int num_peers, uint64_t* epoch_dev, int* error) {
+  __shared__ uint64_t e_sh;
+  if (threadIdx.x == 0) {
+    const uint64_t e = *epoch_dev + 1;
+    *epoch_dev = e;
+    e_sh = e;
+  }
+  __syncthreads();
+  const uint64_t epoch = e_sh;
+  const int q = threadIdx.x;
+  if (q >= num_peers) return;
+  uint64_t* theirs = flags.p[q] + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+  const uint64_t* mine = flags.p[rank] + q;
+  const long long t0 = clock64();
+  while (true) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 20000000000LL) {
+      if (error) *error = 1;
+      break;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace gda
 
@@ -82,6 +111,20 @@ int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint6
     f.p[i] = peer_flags[i];
   }
   k_peer_barrier<<<1, 32, 0, as_stream(stream)>>>(f, rank, num_peers, epoch, error_flag);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_peer_barrier_dev(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t* epoch_dev, int* error_flag,
+                         gda_stream_t stream) {
+  GDA_REQUIRE(peer_flags && epoch_dev && num_peers >= 1 && num_peers <= GDA_MAX_PEERS && rank >= 0 && rank < num_peers,
+              "gda_peer_barrier_dev: bad arguments");
+  FlagPtrs f;
+  for (int i = 0; i < num_peers; ++i) {
+    GDA_REQUIRE(peer_flags[i] != nullptr, "gda_peer_barrier_dev: NULL flag array");
+    f.p[i] = peer_flags[i];
+  }
+  k_peer_barrier_dev<<<1, 32, 0, as_stream(stream)>>>(f, rank, num_peers, epoch_dev, error_flag);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

@@ -628,6 +628,12 @@ k_spmm_rows(const int* __restrict__ rowptr, const int* __restrict__ colidx, cons
 //    2 + ceil(len / U).  Indices and weights reach the lanes by shuffle.
 // The summation order inside a row is unchanged (sequential in CSR = COO order, segments reduced
 // in segment order), so results are bit-identical to k_spmm_rows.
+// Task of warp w in round r of the work list.  The list is sorted by descending length; a plain grid-stride walk
+// (r * W + w) hands warp 0 the longest task of EVERY round and warp W-1 the shortest, a telescoping imbalance of
+// (longest - shortest task) ~ 60 non-zeros against a mean of ~115 per warp at config 2.  Reversing the direction in
+// odd rounds (boustrophedon) pairs each long task with a short one: per-warp totals agree to within one task.
+__device__ __forceinline__ int snake_task(int r, int w, int W) { return r * W + ((r & 1) ? (W - 1 - w) : w); }
+
 template <typename T, int VEC, int K, bool PEER, int NB>
 __device__ __forceinline__ void gather_batch(float (&acc)[NB][VEC], int myc, float myv, int j, const char* __restrict__ Xc,
                                              unsigned ldxb, uint64_t xbsb, int c0, const PeerTable& peers) {
@@ -670,13 +676,15 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
   const int c0 = lane * VEC;
   const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= num_tasks) return;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int r = 0;
+  if (wid >= num_tasks) return;
 
-  uint2 cur = __ldg(tasks + i);
-  bool has_next = i + nwarps < num_tasks;
+  uint2 cur = __ldg(tasks + wid);
+  int inext = snake_task(1, wid, nwarps);
+  bool has_next = inext < num_tasks;
   uint2 nxt = make_uint2(0u, 0u);
-  if (has_next) nxt = __ldg(tasks + i + nwarps);
+  if (has_next) nxt = __ldg(tasks + inext);
   int myc = 0;
   float myv = 0.f;
   if (lane <= static_cast<int>((cur.y >> 25) & 63u)) {
@@ -689,12 +697,13 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
     int nc = 0;
     float nv = 0.f;
     uint2 nn = make_uint2(0u, 0u);
-    const bool has_nn = i + 2 * nwarps < num_tasks;
+    const int inn = snake_task(r + 2, wid, nwarps);
+    const bool has_nn = has_next && inn < num_tasks;
     if (has_next && lane <= static_cast<int>((nxt.y >> 25) & 63u)) {
       nc = __ldg(colidx + nxt.x + lane);
       nv = __ldg(vals + nxt.x + lane);
     }
-    if (has_nn) nn = __ldg(tasks + i + 2 * nwarps);
+    if (has_nn) nn = __ldg(tasks + inn);
 
     // ---- the task: len non-zeros starting at cur.x, first min(len, 32) pairs staged in (myc, myv) ----
     const int len = static_cast<int>((cur.y >> 25) & 63u) + 1;
@@ -770,7 +779,7 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
     if (!has_next) break;
     cur = nxt; myc = nc; myv = nv;
     nxt = nn; has_next = has_nn;
-    i += nwarps;
+    ++r;
   }
 }
 
@@ -787,12 +796,13 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
 // the occupancy at which the regular gather probe peaks (41 us vs 51 us at 40 warps/SM).
 // Summation order inside a row is unchanged (CSR = COO order, segments reduced in segment order); values differ from
 // the weighted kernel by fp32 rounding only (scale applied once per row instead of once per edge).
+// One batch: K row gathers issued from the indices in cj[], then -- while they are in flight -- the NEXT batch's four
+// indices are fetched into the same registers (warp-uniform loads from `pn`; entries past the end of that task are
+// never used), then the K rows are summed in order.  The ncu source view of the first version of this kernel put 15 %
+// of the stall samples on the address computation that waits for the index load: a second serial L2 latency per batch.
 template <int K, int NB>
-__device__ __forceinline__ void gather_sum(float (&acc)[NB][4], const int* __restrict__ ci, const char* __restrict__ Xc,
-                                           unsigned ldxb, uint64_t xbsb) {
-  unsigned cj[K];
-#pragma unroll
-  for (int u = 0; u < K; ++u) cj[u] = static_cast<unsigned>(__ldg(ci + u));
+__device__ __forceinline__ void gather_sum(float (&acc)[NB][4], unsigned (&cj)[4], const int* __restrict__ pn,
+                                           const char* __restrict__ Xc, unsigned ldxb, uint64_t xbsb) {
   uint4 xv[K][NB];
 #pragma unroll
   for (int u = 0; u < K; ++u) {
@@ -800,6 +810,8 @@ __device__ __forceinline__ void gather_sum(float (&acc)[NB][4], const int* __res
 #pragma unroll
     for (int b = 0; b < NB; ++b) xv[u][b] = gather16(src + b * xbsb);
   }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) cj[u] = static_cast<unsigned>(__ldg(pn + u));
 #pragma unroll
   for (int u = 0; u < K; ++u)
 #pragma unroll
@@ -816,32 +828,42 @@ k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict
            const int* __restrict__ long_seg_ptr, const int* __restrict__ seg_long, int* __restrict__ counters,
            const float* __restrict__ X, unsigned ldxb, float* __restrict__ Y, unsigned ldyb, int H,
            Epilogue epi, float* __restrict__ partial, uint64_t xbsb, uint64_t ybsb, int nrows) {
+  static_assert(U == 4, "batches of four");
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
   const char* __restrict__ Xc = reinterpret_cast<const char*>(X + c0);
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= num_tasks) return;
-  uint2 cur = __ldg(tasks + i);
-  while (true) {
-    const int inext = i + nwarps;
-    const bool has_next = inext < num_tasks;
-    uint2 nxt = make_uint2(0u, 0u);
-    if (has_next) nxt = __ldg(tasks + inext);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= num_tasks) return;
+  uint2 cur = __ldg(tasks + wid);
+  int inext = snake_task(1, wid, nwarps);
+  bool has_next = inext < num_tasks;
+  uint2 nxt = has_next ? __ldg(tasks + inext) : cur;
+  unsigned cj[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) cj[u] = static_cast<unsigned>(__ldg(colidx + cur.x + u));
+  for (int r = 0;; ++r) {
+    // descriptor of the task after the next one: by the time the next task starts, its successor is known and the
+    // first indices of that successor can be prefetched in its last batch
+    const int inn = snake_task(r + 2, wid, nwarps);
+    const bool has_nn = has_next && inn < num_tasks;
+    uint2 nn = nxt;
+    if (has_nn) nn = __ldg(tasks + inn);
 
     const int* __restrict__ ci = colidx + cur.x;
+    const int* __restrict__ cn = colidx + nxt.x;          // first indices of the next task (== cur when none: unused)
     int left = static_cast<int>((cur.y >> 25) & 63u) + 1;
     float acc[NB][4];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int v = 0; v < 4; ++v) acc[b][v] = 0.f;
-    for (; left >= U; left -= U, ci += U) gather_sum<U, NB>(acc, ci, Xc, ldxb, xbsb);
-    switch (left) {                                      // warp-uniform: exact tails, no padding gathers
-      case 1: gather_sum<1, NB>(acc, ci, Xc, ldxb, xbsb); break;
-      case 2: gather_sum<2, NB>(acc, ci, Xc, ldxb, xbsb); break;
-      case 3: gather_sum<3, NB>(acc, ci, Xc, ldxb, xbsb); break;
-      default: break;
+    for (; left > 4; left -= 4) { ci += 4; gather_sum<4, NB>(acc, cj, ci, Xc, ldxb, xbsb); }
+    switch (left) {                                      // last batch of the task (warp-uniform): exact, no padding gathers
+      case 1: gather_sum<1, NB>(acc, cj, cn, Xc, ldxb, xbsb); break;
+      case 2: gather_sum<2, NB>(acc, cj, cn, Xc, ldxb, xbsb); break;
+      case 3: gather_sum<3, NB>(acc, cj, cn, Xc, ldxb, xbsb); break;
+      default: gather_sum<4, NB>(acc, cj, cn, Xc, ldxb, xbsb); break;
     }
 
     if (!(cur.y & 0x80000000u)) {
@@ -893,7 +915,8 @@ k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict
     }
     if (!has_next) break;
     cur = nxt;
-    i = inext;
+    nxt = nn;
+    has_next = has_nn;
   }
 }
 
@@ -915,7 +938,7 @@ k_row_scale(const float* __restrict__ X, int64_t ldx, int64_t xbs, float* __rest
 }
 
 inline int unw_mode() {         // experiments: GDA_SPMM_UNW=0 disables the factored chain, =12 / =16 pick CTAs per SM
-  static const int m = [] { const char* e = std::getenv("GDA_SPMM_UNW"); return e ? std::atoi(e) : 16; }();
+  static const int m = [] { const char* e = std::getenv("GDA_SPMM_UNW"); return e ? std::atoi(e) : 12; }();
   return m;
 }
 
@@ -1134,7 +1157,7 @@ int spmm_unw(const gda_graph* g, int transpose, int nb, const float* Z, int64_t 
   float* partial = static_cast<float*>(workspace);
   const unsigned ldzb = static_cast<unsigned>(ldz * sizeof(float)), ldyb = static_cast<unsigned>(ldy * sizeof(float));
   const uint64_t zb = static_cast<uint64_t>(zbs) * sizeof(float), yb = static_cast<uint64_t>(ybs) * sizeof(float);
-  const int per_sm = nb == 2 ? 10 : (unw_mode() == 12 ? 12 : 16);
+  const int per_sm = nb == 2 ? 10 : (unw_mode() == 16 ? 16 : 12);
   int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
   if (tb > static_cast<int64_t>(kNumSMs) * per_sm) tb = static_cast<int64_t>(kNumSMs) * per_sm;
 #define GDA_UNW_LAUNCH(CC, E, B)                                                                              \
@@ -1317,6 +1340,38 @@ int gda_spmm_peer_k_f32(const gda_graph_t* part, int transpose, int k, const flo
   for (int i = 0; i < k; ++i) {
     const bool last = i == k - 1;
     if ((rc = gda_peer_barrier(peer_flags, my_rank, num_peers, ++epoch0, error_flag, stream))) return rc;
+    const void* const* src = (i & 1) ? sym1 : sym0;
+    float* dst = last ? Y : static_cast<float*>(const_cast<void*>(((i & 1) ? sym0 : sym1)[my_rank]));
+    rc = gda_spmm_peer_f32(part, transpose, src, num_peers, my_rank, H, dst, H, H, last ? bias : nullptr,
+                           last ? epi_flags : 0, last ? dropout_p : 0.f, seed, seed_offset, workspace,
+                           workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return GDA_OK;
+}
+
+int gda_peer_barrier_dev(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t* epoch_dev, int* error_flag,
+                         gda_stream_t stream);   // peer.cu
+
+// gda_spmm_peer_k_f32 with the barrier epochs kept in device memory (*epoch_dev advances by k + 1): no launch
+// argument depends on host state, so the whole sequence can be captured in a CUDA graph and replayed.
+int gda_spmm_peer_k_dev_f32(const gda_graph_t* part, int transpose, int k, const float* x_local,
+                            const void* const* sym0, const void* const* sym1, int num_peers, int my_rank, float* Y,
+                            int H, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
+                            const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes,
+                            uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag, gda_stream_t stream) {
+  GDA_REQUIRE(part && part->peer_packed && k >= 1 && x_local && sym0 && sym1 && Y && epoch_dev,
+              "gda_spmm_peer_k_dev_f32: bad arguments");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS && my_rank >= 0 && my_rank < num_peers,
+              "gda_spmm_peer_k_dev_f32: bad peer arguments");
+  cudaStream_t st = gda::as_stream(stream);
+  int rc = gda_peer_barrier_dev(peer_flags, my_rank, num_peers, epoch_dev, error_flag, stream);
+  if (rc) return rc;
+  GDA_CUDA(cudaMemcpyAsync(const_cast<void*>(sym0[my_rank]), x_local, sizeof(float) * part->N * H,
+                           cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < k; ++i) {
+    const bool last = i == k - 1;
+    if ((rc = gda_peer_barrier_dev(peer_flags, my_rank, num_peers, epoch_dev, error_flag, stream))) return rc;
     const void* const* src = (i & 1) ? sym1 : sym0;
     float* dst = last ? Y : static_cast<float*>(const_cast<void*>(((i & 1) ? sym0 : sym1)[my_rank]));
     rc = gda_spmm_peer_f32(part, transpose, src, num_peers, my_rank, H, dst, H, H, last ? bias : nullptr,

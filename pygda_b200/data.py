@@ -215,6 +215,8 @@ class NeighborLoader:
                 extra[k] = v[order.to(v.device)].contiguous()
         self._batch = Data(x=data.x, edge_index=ei[:, order].contiguous(), y=data.y,
                            batch=data.batch, num_graphs=data.num_graphs, **extra)
+        if hasattr(ei, "_gda_partition"):            # row-partitioned multi-GPU graph: the tag travels with the edges
+            self._batch.edge_index._gda_partition = ei._gda_partition
         # the fit loops send this one batch host->device on EVERY step (pygda/models/a2gnn.py:311-312): stage it in
         # pinned memory once (a sparse x row-compressed, Data.pin_memory) instead of paging it through each time
         host = torch.is_tensor(data.x) and not data.x.is_cuda

@@ -143,7 +143,9 @@ class PartitionedGraph:
         # every partitioned graph has its own barrier channel (flag array + epoch counter): graphs used
         # on different streams (source / target branch) then never wait on each other's epochs
         self.flags = SymBuffer(group, 8 * MAX_PEERS)
-        self.epoch = 0
+        # the channel's barrier epoch lives in device memory and is advanced by the barrier kernel itself, so that
+        # a captured CUDA graph of the training step replays correctly (gda_peer_barrier_dev)
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -173,9 +175,8 @@ class PartitionedGraph:
         return s
 
     def _barrier(self):
-        self.epoch += 1
-        gda.peer_barrier(self.flags.ptr_array, self.group.rank, self.group.world, self.epoch,
-                         C.c_void_p(self.group.error.data_ptr()), _stream())
+        gda.peer_barrier_dev(self.flags.ptr_array, self.group.rank, self.group.world, ops._p(self.epoch_dev),
+                             C.c_void_p(self.group.error.data_ptr()), _stream())
 
     def spmm_k(self, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, seed_offset=None):
         """A_hat^k x over the partition: x and the result are this rank's [n_local, H] blocks."""
@@ -190,12 +191,11 @@ class PartitionedGraph:
         flags = (ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)
         if ops.PROFILE is None:
             # barrier + copy-in + k x (barrier, peer aggregation) behind ONE call: k+2 fewer host round trips
-            gda.spmm_peer_k_f32(self._h, int(bool(transpose)), int(k), ops._p(x), bufs[0].ptr_array,
-                                bufs[1].ptr_array, g.world, g.rank, ops._p(out), h, ops._p(bias), flags,
-                                float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, ops._p(seed_offset), ops._p(ws),
-                                ws.numel(), self.flags.ptr_array, self.epoch, C.c_void_p(g.error.data_ptr()),
-                                _stream())
-            self.epoch += k + 1
+            gda.spmm_peer_k_dev_f32(self._h, int(bool(transpose)), int(k), ops._p(x), bufs[0].ptr_array,
+                                    bufs[1].ptr_array, g.world, g.rank, ops._p(out), h, ops._p(bias), flags,
+                                    float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, ops._p(seed_offset), ops._p(ws),
+                                    ws.numel(), self.flags.ptr_array, ops._p(self.epoch_dev),
+                                    C.c_void_p(g.error.data_ptr()), _stream())
             return out
         # bench.py instrumentation: one call per step so that each launch can be timed
         views = [b.view(torch.float32, (self.rows_per_rank, h)) for b in bufs]
@@ -213,7 +213,7 @@ class PartitionedGraph:
                               ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            ops.PROFILE.append((e0, e1, (n, h, "float32")))
+            ops.PROFILE.append((e0, e1, (n, h, "float32", 1, "weighted-peer")))
         return out
 
 

@@ -107,6 +107,12 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         p = float(epoch) / total                                                          # :305
         return 2. / (1. + np.exp(-10. * p)) - 1                                           # :306
 
+    def backward_and_step(self, loss, optimizer):
+        """a2gnn.py:317-319."""
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+
     def train_step(self, source_data, target_data, alpha, optimizer, mmd_indices=None):
         """The loop body at a2gnn.py:309-319; returns (loss tensor, source logits, target logits)."""
         self.a2gnn.train()
@@ -114,9 +120,7 @@ class A2GNN(TwoDomainLoop, BaseGDA):
         target_data = target_data.to(self.device)
         loss, source_logits, target_logits = self.forward_model(source_data, target_data, alpha,
                                                                 mmd_indices=mmd_indices)
-        optimizer.zero_grad()
-        loss.backward()
-        optimizer.step()
+        self.backward_and_step(loss, optimizer)
         return loss, source_logits, target_logits, source_data
 
     def prepare_fit(self, source_data, target_data):

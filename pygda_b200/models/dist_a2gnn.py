@@ -79,14 +79,8 @@ class DistA2GNN(A2GNN):
         target_logits = net(target_data, self.t_pnums, first_layer=t1)
         return loss, source_logits, target_logits
 
-    def train_step(self, source_data, target_data, alpha, optimizer, mmd_indices=None):
-        self.a2gnn.train()
-        source_data = source_data.to(self.device)
-        target_data = target_data.to(self.device)
-        loss, source_logits, target_logits = self.forward_model(source_data, target_data, alpha,
-                                                                mmd_indices=mmd_indices)
+    def backward_and_step(self, loss, optimizer):
         optimizer.zero_grad()
         loss.backward()
         allreduce_grads(list(self.a2gnn.parameters()), self.group.pg)
         optimizer.step()
-        return loss, source_logits, target_logits, source_data

@@ -99,7 +99,10 @@ class GraphedStep:
         self.tgt = self.staged[1].static if self.staged[1] is not None else target_data
         self.h2d_bytes_per_step = sum(sb.nbytes for sb in self.staged if sb is not None)
         self._slot = 0
-        self.ns, self.nt = self.src.x.shape[0], self.tgt.x.shape[0]
+        # MMD sample indices range over the WHOLE graph (a rank of a partitioned run holds a row block of it)
+        self.ns = int(getattr(self.src, "num_nodes_global", self.src.x.shape[0]))
+        self.nt = int(getattr(self.tgt, "num_nodes_global", self.tgt.x.shape[0]))
+        self.group = getattr(est, "group", None)         # partitioned estimator (models/dist_a2gnn.py)
         self.sampling_num, self.times = sampling_num, times
         self.s_idx = torch.zeros(times, sampling_num, dtype=torch.int64, device=dev)
         self.t_idx = torch.zeros(times, sampling_num, dtype=torch.int64, device=dev)
@@ -137,9 +140,7 @@ class GraphedStep:
         idx = (self.s_idx, self.t_idx) if self.uses_mmd else None
         loss, s_logits, t_logits = est.forward_model(self.src, self.tgt, self.alpha if not self.uses_mmd else 0.0,
                                                      mmd_indices=idx)
-        self.opt.zero_grad()
-        loss.backward()
-        self.opt.step()
+        est.backward_and_step(loss, self.opt)            # zero_grad, backward, [gradient all-reduce,] Adam step
         ops.dropout_rng.advance_offset()
         return loss, s_logits, t_logits
 
@@ -149,6 +150,11 @@ class GraphedStep:
                 indices = mmd_utils.draw_indices(self.ns, self.nt, self.sampling_num, self.times)
             mmd_utils.stage_into(self.s_idx, indices[0])
             mmd_utils.stage_into(self.t_idx, indices[1])
+            if self.group is not None and self.group.world > 1:
+                # one draw for all ranks: rank 0's (pygda/utils/mmd.py:148-149), as DistA2GNN._mmd_indices does
+                import torch.distributed as dist
+                dist.broadcast(self.s_idx, src=0, group=self.group.pg)
+                dist.broadcast(self.t_idx, src=0, group=self.group.pg)
         else:
             ops.gda.fill_f32(ops._p(self.alpha), 1, float(alpha), ops._stream())
 

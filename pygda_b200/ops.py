@@ -811,6 +811,26 @@ class GradReverse(torch.autograd.Function):
         return scale(g, -float(ctx.alpha)), None
 
 
+_LABELS_OK = {}
+
+
+def _validate_labels(labels, c):
+    """F.nll_loss raises for a target outside [0, C) (pygda/models/a2gnn.py:182); so does this path -- once per label
+    tensor (the labels of a full-batch fit are the same tensor every step), so no per-step host synchronisation."""
+    key = (labels.data_ptr(), labels._version, labels.numel(), int(c))
+    if _LABELS_OK.get(key):
+        return
+    if torch.cuda.is_current_stream_capturing():
+        return                                           # validated by the warm-up step that precedes every capture
+    if labels.numel():
+        lo, hi = int(labels.min()), int(labels.max())
+        if lo < 0 or hi >= c:
+            raise IndexError(f"Target {lo if lo < 0 else hi} is out of bounds.")
+    if len(_LABELS_OK) > 64:
+        _LABELS_OK.clear()
+    _LABELS_OK[key] = True
+
+
 class SoftmaxCEFn(torch.autograd.Function):
     """mean CE(log_softmax(logits), labels); labels=None means row r has label (r >= split)."""
 
@@ -824,6 +844,7 @@ class SoftmaxCEFn(torch.autograd.Function):
             labels = labels.contiguous()
             if labels.dtype != torch.int64 or labels.numel() != rows:
                 raise ValueError("labels must be int64 with one entry per row")
+            _validate_labels(labels, c)
         gda.softmax_ce_fwd_bwd(_p(z), rows, c, z.stride(0), _p(labels), int(split), _p(loss), _p(dz), _stream())
         ctx.save_for_backward(dz)
         return loss

@@ -25,6 +25,8 @@ def to_device_async(idx, device):
     would block the host until the GPU drains everything queued before it."""
     if idx.is_cuda:
         return idx.contiguous()
+    if torch.device(device).type != "cuda":
+        return idx.to(device)                          # nothing to stage: the tensor is not going to a GPU
     key = (tuple(idx.shape), idx.dtype, str(device))
     ring = _pinned.get(key)
     if ring is None:

@@ -80,6 +80,7 @@ def graph_conv(x, weight, bias, graph, k, w_in_out=False):
     return h if bias is None else h + bias
 ops.graph_conv = graph_conv
 ops.linear = lambda x, w, b=None: F.linear(x, w, b)
+ops.matmul = lambda a, b, trans_b=False: a @ (b.t() if trans_b else b)
 def act_dropout(x, act, p, training):
     if act is not None: x = act(x)
     return F.dropout(x, p, training) if (training and p > 0) else x

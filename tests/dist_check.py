@@ -88,6 +88,40 @@ def main():
                   f"max param err {max(v for k, v in errs.items() if k.startswith('param')):.1e}")
     group.check()
 
+    # ---- 2b. the partitioned step captured as a CUDA graph (fit()'s default) == the single-GPU eager steps -----
+    from pygda_b200.models.graphed import GraphedStep
+    torch.manual_seed(0)
+    single = A2GNN(device=str(dev), **hp)
+    single.a2gnn = single.init_model()
+    single.overlap_streams = False
+    multi = DistA2GNN(device=str(dev), group=group, **hp)
+    multi.a2gnn = multi.init_model()
+    o2 = Adam(multi.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    gs = GraphedStep(multi, s_part, t_part, o2, warmup=1)     # one eager step inside (rank 0's own index draw)
+    # common starting point for the comparison: the weights after that warm-up step, fresh Adam moments on both sides
+    single.a2gnn.load_state_dict(multi.a2gnn.state_dict())
+    o1 = Adam(single.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    for grp in o2.groups:
+        for m in grp.exp_avg + grp.exp_avg_sq:
+            m.zero_()
+        grp.state.zero_()
+    torch.manual_seed(21)
+    for step in range(3):
+        d = tuple(t.to(dev) for t in draw_indices(n, n - 1000))
+        for t in d:
+            dist.broadcast(t, src=0)
+        d = tuple(t.cpu() for t in d)
+        l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=d)
+        l2, sl2, tl2 = gs(mmd_indices=d)
+        errs = {"loss": rel(l2, l1), "source_logits": rel(sl2, sl1[slo:shi]), "target_logits": rel(tl2, tl1[tlo:thi])}
+        perr = max(rel(p, q) for p, q in zip(multi.a2gnn.parameters(), single.a2gnn.parameters()))
+        ok &= max(max(errs.values()), perr) < 5e-4
+        if rank == 0:
+            print(f"graphed dist step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()),
+                  f"max param err {perr:.1e}, {gs.launches_per_replay} kernels per replay")
+    group.check()
+    del gs
+
     # ---- 3. GRADE over the partition (config 4): MMD and JS discrepancies ------------------------
     from pygda_b200.models import GRADE
     from pygda_b200.models.dist_grade import DistGRADE

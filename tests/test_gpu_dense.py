@@ -79,6 +79,29 @@ def test_softmax_ce_and_domain_labels():
     assert_close(ops.domain_cross_entropy(d.cuda(), 120), F.cross_entropy(d, lab), 1e-5, "domain ce")
 
 
+@pytest.mark.parametrize("c", [64, 65, 100, 1000])
+def test_softmax_ce_many_classes_and_bad_labels(c):
+    """More than 64 classes take the warp-per-row kernel (the reference supports any num_classes); a label
+    outside [0, C) raises like F.nll_loss does instead of indexing out of bounds."""
+    from pygda_b200 import ops
+    g = torch.Generator().manual_seed(c)
+    z = torch.randn(513, c, generator=g) * 3
+    y = torch.randint(c, (513,), generator=g)
+    zr = z.clone().requires_grad_(True)
+    ref = F.nll_loss(F.log_softmax(zr, dim=1), y)
+    ref.backward()
+    zg = z.cuda().requires_grad_(True)
+    loss = ops.softmax_cross_entropy(zg, y.cuda())
+    loss.backward()
+    assert_close(loss, ref, 1e-5, f"ce, C={c}")
+    assert_close(zg.grad, zr.grad, 1e-5, f"ce grad, C={c}")
+    for bad in (-100, -1, c):
+        yb = y.clone()
+        yb[7] = bad
+        with pytest.raises(IndexError):
+            ops.softmax_cross_entropy(z.cuda(), yb.cuda())
+
+
 def test_softmax_entropy():
     from pygda_b200 import ops
     z = torch.randn(700, 6) * 4

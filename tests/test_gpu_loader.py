@@ -8,27 +8,55 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_device_collation_equals_from_data_list():
+def test_device_collation_equals_the_oracle_collation():
+    """Device collation (gda_collate_graphs) and the host ``Batch.from_data_list`` against the ORACLE's restatement of
+    PyG's ``Batch.from_data_list`` / ``DataLoader`` (oracle/data.py: collate_graphs, GraphDataLoader) -- bit-exact."""
+    from oracle import data as OD
     from pygda_b200.data import Batch, DataLoader, DeviceGraphDataset
     from pygda_b200.synthetic import graph_dataset
     ds = graph_dataset(200, 30, 2.05, 14, 2, seed=0)
+    ods = [OD.Data(x=d.x, edge_index=d.edge_index, y=d.y) for d in ds]
     res = DeviceGraphDataset(ds, "cuda:0")
     g = torch.Generator().manual_seed(1)
     for ids in ([0], [199, 0, 57], torch.randperm(200, generator=g)[:64].tolist(), list(range(200))):
-        got = res.collate(ids)
-        ref = Batch.from_data_list([ds[i] for i in ids])
-        assert torch.equal(got.x.cpu(), ref.x) and torch.equal(got.edge_index.cpu(), ref.edge_index)   # bit-exact
-        assert torch.equal(got.y.cpu(), ref.y) and torch.equal(got.batch.cpu(), ref.batch)
-        assert torch.equal(got.ptr.cpu(), ref.ptr) and len(got) == len(ref) == len(ids)
-    # the loader: same shuffle order as the host path for the same CPU seed
+        ref = OD.collate_graphs([ods[i] for i in ids])
+        ptr = torch.zeros(len(ids) + 1, dtype=torch.long)
+        ptr[1:] = torch.cumsum(torch.tensor([ods[i].x.size(0) for i in ids]), 0)
+        for got in (res.collate(ids), Batch.from_data_list([ds[i] for i in ids])):
+            assert torch.equal(got.x.cpu(), ref.x) and torch.equal(got.edge_index.cpu(), ref.edge_index)   # bit-exact
+            assert torch.equal(got.y.cpu(), ref.y) and torch.equal(got.batch.cpu(), ref.batch)
+            assert torch.equal(got.ptr.cpu(), ptr) and len(got) == len(ref) == len(ids)
+    # the loaders: the oracle's shuffle order and batches for the same CPU seed, host and device path
+    torch.manual_seed(3)
+    ora = [b for b in OD.GraphDataLoader(ods, batch_size=64, shuffle=True)]
     torch.manual_seed(3)
     host = [b for b in DataLoader(ds, batch_size=64, shuffle=True)]
     torch.manual_seed(3)
     dev = [b for b in DataLoader(ds, batch_size=64, shuffle=True, device="cuda:0")]
-    assert len(host) == len(dev) == 4
-    for h, d in zip(host, dev):
-        assert d.x.is_cuda and torch.equal(d.x.cpu(), h.x) and torch.equal(d.edge_index.cpu(), h.edge_index)
-        assert torch.equal(d.y.cpu(), h.y)
+    assert len(ora) == len(host) == len(dev) == 4
+    for o, h, d in zip(ora, host, dev):
+        for b in (h, d):
+            assert torch.equal(b.x.cpu(), o.x) and torch.equal(b.edge_index.cpu(), o.edge_index)
+            assert torch.equal(b.y.cpu(), o.y) and torch.equal(b.batch.cpu(), o.batch) and len(b) == len(o)
+        assert d.x.is_cuda
+
+
+def test_full_batch_loader_equals_the_oracle_loader():
+    """NeighborLoader in full-batch mode (edges regrouped by destination, node order kept, extra attributes carried)
+    against oracle/data.py: FullBatchNeighborLoader -- index arrays bit-exact, on host and on device-resident input."""
+    from oracle import data as OD
+    from pygda_b200.data import Data, NeighborLoader
+    from pygda_b200.synthetic import citation_graph
+    d = citation_graph(3000, 24000, 40, 4, seed=9)
+    w = torch.rand(d.edge_index.size(1))
+    ref = next(iter(OD.FullBatchNeighborLoader(OD.Data(x=d.x, edge_index=d.edge_index, y=d.y, edge_weight=w,
+                                                       note="kept"))))
+    for dev in ("cpu", "cuda:0"):
+        src = Data(x=d.x, edge_index=d.edge_index, y=d.y, edge_weight=w, note="kept").to(dev)
+        got = next(iter(NeighborLoader(src, [-1, -1], batch_size=3000)))
+        assert torch.equal(got.edge_index.cpu(), ref.edge_index) and torch.equal(got.edge_weight.cpu(), ref.edge_weight)
+        assert torch.equal(got.x.cpu(), ref.x) and torch.equal(got.y.cpu(), ref.y) and got.note == "kept"
+        assert len(got) == len(ref) == 1
 
 
 @pytest.mark.parametrize("rows,c", [(1, 2), (1000, 5), (100_000, 5), (5000, 64)])

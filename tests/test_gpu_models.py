@@ -74,3 +74,28 @@ def test_grade_fit_predict_graph_mode():
     model.fit(src, tgt)
     logits, labels = model.predict(None)
     assert logits.shape == (48, 2) and labels.shape == (48,)
+
+
+def test_adam_step_counters_follow_each_parameters_own_history():
+    """torch.optim.Adam keeps `step` per parameter, creates state at the first gradient and skips parameters without
+    one: a parameter that joins late, or misses a step, must get ITS bias corrections."""
+    from pygda_b200.optim import Adam
+    torch.manual_seed(0)
+    shapes = [(7, 5), (5,), (3, 4)]
+    ours = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in ours]
+    o1 = Adam(ours, lr=0.05, weight_decay=0.01)
+    o2 = torch.optim.Adam(ref, lr=0.05, weight_decay=0.01)
+    live = [(0, 1), (0, 1, 2), (0, 2), (0, 1, 2), (), (1, 2)]          # which parameters get a gradient at each step
+    g = torch.Generator().manual_seed(1)
+    for step, idx in enumerate(live):
+        for ps in (ours, ref):
+            for p in ps:
+                p.grad = None
+        for i in idx:
+            grad = torch.randn(shapes[i], generator=g).cuda()
+            ours[i].grad, ref[i].grad = grad.clone(), grad.clone()
+        o1.step()
+        o2.step()
+        for i, (a, b) in enumerate(zip(ours, ref)):
+            assert_close(a, b, 1e-5, f"parameter {i} after step {step}")
