@@ -653,12 +653,285 @@ def run_gpu_arm(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ BASELINE configs 3 / 4 / 5 (parity-test cases)
+def _peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def _timed_steps(step, warmup, steps, dev, distributed):
+    """`warmup` untimed + `steps` timed calls of step(i); ms per step, max over ranks (CUDA events)."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        step(i)
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = step(warmup + i)
+    e1.record()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps, out
+
+
+def _aggregation_profile(step, n_steps, match):
+    """Per-launch CUDA-event times of the aggregation launches whose profile record satisfies `match(meta)`."""
+    import torch
+    from pygda_b200 import ops
+    ops.PROFILE = []
+    for i in range(n_steps):
+        step(10_000 + i)
+    torch.cuda.synchronize()
+    recs, ops.PROFILE = ops.PROFILE, None
+    return [a.elapsed_time(b) for a, b, meta in recs if match(meta)]
+
+
+def run_config3(dev, steps=10, warmup=3, nodes=1_000_000, edges=10_000_000):
+    """BASELINE.json configs[2]: UDAGCN (GRL + discriminator, ppmi=False), per domain 1M nodes / 10M directed edges /
+    512 features / 5 classes, hid 256, 2 layers, bf16 feature path (fp32 parameters / accumulation / losses), one B200;
+    hyper-parameters of benchmark/node/run_citation.sh:90 (lr 1e-4, wd 1e-3, 400 epochs)."""
+    import itertools
+    import torch
+    from pygda_b200.data import Data
+    from pygda_b200.graph import Graph, clear_graph_cache
+    from pygda_b200.models import UDAGCN
+    from pygda_b200.optim import Adam
+    from pygda_b200.synthetic import bow_features, powerlaw_edge_index_device
+    F_, H, C = 512, 256, 5
+    g = torch.Generator().manual_seed(3)
+
+    def domain(seed, shift, offset):
+        x = bow_features(nodes, F_, seed=seed + 1000, shift=shift, device=dev)
+        x._gda_const = True
+        return Data(x=x, edge_index=powerlaw_edge_index_device(nodes, edges, seed=seed, offset=offset, device=dev),
+                    y=torch.randint(C, (nodes,), generator=g).to(dev))
+    src, tgt = domain(30, 1.5, 32.0), domain(31, 1.4, 48.0)
+    torch.manual_seed(0)
+    est = UDAGCN(in_dim=F_, hid_dim=H, num_classes=C, num_layers=2, ppmi=False, lr=1e-4, weight_decay=1e-3,
+                 epoch=400, device=str(dev), verbose=0, feature_dtype=torch.bfloat16)
+    est.udagcn = est.init_model()
+    opt = Adam(itertools.chain(*[m.parameters() for m in est.udagcn.models]), lr=1e-4, weight_decay=1e-3)
+    step = lambda i: est.train_step(src, tgt, min((i % 400 + 1) / 400.0, 0.05), i % 400, opt)[0]   # noqa: E731
+    ms, loss = _timed_steps(step, warmup, steps, dev, False)
+    tm = _aggregation_profile(step, 3, lambda m: m[:3] == (nodes, H, "bfloat16"))
+    gr = Graph(tgt.edge_index, nodes, None, 1 | 8)               # SELF_LOOPS | NORM_SYM_ROW, as CachedGCNConv builds it
+    b_alg = 4 * (nodes + 1) + 8 * gr.nnz + 2 * 2 * nodes * H
+    us = statistics.mean(tm) * 1e3 if tm else float("nan")
+    peak, src_ = _peak_hbm()
+    out = {"config": 3, "workload": "UDAGCN synthetic %dM nodes / %dM edges / %d feat, hid %d, bf16 features, 1 x B200 "
+                                    "(BASELINE.json configs[2])" % (nodes // 10**6, edges // 10**6, F_, H),
+           "metric": "udagcn_train_epochs_per_sec", "value": 1e3 / ms, "unit": "epochs/s", "ms_per_step": ms,
+           "steps": steps, "warmup": warmup, "dtype": "bf16 features, f32 parameters/accumulation", "loss": float(loss),
+           "parity_note": "bf16 feature path: outputs within 1e-2, gradients by Frobenius norm (tests/test_gpu_bf16.py); "
+                          "the 1e-4 bar applies to the fp32 path",
+           "roofline": {"bound": "hbm", "kernel": "k_spmm_tasks<bf16,8,...> (H=256 bf16, N=%d, nnz=%d)" % (nodes, gr.nnz),
+                        "alg_bytes_per_launch": b_alg, "us_per_launch": us, "achieved": b_alg / us / 1e3, "peak": peak,
+                        "unit": "GB/s", "frac": b_alg / us / 1e3 / peak, "peak_source": src_,
+                        "gathered_GBps": 2 * gr.nnz * H / us / 1e3, "launches_per_step": len(tm) / 3.0,
+                        "working_set_note": "1.1 GB per launch: far beyond the 126 MB L2, the gathers are served by HBM"},
+           "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
+    del est, opt, src, tgt, gr
+    clear_graph_cache()
+    from pygda_b200 import ops
+    ops.split_cache.clear(); ops.bf16_cache.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config4(dev, rank, world, group, steps=5, warmup=2, nodes=5_000_000, edges=50_000_000):
+    """BASELINE.json configs[3]: GRADE (Gaussian-MMD), per domain 5M nodes / 50M directed edges / 256 features / 5
+    classes, hid 128, 2 layers (grade.py:68 default; run_citation.sh:85 uses 5), fp32, 1-D node partition over `world`
+    GPUs of a RANDOM graph (node ids shuffled: no locality, (world-1)/world of the gathered rows are remote)."""
+    import torch
+    from pygda_b200.data import Data
+    from pygda_b200.graph import clear_graph_cache
+    from pygda_b200.models import GRADE
+    from pygda_b200.optim import Adam
+    from pygda_b200.synthetic import bow_features, powerlaw_edge_index_device
+    F_, H, C = 256, 128, 5
+    hp = dict(in_dim=F_, hid_dim=H, num_classes=C, num_layers=2, dropout=0.5, disc="MMD", weight=0.002,
+              weight_decay=0.0, lr=0.001, epoch=300, device=str(dev), verbose=0)
+    distributed = world > 1
+    lo, hi = (0, nodes)
+    if distributed:
+        from pygda_b200.dist import attach_partition, block_range
+        from pygda_b200.models.dist_grade import DistGRADE
+        lo, hi = block_range(nodes, world, rank)
+    gl = torch.Generator().manual_seed(4)
+
+    def domain(seed, shift, offset):
+        ei = powerlaw_edge_index_device(nodes, edges, seed=seed, offset=offset, device=dev)
+        x = bow_features(hi - lo, F_, seed=seed + 1000 + rank, shift=shift, device=dev)
+        x._gda_const = True
+        y = torch.randint(C, (nodes,), generator=gl)[lo:hi].to(dev)
+        d = Data(x=x, edge_index=ei, y=y)
+        if distributed:
+            d.num_nodes_global, d.row_lo, d.row_hi = nodes, lo, hi
+            d = attach_partition(d, group)
+        return d
+    src, tgt = domain(40, 1.5, 32.0), domain(41, 1.4, 48.0)
+    rpr = (nodes + world - 1) // world
+    remote_frac = float(((tgt.edge_index[0] // rpr) != (tgt.edge_index[1] // rpr)).float().mean()) if distributed else 0.0
+    # non-zeros of this rank's row block whose column lives on another GPU (target graph; self loops are local)
+    own = (tgt.edge_index[1] >= lo) & (tgt.edge_index[1] < hi)
+    remote_nnz = int((own & ((tgt.edge_index[0] // rpr) != rank)).sum()) if distributed else 0
+    local_nnz = int(own.sum()) + (hi - lo)
+    del own
+    torch.manual_seed(0)
+    model = DistGRADE(group=group, **hp) if distributed else GRADE(**hp)
+    model.grade = model.init_model()
+    opt = Adam(model.grade.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    E_ = hp["epoch"]
+    import numpy as np
+    step = lambda i: model.train_step(src, tgt, 2. / (1. + np.exp(-10. * (i % E_) / E_)) - 1, opt)[0]   # noqa: E731
+    ms, loss = _timed_steps(step, warmup, steps, dev, distributed)
+    tm = _aggregation_profile(step, 2, lambda m: m[0] == hi - lo and m[1] == H)
+    us = statistics.mean(tm) * 1e3 if tm else float("nan")
+    b_alg = 4 * (hi - lo + 1) + 8 * local_nnz + 2 * 4 * (hi - lo) * H
+    peak, src_ = _peak_hbm()
+    # per step and GPU: 2 domains x 2 layers x (forward + backward) aggregations; layer widths H (hidden) and C (5 -> the
+    # classifier is a Linear in GRADE, not a conv), so all 8 launches gather H-wide rows
+    nvlink_per_launch = remote_nnz * 4 * H
+    out = {"config": 4, "workload": "GRADE (Gaussian-MMD) synthetic %dM nodes / %dM edges / %d feat, hid %d, fp32, 1-D node "
+                                    "partition over %d x B200, RANDOM graph (no partition locality) "
+                                    "(BASELINE.json configs[3])" % (nodes // 10**6, edges // 10**6, F_, H, world),
+           "metric": "grade_train_epochs_per_sec", "value": 1e3 / ms, "unit": "epochs/s", "ms_per_step": ms, "n_gpus": world,
+           "steps": steps, "warmup": warmup, "dtype": "f32", "scaling": "strong (one graph pair split over the GPUs)",
+           "loss": float(loss),
+           "partition": {"rows_per_gpu": hi - lo, "local_nnz_target_graph": local_nnz,
+                         "remote_column_fraction": remote_frac, "remote_nnz_per_launch_this_gpu": remote_nnz,
+                         "nvlink_bytes_per_aggregation_launch_per_gpu": nvlink_per_launch,
+                         "nvlink_bytes_per_step_per_gpu_estimate": 8 * nvlink_per_launch,
+                         "nvlink_floor_ms_per_step_at_900GBps": 8 * nvlink_per_launch / 900e9 * 1e3,
+                         "comm_bound_fraction_of_step": min(1.0, 8 * nvlink_per_launch / 900e9 * 1e3 / ms)},
+           "roofline": {"bound": "hbm" if not distributed else "nvlink (remote gathers) / hbm (local)",
+                        "kernel": "aggregation at H=%d on this GPU's row block (target graph)" % H,
+                        "alg_bytes_per_launch": b_alg, "us_per_launch": us, "achieved": b_alg / us / 1e3, "peak": peak,
+                        "unit": "GB/s", "frac": b_alg / us / 1e3 / peak, "peak_source": src_,
+                        "launches_profiled_per_step": len(tm) / 2.0},
+           "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
+    del model, opt, src, tgt
+    clear_graph_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config5(dev, rank, world, group, steps=20, warmup=3, graphs=50_000, batch=512):
+    """BASELINE.json configs[4]: AdaGCN graph-level, Mutagenicity -> PROTEINS-shaped synthetic datasets of 50k graphs
+    per domain (source ~Poisson(30) nodes, 2.05 directed edges per node; target ~Poisson(39), 3.7), 14 one-hot features,
+    2 classes, DataLoader(batch_size=512, shuffle=True), hyper-parameters of benchmark/graph/run_all_M.sh:2; data
+    parallel over `world` GPUs (every mini-batch's graphs split over the ranks)."""
+    import torch
+    import torch.distributed as dist
+    from pygda_b200.data import DataLoader, DeviceGraphDataset
+    from pygda_b200.dist import shard_batch
+    from pygda_b200.models import AdaGCN
+    from pygda_b200.optim import Adam
+    from pygda_b200.synthetic import graph_dataset
+    distributed = world > 1
+    hp = dict(in_dim=14, hid_dim=128, num_classes=2, mode="graph", num_layers=2, dropout=0.4, gnn_type="gcn", adv_dim=40,
+              gp_weight=5.0, domain_weight=0.1, weight_decay=0.01, lr=0.01, epoch=400, device=str(dev), batch_size=batch,
+              verbose=0)
+    t0 = time.perf_counter()
+    ds_s = DeviceGraphDataset(graph_dataset(graphs, 30, 2.05, 14, 2, seed=50), dev)
+    ds_t = DeviceGraphDataset(graph_dataset(graphs, 39, 3.7, 14, 2, seed=51), dev)
+    t_gen = time.perf_counter() - t0
+    torch.manual_seed(0)
+    if distributed:
+        from pygda_b200.models.dist_adagcn import DistAdaGCN
+        model = DistAdaGCN(pg=group.pg, **hp)
+    else:
+        model = AdaGCN(**hp)
+    model.adagcn = model.init_model()
+    opt = Adam(model.adagcn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    model.init_critic()
+    torch.manual_seed(1234)                                   # every rank iterates the same shuffled batches
+    loaders = (DataLoader(ds_s, batch_size=batch, shuffle=True, device=dev),
+               DataLoader(ds_t, batch_size=batch, shuffle=True, device=dev))
+    it = [None]
+
+    def batches():
+        while True:
+            for sb, tb in zip(*loaders):
+                yield sb, tb
+
+    def step(i):
+        if it[0] is None:
+            it[0] = batches()
+        sb, tb = next(it[0])
+        if distributed:
+            sb, tb = shard_batch(sb, rank, world), shard_batch(tb, rank, world)
+        return model.train_step(sb, tb, opt)[0]
+    from pygda_b200._lib import load
+    lib = load()
+    ms_warm, _ = _timed_steps(step, warmup, 1, dev, distributed)
+    n0 = lib.gda_launch_count()
+    host0 = time.perf_counter()
+    ms, loss = _timed_steps(step, 0, steps, dev, distributed)
+    host_ms = (time.perf_counter() - host0) * 1e3 / steps
+    launches = (lib.gda_launch_count() - n0) / steps
+    out = {"config": 5, "workload": "AdaGCN graph-level synthetic Mutagenicity->PROTEINS-shape, %dk graphs per domain, batch "
+                                    "%d, %d x B200 data parallel (BASELINE.json configs[4])" % (graphs // 1000, batch, world),
+           "metric": "adagcn_train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s (one step = one mini-batch of %d "
+           "graphs per domain: 10 critic iterations + 1 encoder update)" % batch, "ms_per_step": ms, "n_gpus": world,
+           "graphs_per_sec": 2 * batch * 1e3 / ms, "epochs_per_sec": 1e3 / ms / ((graphs + batch - 1) // batch),
+           "steps": steps, "warmup": warmup, "dtype": "f32", "scaling": "strong (each mini-batch split over the GPUs)",
+           "loss": float(loss), "gda_launches_per_step": launches, "host_ms_per_step": host_ms,
+           "critic": "closed-form WGAN-GP on libgda (ops.linear / ops.matmul), libgda Adam" if model.analytic_critic
+           else "torch double backward", "dataset_seconds": t_gen,
+           "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
+    del model, opt, ds_s, ds_t, loaders
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_other_config(args, rank, world, local_rank):
+    """`--config 3|4|5`: one JSON line for that BASELINE configuration (builder-run; the driver times config 2)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from pygda_b200.dist import PeerGroup
+        group = PeerGroup(device=dev)
+    if args.config == 3:
+        out = run_config3(dev, max(args.steps, 1), max(args.warmup, 1)) if rank == 0 else None
+    elif args.config == 4:
+        out = run_config4(dev, rank, world, group, max(args.steps, 1), max(args.warmup, 1))
+    else:
+        out = run_config5(dev, rank, world, group, max(args.steps, 1), max(args.warmup, 1))
+    if rank == 0 and out is not None:
+        out.update({"higher_is_better": True, "data": "synthetic", "vs_baseline": None})
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configuration: 2 = the metric's (default, what the driver times); 3 = UDAGCN 1M/10M "
+                         "bf16 on one GPU; 4 = GRADE-MMD 5M/50M over --gpus GPUs (random partition); 5 = AdaGCN graph-level "
+                         "50k graphs / batch 512 over --gpus GPUs")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the side measurements of configs 3 / 4 / 5 the default run appends (other_configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-scale", type=int, default=1,
                     help="tests only: run the reference arm on a 1/SCALE graph pair (the line says so); default full scale")
@@ -670,6 +943,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.config != 2:
+        run_other_config(args, rank, world, local_rank)
         return
     run_gpu_arm(args, rank, world, local_rank)
     if world > 1:

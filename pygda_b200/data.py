@@ -109,6 +109,9 @@ class Data:
             xd._gda_key = getattr(xsrc, "_gda_key", None) or (
                 "src", xsrc.data_ptr(), xsrc._version, tuple(xsrc.shape), str(xsrc.device))
             xd._gda_keepalive = getattr(xsrc, "_gda_keepalive", xsrc)
+        yd, ysrc = out.__dict__.get("y"), self.__dict__.get("y")
+        if torch.is_tensor(yd) and yd is not ysrc and torch.is_tensor(ysrc):
+            yd._gda_src = ysrc                      # label-range validation is remembered on the host tensor (ops)
         ew, wsrc = out.__dict__.get("edge_weight"), self.__dict__.get("edge_weight")
         if torch.is_tensor(ew) and ew is not wsrc:
             # same for per-edge weights (StruRW): the re-weighted CSR is keyed by the host tensor they came from

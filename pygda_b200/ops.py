@@ -811,14 +811,12 @@ class GradReverse(torch.autograd.Function):
         return scale(g, -float(ctx.alpha)), None
 
 
-_LABELS_OK = {}
-
-
 def _validate_labels(labels, c):
     """F.nll_loss raises for a target outside [0, C) (pygda/models/a2gnn.py:182); so does this path -- once per label
-    tensor (the labels of a full-batch fit are the same tensor every step), so no per-step host synchronisation."""
-    key = (labels.data_ptr(), labels._version, labels.numel(), int(c))
-    if _LABELS_OK.get(key):
+    tensor OBJECT (and per host tensor it was copied from, ``Data.to`` links the two): the labels of a full-batch fit
+    are the same tensor every step, so there is no per-step host synchronisation."""
+    src = getattr(labels, "_gda_src", None)
+    if getattr(labels, "_gda_labels_ok", None) == c or (src is not None and getattr(src, "_gda_labels_ok", None) == c):
         return
     if torch.cuda.is_current_stream_capturing():
         return                                           # validated by the warm-up step that precedes every capture
@@ -826,9 +824,9 @@ def _validate_labels(labels, c):
         lo, hi = int(labels.min()), int(labels.max())
         if lo < 0 or hi >= c:
             raise IndexError(f"Target {lo if lo < 0 else hi} is out of bounds.")
-    if len(_LABELS_OK) > 64:
-        _LABELS_OK.clear()
-    _LABELS_OK[key] = True
+    labels._gda_labels_ok = c
+    if src is not None:
+        src._gda_labels_ok = c
 
 
 class SoftmaxCEFn(torch.autograd.Function):
