@@ -180,6 +180,23 @@ int gda_spmm_peer_k_dev_f32(const gda_graph_t* part, int transpose, int k, const
                             uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag, gda_stream_t stream);
 int gda_peer_barrier_dev(uint64_t* const* peer_flags, int rank, int num_peers, uint64_t* epoch_dev,
                          int* error_flag, gda_stream_t stream);
+/* PUSH mode for partitions with little locality (a random graph over P GPUs references (P-1)/P of its columns on other
+ * GPUs): every rank keeps a full local copy of the (padded) global matrix in a symmetric GATHER buffer
+ * [num_peers * rows_per_rank, H]; an aggregation gathers from that local copy and stores each output row into block
+ * `my_rank` of the next gather buffer on EVERY rank (P2P stores over NVLink inside the kernel), so the exchange is
+ * fused into the producer, overlaps its gathers and moves each row once per peer as coalesced 512-byte stores --
+ * instead of one remote 512-byte load per referencing non-zero (gda_spmm_peer_f32).  gda_spmm_push_f32: one step
+ * (gather_local = this rank's copy; out_blocks[0..num_out) = where each output row goes, pre-offset to this rank's
+ * block); gda_spmm_push_k_f32: barrier, copy-in to every rank, k x (barrier, step), the last step writing Y. */
+int gda_spmm_push_f32(const gda_graph_t* part, int transpose, const void* gather_local, void* const* out_blocks,
+                      int num_out, int num_peers, int64_t ldx, int64_t ldy, int H, const float* bias, int epi_flags,
+                      float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                      int64_t workspace_bytes, gda_stream_t stream);
+int gda_spmm_push_k_f32(const gda_graph_t* part, int transpose, int k, const float* x_local, void* const* gbuf0,
+                        void* const* gbuf1, int num_peers, int my_rank, float* Y, int H, const float* bias,
+                        int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                        int64_t workspace_bytes, uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag,
+                        gda_stream_t stream);
 int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
 int gda_sym_open(const unsigned char* handle /* 64 bytes */, void** ptr);
 int gda_sym_close(void* ptr);
@@ -412,6 +429,13 @@ int gda_collate_graphs(const float* x_all, int F, const int64_t* edge_index_all,
  * The reference moves every batch host->device on every step (`.to(self.device)`, pygda/models/a2gnn.py:311-312);
  * for bag-of-words features (a few per cent non-zero) the pinned staging copy is kept compressed
  * (pygda_b200.data.Data.pin_memory) and only the non-zeros cross PCIe. */
+/* gda_unpack_rows_delta_f32: the same from DELTA-coded column ids, one byte per entry (half the index bytes of the
+ * uint16 form): per row the running column starts at 0, every byte adds its value, a byte of 255 only advances
+ * (escape), any other byte emits the row's next value at the running column.  val_ptr / byte_ptr int32 [N + 1] are
+ * the row offsets into vals / deltas.  *error_flag (device int, may be NULL) is set if a column lands outside F. */
+int gda_unpack_rows_delta_f32(const float* vals, const uint8_t* deltas, const int32_t* val_ptr,
+                              const int32_t* byte_ptr, int64_t N, int64_t F, float* out, int64_t ldo,
+                              int* error_flag, gda_stream_t stream);
 int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, const int64_t* rowptr, int64_t N,
                         int64_t F, float* out, int64_t ldo, gda_stream_t stream);
 /* gda_argmax_confusion: pred[r] = argmax_c logits[r, c] (first maximal index) and counts[y * C + p] += 1

@@ -44,6 +44,9 @@ SIGNATURES = {
     "gda_spmm_peer_k_dev_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
                                       vp, vp, vp, vp]),
     "gda_peer_barrier_dev": (i32, [vp, i32, i32, vp, vp, vp]),
+    "gda_spmm_push_f32": (i32, [vp, i32, vp, vp, i32, i32, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_push_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp, vp, vp,
+                                  vp]),
     "gda_spmm_bf16": (i32, [vp, i32, vp, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_graph_partition": (i32, [vp, i64, i64, i64, vp, C.POINTER(vp)]),
     "gda_spmm_peer_f32": (i32, [vp, i32, vp, i32, i32, i64, vp, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
@@ -96,6 +99,7 @@ SIGNATURES = {
     "gda_wedges_export": (i32, [vp, vp, vp, vp, vp]),
     "gda_wedges_destroy": (i32, [vp]),
     "gda_collate_graphs": (i32, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
+    "gda_unpack_rows_delta_f32": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gda_unpack_rows_f32": (i32, [vp, vp, i32, vp, i64, i64, vp, i64, vp]),
     "gda_argmax_confusion": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),

@@ -71,6 +71,42 @@ __global__ void k_unpack_rows(const float* __restrict__ vals, const CI* __restri
   }
 }
 
+// The same from DELTA-coded column ids, one byte per entry: within a row the running column starts at 0 and every byte
+// adds its value; a byte of 255 only advances (escape), any other byte b advances by b and emits the row's next value.
+// One warp per row, 32 bytes per round: inclusive scan of the increments, ballot / popcount for the rank of the
+// emitting bytes.  Half the index bytes of the uint16 form (bag-of-words rows have gaps of ~1/density << 255).
+__global__ void k_unpack_rows_delta(const float* __restrict__ vals, const uint8_t* __restrict__ deltas,
+                                    const int32_t* __restrict__ val_ptr, const int32_t* __restrict__ byte_ptr,
+                                    int64_t N, int64_t F, int64_t ldo, float* __restrict__ out, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < N; r += nwarps) {
+    const int b0 = __ldg(byte_ptr + r), b1 = __ldg(byte_ptr + r + 1);
+    const float* __restrict__ v = vals + __ldg(val_ptr + r);
+    float* __restrict__ row = out + r * ldo;
+    int col = 0, cnt = 0;
+    for (int base = b0; base < b1; base += 32) {
+      const bool valid = base + lane < b1;
+      const int byte = valid ? static_cast<int>(__ldg(deltas + base + lane)) : 0;
+      int incl = byte;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const bool emit = valid && byte != 255;
+      const unsigned m = __ballot_sync(0xffffffffu, emit);
+      if (emit) {
+        const int c = col + incl;
+        if (c < F) row[c] = __ldg(v + cnt + __popc(m & ((1u << lane) - 1u)));
+        else if (err) *err = 1;
+      }
+      col += __shfl_sync(0xffffffffu, incl, 31);
+      cnt += __popc(m);
+    }
+  }
+}
+
 constexpr int kMaxClasses = 64;
 
 // argmax (first maximal index, like torch.argmax on the CPU) + confusion counts[label * C + pred]
@@ -172,6 +208,26 @@ int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, cons
   else
     k_unpack_rows<int32_t><<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, static_cast<const int32_t*>(cols), rowptr, N,
                                                                          ldo, out);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_unpack_rows_delta_f32(const float* vals, const uint8_t* deltas, const int32_t* val_ptr, const int32_t* byte_ptr,
+                              int64_t N, int64_t F, float* out, int64_t ldo, int* error_flag, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(N >= 0 && F >= 0 && ldo >= F, "gda_unpack_rows_delta_f32: bad size");
+  if (N == 0 || F == 0) return GDA_OK;
+  GDA_REQUIRE(val_ptr && byte_ptr && out, "gda_unpack_rows_delta_f32: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  if (ldo == F) {
+    GDA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(N) * F, st));
+  } else {
+    GDA_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * F, static_cast<size_t>(N), st));
+  }
+  int64_t blocks = ceil_div(N, 8);
+  if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+  k_unpack_rows_delta<<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, deltas, val_ptr, byte_ptr, N, F, ldo, out,
+                                                                     error_flag);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

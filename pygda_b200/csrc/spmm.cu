@@ -663,14 +663,20 @@ __device__ __forceinline__ void gather_batch(float (&acc)[NB][VEC], int myc, flo
 
 // NB > 1: NB feature matrices (xbsb / ybsb bytes apart, `nrows` rows each) share the graph -- one index read and one
 // dependency chain per row for NB gathers (the two bottleneck evaluations of a domain, models/a2gnn.py).
-template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER, int NB>
+// PUSH (partitioned graphs with little locality, dist.py): the output row is stored into the row block of this rank
+// inside EVERY rank's gather buffer (outs.p[q], P2P stores over NVLink), so that the next propagation step gathers
+// from local memory only -- the exchange is fused into the producer and overlaps its gathers row by row, and it moves
+// each row once per peer in bulk-friendly 512-byte stores instead of once per referencing non-zero as a remote load.
+template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER, int NB, bool PUSH = false>
 __global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
 k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
              const float* __restrict__ vals, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
              const int* __restrict__ seg_long, int* __restrict__ counters,
              const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int H,
-             Epilogue epi, float* __restrict__ partial, PeerTable peers, uint64_t xbsb, uint64_t ybsb, int nrows) {
+             Epilogue epi, float* __restrict__ partial, PeerTable peers, uint64_t xbsb, uint64_t ybsb, int nrows,
+             PeerTable outs = PeerTable{}, int nout = 0) {
   static_assert(NB == 1 || !PEER, "batched form is local only");
+  static_assert(!PUSH || (PEER && NB == 1), "push mode is the partitioned single-matrix form");
   static_assert(U == 4 || U == 8, "batch depth");
   const int lane = threadIdx.x & 31;
   const int c0 = lane * VEC;
@@ -741,7 +747,13 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         if (EPI) apply_epilogue<VEC>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
-        VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+        if (PUSH) {
+          for (int q = 0; q < nout; ++q)
+            VecIO<T, VEC>::store(reinterpret_cast<T*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(T) +
+                                                      static_cast<uint64_t>(row) * ldyb), acc[b]);
+        } else {
+          VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+        }
       }
     } else {                                             // segment of a long row: ordered reduction by the last arrival
       const int sgid = static_cast<int>(cur.y & 0x01FFFFFFu);
@@ -770,7 +782,13 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
             for (int v = 0; v < VEC; ++v) acc[b][v] += __ldcg(srcp + v);
           }
           if (EPI) apply_epilogue<VEC>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
-          VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+          if (PUSH) {
+            for (int q = 0; q < nout; ++q)
+              VecIO<T, VEC>::store(reinterpret_cast<T*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(T) +
+                                                        static_cast<uint64_t>(row) * ldyb), acc[b]);
+          } else {
+            VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+          }
         }
         if (lane == 0) counters[L] = 0;
       }
@@ -1129,6 +1147,39 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   return GDA_OK;
 }
 
+// Push-mode step over a partition (fp32, one 16-byte slice per lane): gathers from the LOCAL copy of the whole matrix
+// (`gather`: block q of every rank at gather.p[q]), stores every output row into outs.p[0 .. nout-1].
+int spmm_push(const gda_graph* g, int transpose, const PeerTable& gather, const PeerTable& outs, int nout, int64_t ldx,
+              int64_t ldy, int H, const Epilogue& epi, float* partial, int64_t workspace_bytes, cudaStream_t st) {
+  const Csr& c = transpose ? g->csr_t : g->csr;
+  bool wide_ok = H == 128 && ldx % 4 == 0 && ldy % 4 == 0;
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(gather.p[i]) % 16 == 0);
+  for (int i = 0; i < nout; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(outs.p[i]) % 16 == 0);
+  const bool on_tasks_path = tasks_path<float, 4>(c, H, wide_ok);
+  GDA_REQUIRE(on_tasks_path, "gda_spmm_push: needs H = 128 fp32, aligned buffers and a task list");
+  GDA_REQUIRE(g->rows_per_rank * ldx < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32), "gda_spmm_push: block too large");
+  const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
+  if (need > 0 && (partial == nullptr || workspace_bytes < need))
+    return fail(GDA_E_WORKSPACE, "gda_spmm_push: workspace smaller than gda_spmm_workspace_bytes()");
+  if (g->N == 0) return GDA_OK;
+  const unsigned ldxb = static_cast<unsigned>(ldx * sizeof(float)), ldyb = static_cast<unsigned>(ldy * sizeof(float));
+  int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
+  if (tb > static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS) tb = static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS;
+  const bool has_epi = epi.bias != nullptr || epi.flags != 0;
+  const float* X = static_cast<const float*>(gather.p[0]);
+  float* Y = static_cast<float*>(const_cast<void*>(outs.p[0]));
+  if (has_epi)
+    k_spmm_tasks<float, 4, 4, GDA_TASKS_MIN_CTAS, true, true, 1, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+        c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y, ldyb, H,
+        epi, partial, gather, 0, 0, static_cast<int>(g->N), outs, nout);
+  else
+    k_spmm_tasks<float, 4, 4, GDA_TASKS_MIN_CTAS, false, true, 1, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+        c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y, ldyb, H,
+        epi, partial, gather, 0, 0, static_cast<int>(g->N), outs, nout);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
 // true when the factored (weight-free) kernel can take a step over this graph at this width
 bool unw_path(const gda_graph* g, const Csr& c, int H, int64_t ldx, int64_t ldy, const float* X, const float* Y, int nb,
               int64_t xbs, int64_t ybs) {
@@ -1377,6 +1428,72 @@ int gda_spmm_peer_k_dev_f32(const gda_graph_t* part, int transpose, int k, const
     rc = gda_spmm_peer_f32(part, transpose, src, num_peers, my_rank, H, dst, H, H, last ? bias : nullptr,
                            last ? epi_flags : 0, last ? dropout_p : 0.f, seed, seed_offset, workspace,
                            workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return GDA_OK;
+}
+
+// ---- push mode: A_hat^k over a partition with the exchange fused into the producer (dist.py) ------------------------
+// gbuf0 / gbuf1: per-rank base pointers of two symmetric GATHER buffers, each [num_peers * rows_per_rank, H] fp32 -- a
+// full copy of the (padded) global matrix on every rank, block q = rank q's rows.  Step i gathers from the local copy
+// and stores each output row into block `my_rank` of the other buffer on EVERY rank (P2P stores); the last step writes
+// Y (local, plain).  Barriers (device epoch) order the steps.  One aggregation launch moves (num_peers - 1) x block
+// bytes over NVLink as coalesced 512-byte row stores, instead of one remote 512-byte load per referencing non-zero.
+int gda_spmm_push_f32(const gda_graph_t* part, int transpose, const void* gather_local, void* const* out_blocks,
+                      int num_out, int num_peers, int64_t ldx, int64_t ldy, int H, const float* bias, int epi_flags,
+                      float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                      int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(part && part->peer_packed && gather_local && out_blocks, "gda_spmm_push_f32: bad arguments");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS && num_out >= 1 && num_out <= GDA_MAX_PEERS,
+              "gda_spmm_push_f32: bad peer counts");
+  GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm_push_f32: dropout_p outside [0,1)");
+  gda::PeerTable gt, ot;
+  const char* base = static_cast<const char*>(gather_local);
+  for (int i = 0; i < GDA_MAX_PEERS; ++i)
+    gt.p[i] = base + static_cast<int64_t>(i < num_peers ? i : 0) * part->rows_per_rank * ldx * static_cast<int64_t>(sizeof(float));
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) {
+    ot.p[i] = out_blocks[i < num_out ? i : 0];
+    GDA_REQUIRE(ot.p[i] != nullptr, "gda_spmm_push_f32: NULL output block");
+  }
+  gda::Epilogue epi;
+  epi.bias = bias; epi.flags = epi_flags; epi.thresh = gda::dropout_threshold(dropout_p);
+  epi.scale = 1.0f / (1.0f - dropout_p); epi.seed = seed; epi.seed_offset = seed_offset;
+  return gda::spmm_push(part, transpose, gt, ot, num_out, ldx, ldy, H, epi, static_cast<float*>(workspace),
+                        workspace_bytes, gda::as_stream(stream));
+}
+
+int gda_spmm_push_k_f32(const gda_graph_t* part, int transpose, int k, const float* x_local, void* const* gbuf0,
+                        void* const* gbuf1, int num_peers, int my_rank, float* Y, int H, const float* bias,
+                        int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
+                        int64_t workspace_bytes, uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag,
+                        gda_stream_t stream) {
+  GDA_REQUIRE(part && part->peer_packed && k >= 1 && x_local && gbuf0 && gbuf1 && Y && epoch_dev,
+              "gda_spmm_push_k_f32: bad arguments");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS && my_rank >= 0 && my_rank < num_peers,
+              "gda_spmm_push_k_f32: bad peer arguments");
+  cudaStream_t st = gda::as_stream(stream);
+  const int64_t block_bytes = part->rows_per_rank * static_cast<int64_t>(H) * sizeof(float);
+  int rc = gda_peer_barrier_dev(peer_flags, my_rank, num_peers, epoch_dev, error_flag, stream);
+  if (rc) return rc;
+  for (int q = 0; q < num_peers; ++q)               // copy-in: this rank's rows into block my_rank of every gather buffer 0
+    GDA_CUDA(cudaMemcpyAsync(static_cast<char*>(gbuf0[q]) + my_rank * block_bytes, x_local, sizeof(float) * part->N * H,
+                             cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < k; ++i) {
+    const bool last = i == k - 1;
+    if ((rc = gda_peer_barrier_dev(peer_flags, my_rank, num_peers, epoch_dev, error_flag, stream))) return rc;
+    void* const* src = (i & 1) ? gbuf1 : gbuf0;
+    void* const* dstb = (i & 1) ? gbuf0 : gbuf1;
+    void* outs[GDA_MAX_PEERS];
+    int nout = 1;
+    if (last) {
+      outs[0] = Y;
+    } else {
+      nout = num_peers;
+      for (int q = 0; q < num_peers; ++q) outs[q] = static_cast<char*>(dstb[q]) + my_rank * block_bytes;
+    }
+    rc = gda_spmm_push_f32(part, transpose, src[my_rank], outs, nout, num_peers, H, H, H, last ? bias : nullptr,
+                           last ? epi_flags : 0, last ? dropout_p : 0.f, seed, seed_offset, workspace, workspace_bytes,
+                           stream);
     if (rc) return rc;
   }
   return GDA_OK;

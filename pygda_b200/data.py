@@ -15,51 +15,76 @@ import torch
 
 class PackedRows:
     """Row-compressed PINNED host copy of a sparse fp32 matrix (bag-of-words features are a few per cent
-    non-zero): values, column ids (uint16 when the width allows) and row pointers.  ``to_dense(device)`` copies
-    only these over PCIe and rebuilds the dense [N, F] matrix on the GPU bit for bit (``gda_unpack_rows_f32``;
-    an entry is kept iff its BIT PATTERN is non-zero, so -0.0 survives)."""
+    non-zero): the non-zero values and their DELTA-coded column ids, one byte per entry (within a row the running
+    column starts at 0, every byte adds its value, 255 is an escape that only advances) -- 5 bytes per non-zero
+    instead of the dense row.  ``to_dense(device)`` copies only these over PCIe and rebuilds the dense [N, F] matrix
+    on the GPU bit for bit (``gda_unpack_rows_delta_f32``; an entry is kept iff its BIT PATTERN is non-zero, so
+    -0.0 survives)."""
 
     def __init__(self, x, chunk=8192):
         n, f = x.shape
         x = x.contiguous()
-        vals, cols, counts = [], [], []
+        vals, deltas, counts, nbytes = [], [], [], []
         for s in range(0, n, chunk):
             blk = x[s:s + chunk]
             mask = blk.view(torch.int32) != 0
-            counts.append(mask.sum(1))
+            cnt = mask.sum(1)
+            col = mask.nonzero(as_tuple=True)[1]
             vals.append(blk[mask])
-            cols.append(mask.nonzero(as_tuple=True)[1])
-        rowptr = torch.zeros(n + 1, dtype=torch.int64)
-        if counts:
-            rowptr[1:] = torch.cumsum(torch.cat(counts), 0)
-        col = torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int64)
-        if f <= 65536:
-            self.col_bytes = 2
-            col = torch.from_numpy(col.numpy().astype(np.uint16).view(np.int16))
-        else:
-            self.col_bytes = 4
-            col = col.to(torch.int32)
+            counts.append(cnt)
+            # gap to the previous entry of the same row (to column 0 for a row's first entry)
+            d = col.clone()
+            if col.numel() > 1:
+                d[1:] -= col[:-1]
+            starts = (torch.cumsum(cnt, 0) - cnt)[cnt > 0]
+            d[starts] = col[starts]
+            width = 1 + d // 255                                  # escape bytes + the emitting byte
+            pos = torch.cumsum(width, 0) - 1
+            out = torch.full((int(width.sum()),), 255, dtype=torch.uint8)
+            out[pos] = (d % 255).to(torch.uint8)
+            deltas.append(out)
+            rows = torch.repeat_interleave(torch.arange(blk.size(0)), cnt)
+            nbytes.append(torch.zeros(blk.size(0), dtype=torch.int64).index_add_(0, rows, width))
+        def ptr(parts):
+            p = torch.zeros(n + 1, dtype=torch.int64)
+            if parts:
+                p[1:] = torch.cumsum(torch.cat(parts), 0)
+            return p
+        val_ptr, byte_ptr = ptr(counts), ptr(nbytes)
+        if int(byte_ptr[-1]) >= 2 ** 31:
+            raise ValueError("PackedRows: more than 2^31 packed bytes; pin_memory(pack=False) keeps the dense form")
         self.shape = (n, f)
         pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
         self.vals = pin(torch.cat(vals) if vals else torch.zeros(0))
-        self.cols = pin(col)
-        self.rowptr = pin(rowptr)
+        self.deltas = pin(torch.cat(deltas) if deltas else torch.zeros(0, dtype=torch.uint8))
+        self.val_ptr = pin(val_ptr.to(torch.int32))
+        self.byte_ptr = pin(byte_ptr.to(torch.int32))
+
+    def tensors(self):
+        """The pinned host arrays that cross PCIe, by staging name."""
+        return {"_vals": self.vals, "_deltas": self.deltas, "_val_ptr": self.val_ptr, "_byte_ptr": self.byte_ptr}
 
     @property
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.vals, self.cols, self.rowptr))
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
 
-    def to_dense(self, device, non_blocking=True):
+    def unpack_into(self, dev, out, stream=None):
+        """Rebuild the dense matrix in ``out`` [N, F] from DEVICE copies ``dev`` of ``tensors()`` (current stream)."""
         from ._lib import gda
         n, f = self.shape
+        p = lambda t: C.c_void_p(t.data_ptr())                    # noqa: E731
+        gda.unpack_rows_delta_f32(p(dev["_vals"]), p(dev["_deltas"]), p(dev["_val_ptr"]), p(dev["_byte_ptr"]), n, f,
+                                  p(out), f, C.c_void_p(0),
+                                  C.c_void_p((stream or torch.cuda.current_stream(out.device)).cuda_stream))
+
+    def to_dense(self, device, non_blocking=True):
+        n, f = self.shape
         dev = torch.device(device)
-        v, c, r = (t.to(dev, non_blocking=non_blocking) for t in (self.vals, self.cols, self.rowptr))
+        d = {k: t.to(dev, non_blocking=non_blocking) for k, t in self.tensors().items()}
         out = torch.empty(n, f, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            gda.unpack_rows_f32(C.c_void_p(v.data_ptr()), C.c_void_p(c.data_ptr()), self.col_bytes,
-                                C.c_void_p(r.data_ptr()), n, f, C.c_void_p(out.data_ptr()), f,
-                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        for t in (v, c, r):
+            self.unpack_into(d, out)
+        for t in d.values():
             t.record_stream(torch.cuda.current_stream(dev))
         return out
 

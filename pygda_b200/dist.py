@@ -9,6 +9,7 @@ mean becomes a scalar all-reduce and the MMD sample rows (5 x 1000 per domain) a
 with one small all-reduce.  The reference has no distributed code at all.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -19,6 +20,12 @@ from .data import Data
 from .graph import Graph, NORM_SYM_COL, SELF_LOOPS
 
 MAX_PEERS = 8
+# Above this share of remote columns the aggregation switches from in-kernel NVLink GATHERS (only referenced rows cross
+# the fabric, one 512-byte remote load per non-zero: right for partitions with locality, e.g. a 5 % edge cut) to PUSH
+# mode (every output row is stored into every rank's local gather buffer by the kernel that produces it; gathers are
+# local).  Measured at BASELINE config 4 on 2 GPUs (random graph, 50 % remote): 31 ms per aggregation with remote
+# gathers (~206 GB/s of useful NVLink traffic) -- profiles/r2_f_multi.
+PUSH_MIN_REMOTE = 0.25
 
 
 def _stream():
@@ -131,6 +138,16 @@ class PartitionedGraph:
         self.rows_per_rank = group.rows_per_rank(self.global_nodes)
         self.row_lo, self.row_hi = group.block(self.global_nodes)
         self.num_nodes = self.row_hi - self.row_lo
+        # share of this rank's non-zeros whose column lives on another GPU: decides how the exchange is done
+        owner = edge_index[0] // self.rows_per_rank
+        mine = (edge_index[1] >= self.row_lo) & (edge_index[1] < self.row_hi)
+        n_mine = int(mine.sum())
+        self.remote_fraction = float((mine & (owner != group.rank)).sum()) / max(n_mine + self.num_nodes, 1)
+        del owner, mine
+        frac = torch.tensor([self.remote_fraction], device=group.device)
+        dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group.pg)         # every rank must take the same path
+        forced = os.environ.get("GDA_DIST_MODE")
+        self.push = (forced == "push") if forced in ("push", "peer") else float(frac.item()) > PUSH_MIN_REMOTE
         full = Graph(edge_index, self.global_nodes, edge_weight, flags)      # normalisation needs global degrees
         self._h = C.c_void_p(0)
         gda.graph_partition(full.handle, self.row_lo, self.row_hi, self.rows_per_rank, _stream(), C.byref(self._h))
@@ -174,6 +191,14 @@ class PartitionedGraph:
             s = self._sym[width] = (SymBuffer(self.group, nbytes), SymBuffer(self.group, nbytes))
         return s
 
+    def _gather_buffers(self, width):
+        """Push mode: two symmetric buffers holding the WHOLE (padded) matrix, [world * rows_per_rank, width] each."""
+        s = self._sym.get(("push", width))
+        if s is None:
+            nbytes = self.group.world * self.rows_per_rank * width * 4
+            s = self._sym[("push", width)] = (SymBuffer(self.group, nbytes), SymBuffer(self.group, nbytes))
+        return s
+
     def _barrier(self):
         gda.peer_barrier_dev(self.flags.ptr_array, self.group.rank, self.group.world, ops._p(self.epoch_dev),
                              C.c_void_p(self.group.error.data_ptr()), _stream())
@@ -185,10 +210,12 @@ class PartitionedGraph:
         if n != self.num_nodes:
             raise ValueError(f"x has {n} rows, this rank owns {self.num_nodes}")
         g = self.group
-        bufs = self._buffers(h)
         ws = self.workspace(transpose, h)
         out = torch.empty(n, h, dtype=torch.float32, device=self.device)
         flags = (ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)
+        if self.push and h == 128:
+            return self._spmm_k_push(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, ws, out)
+        bufs = self._buffers(h)
         if ops.PROFILE is None:
             # barrier + copy-in + k x (barrier, peer aggregation) behind ONE call: k+2 fewer host round trips
             gda.spmm_peer_k_dev_f32(self._h, int(bool(transpose)), int(k), ops._p(x), bufs[0].ptr_array,
@@ -214,6 +241,40 @@ class PartitionedGraph:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             ops.PROFILE.append((e0, e1, (n, h, "float32", 1, "weighted-peer")))
+        return out
+
+
+    def _spmm_k_push(self, x, k, transpose, bias, flags, dropout_p, seed, seed_offset, ws, out):
+        """A_hat^k x with the exchange fused into the producing kernel (gda_spmm_push_k_f32)."""
+        g, (n, h) = self.group, x.shape
+        b0, b1 = self._gather_buffers(h)
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        err = C.c_void_p(g.error.data_ptr())
+        if ops.PROFILE is None:
+            gda.spmm_push_k_f32(self._h, int(bool(transpose)), int(k), ops._p(x), b0.ptr_array, b1.ptr_array, g.world,
+                                g.rank, ops._p(out), h, ops._p(bias), flags, float(dropout_p), seed, ops._p(seed_offset),
+                                ops._p(ws), ws.numel(), self.flags.ptr_array, ops._p(self.epoch_dev), err, _stream())
+            return out
+        # bench.py instrumentation: the same sequence, one call per step so that each launch can be timed
+        block = self.rows_per_rank * h * 4
+        self._barrier()
+        for q in range(g.world):
+            dst = torch.as_tensor(_DevPtr(b0.peer_ptrs[q] + g.rank * block, n * h * 4), device=self.device)
+            dst.view(torch.float32).view(n, h).copy_(x)
+        for i in range(k):
+            last = i == k - 1
+            self._barrier()
+            src, dstb = (b1, b0) if i & 1 else (b0, b1)
+            outs = [out.data_ptr()] if last else [dstb.peer_ptrs[q] + g.rank * block for q in range(g.world)]
+            arr = (C.c_void_p * len(outs))(*outs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gda.spmm_push_f32(self._h, int(bool(transpose)), C.c_void_p(src.peer_ptrs[g.rank]), arr, len(outs), g.world,
+                              h, h, h, ops._p(bias if last else None), flags if last else 0,
+                              float(dropout_p if last else 0.0), seed, ops._p(seed_offset), ops._p(ws), ws.numel(),
+                              _stream())
+            e1.record()
+            ops.PROFILE.append((e0, e1, (n, h, "float32", 1, "weighted-push" if not last else "weighted-push-last")))
         return out
 
 

@@ -38,10 +38,16 @@ class StagedBatch:
         self.packed = host_batch.__dict__.get("_packed_x")
         self.fields = {}
         if self.packed is not None:
-            self.fields.update(_vals=self.packed.vals, _cols=self.packed.cols, _rowptr=self.packed.rowptr)
+            self.fields.update(self.packed.tensors())
         for k, v in host_batch.__dict__.items():
             if torch.is_tensor(v) and not v.is_cuda and not (k == "x" and self.packed is not None):
-                self.fields[k] = v if v.is_pinned() else v.pin_memory()
+                if k == "edge_index" and v.dtype == torch.int64 and v.numel() and int(v.max()) < 2 ** 31 \
+                        and int(v.min()) >= 0:
+                    # node ids cross PCIe as int32 (half the bytes) and are widened on the device; like the packed x,
+                    # this staging form is built once, when the loader's batch is first staged
+                    self.fields[k] = v.to(torch.int32).pin_memory()
+                else:
+                    self.fields[k] = v if v.is_pinned() else v.pin_memory()
         self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in self.fields.items()}
                       for _ in range(2)]
         self.copied, self.consumed = [None, None], [None, None]
@@ -65,10 +71,7 @@ class StagedBatch:
         main.wait_event(self.copied[slot])
         s = self.slots[slot]
         if self.packed is not None:
-            n, f = self.packed.shape
-            x = self.static.x
-            ops.gda.unpack_rows_f32(ops._p(s["_vals"]), ops._p(s["_cols"]), self.packed.col_bytes, ops._p(s["_rowptr"]),
-                                    n, f, ops._p(x), f, ops._stream())
+            self.packed.unpack_into(s, self.static.x)
         for k, v in s.items():
             if not k.startswith("_"):
                 getattr(self.static, k).copy_(v, non_blocking=True)

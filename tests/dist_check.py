@@ -38,17 +38,25 @@ def main():
     n, h = 30011, 128                                       # not divisible by the world size
     src, tgt = domain_pair(n, 300000, 64, 5, seed=3, target_nodes=n - 1000, target_edges=280000)
     full = Graph(src.edge_index.to(dev), n)
-    part = PartitionedGraph(group, src.edge_index.to(dev), n)
     x = torch.randn(n, h, generator=torch.Generator().manual_seed(1)).to(dev)
     lo, hi = group.block(n)
-    for k, transpose in ((1, False), (3, False), (2, True)):
-        ref = ops.spmm_k(full, x, k, transpose=transpose)[lo:hi]
-        out = part.spmm_k(x[lo:hi].contiguous(), k, transpose=transpose)
-        e = rel(out, ref)
-        ok &= e < 1e-6
-        if rank == 0:
-            print(f"peer spmm k={k} T={transpose}: rel err {e:.2e}")
-    group.check()
+    bias = torch.randn(h, generator=torch.Generator().manual_seed(2)).to(dev)
+    for mode in ("peer", "push"):            # in-kernel NVLink gathers / exchange fused into the producer (dist.py)
+        os.environ["GDA_DIST_MODE"] = mode
+        part = PartitionedGraph(group, src.edge_index.to(dev), n)
+        assert part.push == (mode == "push")
+        for k, transpose in ((1, False), (3, False), (2, True), (4, False)):
+            ref = ops.spmm_k(full, x, k, transpose=transpose, bias=bias, relu=True)[lo:hi]
+            out = part.spmm_k(x[lo:hi].contiguous(), k, transpose=transpose, bias=bias, relu=True)
+            e = rel(out, ref)
+            ok &= e < 1e-6
+            again = part.spmm_k(x[lo:hi].contiguous(), k, transpose=transpose, bias=bias, relu=True)
+            ok &= bool(torch.equal(out, again))
+            if rank == 0:
+                print(f"{mode} spmm k={k} T={transpose}: rel err {e:.2e}, remote fraction {part.remote_fraction:.2f}")
+        group.check()
+        del part
+    os.environ.pop("GDA_DIST_MODE", None)
 
     # ---- 2. one training step: loss, logits, updated weights ------------------------------------
     hp = dict(in_dim=64, hid_dim=32, num_classes=5, num_layers=2, dropout=0.0, s_pnums=0, t_pnums=4, weight=10,
@@ -96,28 +104,33 @@ def main():
     single.overlap_streams = False
     multi = DistA2GNN(device=str(dev), group=group, **hp)
     multi.a2gnn = multi.init_model()
-    o2 = Adam(multi.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
-    gs = GraphedStep(multi, s_part, t_part, o2, warmup=1)     # one eager step inside (rank 0's own index draw)
-    # common starting point for the comparison: the weights after that warm-up step, fresh Adam moments on both sides
     single.a2gnn.load_state_dict(multi.a2gnn.state_dict())
     o1 = Adam(single.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
-    for grp in o2.groups:
-        for m in grp.exp_avg + grp.exp_avg_sq:
-            m.zero_()
-        grp.state.zero_()
+    o2 = Adam(multi.a2gnn.parameters(), lr=hp["lr"], weight_decay=hp["weight_decay"])
+    torch.manual_seed(77)
+    d0 = draw_indices(n, n - 1000)                            # what rank 0 draws inside the warm-up step below
+    torch.manual_seed(77)
+    gs = GraphedStep(multi, s_part, t_part, o2, warmup=1,     # one eager step inside, on rank 0's draw (broadcast)
+                     alpha_fn=lambda i: 0.3)
+    l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=d0)
+    l2, sl2, tl2 = gs.warmup_results[0]
     torch.manual_seed(21)
-    for step in range(3):
-        d = tuple(t.to(dev) for t in draw_indices(n, n - 1000))
-        for t in d:
-            dist.broadcast(t, src=0)
-        d = tuple(t.cpu() for t in d)
-        l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=d)
-        l2, sl2, tl2 = gs(mmd_indices=d)
+    for step in range(4):
+        if step > 0:
+            d = tuple(t.to(dev) for t in draw_indices(n, n - 1000))
+            for t in d:
+                dist.broadcast(t, src=0)
+            d = tuple(t.cpu() for t in d)
+            l1, sl1, tl1, _ = single.train_step(s_full, t_full, 0.3, o1, mmd_indices=d)
+            l2, sl2, tl2 = gs(mmd_indices=d)
         errs = {"loss": rel(l2, l1), "source_logits": rel(sl2, sl1[slo:shi]), "target_logits": rel(tl2, tl1[tlo:thi])}
         perr = max(rel(p, q) for p, q in zip(multi.a2gnn.parameters(), single.a2gnn.parameters()))
-        ok &= max(max(errs.values()), perr) < 5e-4
+        # forward quantities tight; weights at the bar of tests/test_gpu_graphed.py (Adam divides by sqrt(v): last-bit
+        # differences of atomically accumulated reductions are amplified where a gradient element is ~0)
+        ok &= max(errs.values()) < 1e-4 and perr < 1e-3
         if rank == 0:
-            print(f"graphed dist step {step}: " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()),
+            print(f"graphed dist step {step}{' (eager warm-up)' if step == 0 else ''}: " +
+                  ", ".join(f"{k}={v:.1e}" for k, v in errs.items()),
                   f"max param err {perr:.1e}, {gs.launches_per_replay} kernels per replay")
     group.check()
     del gs
