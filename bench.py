@@ -614,6 +614,26 @@ def run_gpu_arm(args, rank, world, local_rank):
         e2e_value = timed_loop(lambda i: one_step(sb_p, tb_p), e2e_steps)
         del sb_p, tb_p
 
+    # ---------------- the other BASELINE configurations, as side measurements (`other_configs`) ----------------
+    # config 3 (UDAGCN 1M / 10M, bf16, one GPU) rides along at N = 1, config 4 (GRADE-MMD 5M / 50M, random partition) at
+    # N = 4, config 5 (AdaGCN graph-level, 50k graphs / batch 512) at N = 8 -- the GPU counts BASELINE.json names them on.
+    # `python bench.py --config K --gpus N` runs any of them alone at any N.  Never allowed to take the main line down.
+    other = {}
+    if not args.no_other_configs:
+        try:
+            del model, sopt
+            from pygda_b200.graph import clear_graph_cache
+            clear_graph_cache()
+            ops.split_cache.clear(); ops.bf16_cache.clear()
+            torch.cuda.empty_cache()
+            if world == 1:
+                other["config3"] = run_config3(dev, steps=5, warmup=2)
+            elif world == 4:
+                other["config4"] = run_config4(dev, rank, world, group, steps=3, warmup=1)
+            elif world == 8:
+                other["config5"] = run_config5(dev, rank, world, group, steps=20, warmup=3)
+        except Exception as exc:                                            # noqa: BLE001
+            other["error"] = repr(exc)[:400]
     if rank != 0:
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -637,7 +657,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "dense_staging": ({"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": h2d_dense}
                                       if e2e_dense is not None else None)},
             "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "roofline": roofline,
-            "clocks": clocks}
+            "clocks": clocks, "other_configs": other or None}
     if world == 1 and not args.no_cpu_baseline:
         # bounded sample of the SAME workload: full-scale oracle steps on the graphs the GPU arm just trained on
         # (one warm-up + one timed step; the warm-up itself when a step takes longer than 20 s)

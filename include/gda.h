@@ -68,6 +68,9 @@ uint64_t    gda_launch_count(void);
 #define GDA_IMPROVED      2      /* fill value 2 instead of 1 */
 #define GDA_NORM_SYM_COL  4      /* D^-1/2 A D^-1/2, degree summed at the target index */
 #define GDA_NORM_SYM_ROW  8      /* same, degree summed at the source index */
+#define GDA_SKIP_EMPTY_ROWS 16   /* rows without non-zeros are NOT written by the aggregation (their output keeps its
+                                    content): rectangular local blocks of a partitioned graph, whose trailing "rows" are
+                                    halo slots filled by other GPUs (pygda_b200/dist.py, halo mode); H = 128 fp32 only */
 int gda_graph_create(const int64_t* edge_index, int64_t E, int64_t N,
                      const float* edge_weight, int flags, gda_stream_t stream,
                      gda_graph_t** out);
@@ -197,6 +200,21 @@ int gda_spmm_push_k_f32(const gda_graph_t* part, int transpose, int k, const flo
                         int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
                         int64_t workspace_bytes, uint64_t* const* peer_flags, uint64_t* epoch_dev, int* error_flag,
                         gda_stream_t stream);
+/* HALO mode for partitions WITH locality (few remote columns): the local block is a rectangular graph whose trailing
+ * columns are halo slots; after every step each rank copies the rows other ranks reference into their halo slots
+ * (gda_push_rows_f32: entry i = row rows[i] of src -> row slots[i] of rank peer[i]'s buffer, P2P stores), so that the
+ * aggregation itself runs on local memory with the ordinary kernels.  Each referenced row crosses NVLink once per
+ * consumer and step instead of once per referencing non-zero. */
+/* gda_spmm_halo_f32: gda_spmm_f32 on such a local block with the halo exchange FUSED into the producer: row r is
+ * stored to Y and, for every rank q with bit q set in halo_mask[r], into row halo_slot[r * num_peers + q] of
+ * peer_base[q] (P2P stores issued as soon as the row is reduced, overlapping the gathers of the rows in flight). */
+int gda_spmm_halo_f32(const gda_graph_t* block, const float* X, int64_t ldx, float* Y, int64_t ldy, int H,
+                      const int32_t* halo_mask, const int32_t* halo_slot, void* const* peer_base, int num_peers,
+                      const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                      void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+int gda_push_rows_f32(const float* src, int64_t ld, const int32_t* rows, const int32_t* slots, const int32_t* peer,
+                      int64_t count, void* const* peer_base, int num_peers, int64_t peer_ld, int H,
+                      gda_stream_t stream);
 int gda_sym_alloc(int64_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
 int gda_sym_open(const unsigned char* handle /* 64 bytes */, void** ptr);
 int gda_sym_close(void* ptr);

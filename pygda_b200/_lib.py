@@ -44,6 +44,8 @@ SIGNATURES = {
     "gda_spmm_peer_k_dev_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64,
                                       vp, vp, vp, vp]),
     "gda_peer_barrier_dev": (i32, [vp, i32, i32, vp, vp, vp]),
+    "gda_spmm_halo_f32": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_push_rows_f32": (i32, [vp, i64, vp, vp, vp, i64, vp, i32, i64, i32, vp]),
     "gda_spmm_push_f32": (i32, [vp, i32, vp, vp, i32, i32, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_push_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp, vp, vp,
                                   vp]),

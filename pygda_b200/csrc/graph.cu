@@ -151,6 +151,13 @@ __global__ void k_long_fill(const int* __restrict__ is_long, const int* __restri
   for (int j = 0; j < nsegs[i]; ++j) seg_long[seg_pos[i] + j] = L;
 }
 
+__global__ void k_count_key(const unsigned* __restrict__ keys, int64_t n, unsigned key, int* __restrict__ count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool hit = i < n && keys[i] == key;
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
 // Work items of k_spmm_tasks: item < num_segs is a segment of a long row, item - num_segs a row.
 // Rows covered by segments (and empty rows) get length 0 and sort to the end of the list.
 __global__ void k_task_make(const int* __restrict__ rowptr, int64_t N, int num_segs, int seg,
@@ -240,7 +247,8 @@ int build_tasks(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
   c.tasks = nullptr;
   c.num_tasks = 0;
   const int64_t total = static_cast<int64_t>(c.num_segs) + N;
-  if (c.may_have_empty_rows || total == 0 || N >= (int64_t(1) << 25) || c.num_segs >= (1 << 25) || seg > 64)
+  if ((c.may_have_empty_rows && !c.skip_empty_rows) || total == 0 || N >= (int64_t(1) << 25) ||
+      c.num_segs >= (1 << 25) || seg > 64)
     return GDA_OK;
   unsigned *keys, *keys_sorted;
   unsigned long long *descs, *sorted;
@@ -258,8 +266,16 @@ int build_tasks(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
   if ((rc = sc.get(reinterpret_cast<char**>(&tmp), static_cast<int64_t>(bytes)))) return rc;
   GDA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, keys_sorted, descs, sorted,
                                            static_cast<int>(total), 0, 8, st));
+  int* zero_len = nullptr;                               // items of length 0: split long rows, and empty rows
+  if ((rc = sc.get(&zero_len, 1))) return rc;
+  GDA_CUDA(cudaMemsetAsync(zero_len, 0, sizeof(int), st));
+  k_count_key<<<blocks_for(total), kThreads, 0, st>>>(keys, total, static_cast<unsigned>(seg), zero_len);
+  GDA_LAUNCH_CHECK();
+  int h_zero = 0;
+  GDA_CUDA(cudaMemcpyAsync(&h_zero, zero_len, sizeof(int), cudaMemcpyDeviceToHost, st));
   GDA_CUDA(cudaStreamSynchronize(st));
-  c.num_tasks = static_cast<int32_t>(total - c.num_long);
+  c.num_tasks = static_cast<int32_t>(total - h_zero);    // == total - num_long when no row is empty
+  if (c.skip_empty_rows) c.may_have_empty_rows = false;  // empty rows are simply not in the list: lean kernels apply
   return GDA_OK;
 }
 
@@ -406,6 +422,7 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
 
   g->unit_weights = norm && w == nullptr && !(flags & GDA_IMPROVED);
   g->csr.may_have_empty_rows = g->csr_t.may_have_empty_rows = !loops;   // a self loop in every row
+  g->csr.skip_empty_rows = g->csr_t.skip_empty_rows = (flags & GDA_SKIP_EMPTY_ROWS) != 0;
   if (!loops && N > 0) {
     // graphs given with their loops already in place (TDSS's smoothing graph, tdss.py:376-385) have no empty
     // row either: look, so that they take the lean aggregation kernels as well

@@ -28,6 +28,7 @@ struct Csr {
   uint2*   tasks = nullptr;         // [num_tasks]; null when not built (empty rows possible, ids >= 2^25)
   int32_t  num_tasks = 0;
   bool     may_have_empty_rows = true;   // false when every row holds a self loop
+  bool     skip_empty_rows = false;      // GDA_SKIP_EMPTY_ROWS: empty rows are left out of the work list and never written
 };
 
 }  // namespace gda

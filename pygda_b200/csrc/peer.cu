@@ -64,6 +64,22 @@ __global__ void k_peer_barrier_dev(FlagPtrs flags, int rank, int num_peers, uint
   }
 }
 
+// Halo exchange of a partitioned matrix (dist.py, halo mode): entry i copies row rows[i] of the local matrix into row
+// slots[i] of rank peer[i]'s buffer (P2P stores over NVLink).  One warp per entry, 16 bytes per lane and round.
+struct PushPtrs { char* p[GDA_MAX_PEERS]; };
+
+__global__ void k_push_rows(const float* __restrict__ src, int64_t ld, const int32_t* __restrict__ rows,
+                            const int32_t* __restrict__ slots, const int32_t* __restrict__ peer, int64_t count,
+                            PushPtrs dst, int64_t dst_ld, int H4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < count; i += nwarps) {
+    const float4* s = reinterpret_cast<const float4*>(src + static_cast<int64_t>(__ldg(rows + i)) * ld);
+    float4* d = reinterpret_cast<float4*>(dst.p[__ldg(peer + i)] + static_cast<int64_t>(__ldg(slots + i)) * dst_ld * 4);
+    for (int c = lane; c < H4; c += 32) d[c] = s[c];
+  }
+}
+
 }  // namespace
 }  // namespace gda
 
@@ -111,6 +127,23 @@ int gda_peer_barrier(uint64_t* const* peer_flags, int rank, int num_peers, uint6
     f.p[i] = peer_flags[i];
   }
   k_peer_barrier<<<1, 32, 0, as_stream(stream)>>>(f, rank, num_peers, epoch, error_flag);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_push_rows_f32(const float* src, int64_t ld, const int32_t* rows, const int32_t* slots, const int32_t* peer,
+                      int64_t count, void* const* peer_base, int num_peers, int64_t peer_ld, int H, gda_stream_t stream) {
+  GDA_REQUIRE(count >= 0 && H > 0 && H % 4 == 0 && ld % 4 == 0 && peer_ld % 4 == 0,
+              "gda_push_rows_f32: H and leading dimensions must be multiples of 4");
+  if (count == 0) return GDA_OK;
+  GDA_REQUIRE(src && rows && slots && peer && peer_base && num_peers >= 1 && num_peers <= GDA_MAX_PEERS,
+              "gda_push_rows_f32: bad arguments");
+  PushPtrs d;
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) d.p[i] = static_cast<char*>(peer_base[i < num_peers ? i : 0]);
+  int64_t blocks = ceil_div(count, 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  k_push_rows<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(src, ld, rows, slots, peer, count, d, peer_ld,
+                                                                            H / 4);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

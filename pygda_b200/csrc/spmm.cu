@@ -667,16 +667,23 @@ __device__ __forceinline__ void gather_batch(float (&acc)[NB][VEC], int myc, flo
 // inside EVERY rank's gather buffer (outs.p[q], P2P stores over NVLink), so that the next propagation step gathers
 // from local memory only -- the exchange is fused into the producer and overlaps its gathers row by row, and it moves
 // each row once per peer in bulk-friendly 512-byte stores instead of once per referencing non-zero as a remote load.
-template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER, int NB, bool PUSH = false>
+// HALO (partitions with locality, dist.py): the row is stored locally AND into the halo slot of every rank that references
+// it (halo_mask[row] = bit set of those ranks, halo_slot[row * nout + q] = its row in rank q's buffer): the halo exchange
+// is fused into the producer, so the NVLink stores overlap the gathers of the rows still in flight instead of running
+// as a separate pass between two barriers (measured at 2 GPUs, 25 MB of halo rows per step: separate push kernel
+// 8.4 ms per training step, peer gathers 7.7 ms).
+template <typename T, int VEC, int U, int CTAS, bool EPI, bool PEER, int NB, bool PUSH = false, bool HALO = false>
 __global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
 k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
              const float* __restrict__ vals, const int* __restrict__ long_rows, const int* __restrict__ long_seg_ptr,
              const int* __restrict__ seg_long, int* __restrict__ counters,
              const T* __restrict__ X, unsigned ldxb, T* __restrict__ Y, unsigned ldyb, int H,
              Epilogue epi, float* __restrict__ partial, PeerTable peers, uint64_t xbsb, uint64_t ybsb, int nrows,
-             PeerTable outs = PeerTable{}, int nout = 0) {
+             PeerTable outs = PeerTable{}, int nout = 0, const int* __restrict__ halo_mask = nullptr,
+             const int* __restrict__ halo_slot = nullptr) {
   static_assert(NB == 1 || !PEER, "batched form is local only");
   static_assert(!PUSH || (PEER && NB == 1), "push mode is the partitioned single-matrix form");
+  static_assert(!HALO || (!PEER && !PUSH && NB == 1), "halo mode runs on the local rectangular block");
   static_assert(U == 4 || U == 8, "batch depth");
   const int lane = threadIdx.x & 31;
   const int c0 = lane * VEC;
@@ -713,6 +720,8 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
 
     // ---- the task: len non-zeros starting at cur.x, first min(len, 32) pairs staged in (myc, myv) ----
     const int len = static_cast<int>((cur.y >> 25) & 63u) + 1;
+    int hmask = 0;                                       // which ranks reference this row (issued now, used after the gathers)
+    if (HALO && !(cur.y & 0x80000000u)) hmask = __ldg(halo_mask + (cur.y & 0x01FFFFFFu));
     float acc[NB][VEC];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
@@ -753,6 +762,12 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
                                                       static_cast<uint64_t>(row) * ldyb), acc[b]);
         } else {
           VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+          if (HALO && hmask) {
+            for (int q = 0; q < nout; ++q)
+              if ((hmask >> q) & 1)
+                VecIO<T, VEC>::store(reinterpret_cast<T*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(T) +
+                                                          static_cast<uint64_t>(__ldg(halo_slot + row * nout + q)) * ldyb), acc[b]);
+          }
         }
       }
     } else {                                             // segment of a long row: ordered reduction by the last arrival
@@ -788,6 +803,13 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
                                                         static_cast<uint64_t>(row) * ldyb), acc[b]);
           } else {
             VecIO<T, VEC>::store(reinterpret_cast<T*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+            if (HALO) {
+              const int hm = __ldg(halo_mask + row);
+              for (int q = 0; q < nout; ++q)
+                if ((hm >> q) & 1)
+                  VecIO<T, VEC>::store(reinterpret_cast<T*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(T) +
+                                                            static_cast<uint64_t>(__ldg(halo_slot + row * nout + q)) * ldyb), acc[b]);
+            }
           }
         }
         if (lane == 0) counters[L] = 0;
@@ -1115,6 +1137,8 @@ int spmm_any(const gda_graph* g, int transpose, const T* X, int64_t ldx, T* Y, i
   bool wide_ok = (H % WIDE == 0) && (ldx % WIDE == 0) && (ldy % WIDE == 0) &&
                  (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (reinterpret_cast<uintptr_t>(Y) % 16 == 0);
   if (nb > 1) wide_ok = wide_ok && (xbs % WIDE == 0) && (ybs % WIDE == 0);
+  if (c.skip_empty_rows)          // only the work-list kernel leaves rows without non-zeros untouched
+    GDA_REQUIRE((tasks_path<T, WIDE>(c, H, wide_ok)), "gda_spmm: a GDA_SKIP_EMPTY_ROWS graph needs the H = 128 fp32 / 256 bf16 path");
   const int pad_col = peers ? (my_rank << 28) : 0;
   if (peers)
     for (int i = 0; i < GDA_MAX_PEERS; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(peers->p[i]) % 16 == 0);
@@ -1176,6 +1200,38 @@ int spmm_push(const gda_graph* g, int transpose, const PeerTable& gather, const 
     k_spmm_tasks<float, 4, 4, GDA_TASKS_MIN_CTAS, false, true, 1, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
         c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y, ldyb, H,
         epi, partial, gather, 0, 0, static_cast<int>(g->N), outs, nout);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+// Halo-mode step on a local rectangular block (GDA_SKIP_EMPTY_ROWS graph): ordinary local gathers, every row stored to Y
+// and to the halo slots of the ranks that reference it.
+int spmm_halo(const gda_graph* g, const float* X, int64_t ldx, float* Y, int64_t ldy, int H, const int* halo_mask,
+              const int* halo_slot, const PeerTable& outs, int nout, const Epilogue& epi, float* partial,
+              int64_t workspace_bytes, cudaStream_t st) {
+  const Csr& c = g->csr;
+  bool wide_ok = H == 128 && ldx % 4 == 0 && ldy % 4 == 0 && reinterpret_cast<uintptr_t>(X) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(Y) % 16 == 0;
+  for (int i = 0; i < nout; ++i) wide_ok = wide_ok && (reinterpret_cast<uintptr_t>(outs.p[i]) % 16 == 0);
+  const bool on_tasks_path = tasks_path<float, 4>(c, H, wide_ok);
+  GDA_REQUIRE(on_tasks_path, "gda_spmm_halo: needs H = 128 fp32, aligned buffers and a task list");
+  GDA_REQUIRE(g->N * ldx < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32), "gda_spmm_halo: block too large");
+  const int64_t need = static_cast<int64_t>(c.num_segs) * H * sizeof(float);
+  if (need > 0 && (partial == nullptr || workspace_bytes < need))
+    return fail(GDA_E_WORKSPACE, "gda_spmm_halo: workspace smaller than gda_spmm_workspace_bytes()");
+  if (g->N == 0 || c.num_tasks == 0) return GDA_OK;
+  const unsigned ldxb = static_cast<unsigned>(ldx * sizeof(float)), ldyb = static_cast<unsigned>(ldy * sizeof(float));
+  int64_t tb = ceil_div(c.num_tasks, GDA_ROWS_BLOCK / 32);
+  if (tb > static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS) tb = static_cast<int64_t>(kNumSMs) * GDA_TASKS_MIN_CTAS;
+  const bool has_epi = epi.bias != nullptr || epi.flags != 0;
+  if (has_epi)
+    k_spmm_tasks<float, 4, 4, GDA_TASKS_MIN_CTAS, true, false, 1, false, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+        c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y, ldyb, H,
+        epi, partial, PeerTable{}, 0, 0, static_cast<int>(g->N), outs, nout, halo_mask, halo_slot);
+  else
+    k_spmm_tasks<float, 4, 4, GDA_TASKS_MIN_CTAS, false, false, 1, false, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+        c.tasks, c.num_tasks, c.colidx, c.vals, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, X, ldxb, Y, ldyb, H,
+        epi, partial, PeerTable{}, 0, 0, static_cast<int>(g->N), outs, nout, halo_mask, halo_slot);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }
@@ -1460,6 +1516,22 @@ int gda_spmm_push_f32(const gda_graph_t* part, int transpose, const void* gather
   epi.scale = 1.0f / (1.0f - dropout_p); epi.seed = seed; epi.seed_offset = seed_offset;
   return gda::spmm_push(part, transpose, gt, ot, num_out, ldx, ldy, H, epi, static_cast<float*>(workspace),
                         workspace_bytes, gda::as_stream(stream));
+}
+
+int gda_spmm_halo_f32(const gda_graph_t* block, const float* X, int64_t ldx, float* Y, int64_t ldy, int H,
+                      const int32_t* halo_mask, const int32_t* halo_slot, void* const* peer_base, int num_peers,
+                      const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                      void* workspace, int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(block && X && Y && X != Y && halo_mask && halo_slot && peer_base, "gda_spmm_halo_f32: bad arguments");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS, "gda_spmm_halo_f32: bad peer count");
+  GDA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gda_spmm_halo_f32: dropout_p outside [0,1)");
+  gda::PeerTable ot;
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) ot.p[i] = peer_base[i < num_peers ? i : 0];
+  gda::Epilogue epi;
+  epi.bias = bias; epi.flags = epi_flags; epi.thresh = gda::dropout_threshold(dropout_p);
+  epi.scale = 1.0f / (1.0f - dropout_p); epi.seed = seed; epi.seed_offset = seed_offset;
+  return gda::spmm_halo(block, X, ldx, Y, ldy, H, halo_mask, halo_slot, ot, num_peers, epi,
+                        static_cast<float*>(workspace), workspace_bytes, gda::as_stream(stream));
 }
 
 int gda_spmm_push_k_f32(const gda_graph_t* part, int transpose, int k, const float* x_local, void* const* gbuf0,

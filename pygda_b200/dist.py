@@ -26,6 +26,7 @@ MAX_PEERS = 8
 # local).  Measured at BASELINE config 4 on 2 GPUs (random graph, 50 % remote): 31 ms per aggregation with remote
 # gathers (~206 GB/s of useful NVLink traffic) -- profiles/r2_f_multi.
 PUSH_MIN_REMOTE = 0.25
+FUSED_HALO = os.environ.get("GDA_HALO_FUSED", "1") != "0"     # A/B switch: 0 = separate halo push kernel after every step
 
 
 def _stream():
@@ -147,14 +148,16 @@ class PartitionedGraph:
         frac = torch.tensor([self.remote_fraction], device=group.device)
         dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group.pg)         # every rank must take the same path
         forced = os.environ.get("GDA_DIST_MODE")
-        self.push = (forced == "push") if forced in ("push", "peer") else float(frac.item()) > PUSH_MIN_REMOTE
+        self.mode = forced if forced in ("push", "peer", "halo") else \
+            ("push" if float(frac.item()) > PUSH_MIN_REMOTE else "halo")
+        self.push = self.mode == "push"
         full = Graph(edge_index, self.global_nodes, edge_weight, flags)      # normalisation needs global degrees
+
         self._h = C.c_void_p(0)
         gda.graph_partition(full.handle, self.row_lo, self.row_hi, self.rows_per_rank, _stream(), C.byref(self._h))
         n_, nnz_, a_, b_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         gda.graph_info(self._h, C.byref(n_), C.byref(nnz_), C.byref(a_), C.byref(b_))
         self.local_nnz = nnz_.value
-        del full
         self.device = group.device
         self._ws, self._sym = {}, {}
         # every partitioned graph has its own barrier channel (flag array + epoch counter): graphs used
@@ -163,6 +166,8 @@ class PartitionedGraph:
         # the channel's barrier epoch lives in device memory and is advanced by the barrier kernel itself, so that
         # a captured CUDA graph of the training step replays correctly (gda_peer_barrier_dev)
         self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._halo = _HaloPlan(self, full) if self.mode == "halo" else None
+        del full
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -215,6 +220,8 @@ class PartitionedGraph:
         flags = (ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)
         if self.push and h == 128:
             return self._spmm_k_push(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, ws, out)
+        if self._halo is not None and h == 128:
+            return self._halo.spmm_k(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out)
         bufs = self._buffers(h)
         if ops.PROFILE is None:
             # barrier + copy-in + k x (barrier, peer aggregation) behind ONE call: k+2 fewer host round trips
@@ -275,6 +282,114 @@ class PartitionedGraph:
                               _stream())
             e1.record()
             ops.PROFILE.append((e0, e1, (n, h, "float32", 1, "weighted-push" if not last else "weighted-push-last")))
+        return out
+
+
+class _HaloPlan:
+    """HALO mode of a partitioned graph (few remote columns): this rank's row block as a RECTANGULAR local graph --
+    columns [0, n_own) are its own rows, columns n_own.. are halo slots, one per distinct remote row it references --
+    plus the list of its own rows that other ranks reference.  An aggregation then runs on local memory with the
+    ordinary work-list kernel (entries of a row keep the global COO order, so results are those of the single-GPU
+    kernel); after every step each rank copies the rows its peers need into their halo slots (gda_push_rows_f32, P2P
+    stores over NVLink): a referenced row crosses the fabric once per consumer and step, not once per non-zero."""
+
+    def __init__(self, part, full):
+        from .graph import SKIP_EMPTY_ROWS
+        g, dev = part.group, part.device
+        self.part = part
+        lo, hi, rpr = part.row_lo, part.row_hi, part.rows_per_rank
+        n_own = hi - lo
+        ei, w = full.coo()                                   # normalised weights, the reference's entry order
+        src, dst = ei[0], ei[1]
+
+        def block(rows, cols):
+            m = (rows >= lo) & (rows < hi)
+            return rows[m] - lo, cols[m], w[m]
+        fr, fc, fw = block(dst, src)                         # A_hat   : row = target, column = source
+        tr, tc, tw = block(src, dst)                         # A_hat^T : row = source, column = target
+        remote = lambda c: c[(c < lo) | (c >= hi)]           # noqa: E731
+        halo = torch.unique(torch.cat([remote(fc), remote(tc)]))          # sorted global ids of the referenced remote rows
+        self.n_own, self.n_halo = n_own, int(halo.numel())
+        self.n_tot = n_own + self.n_halo
+
+        def remap(c):
+            own = (c >= lo) & (c < hi)
+            slot = torch.searchsorted(halo, c.clamp(min=0)) if self.n_halo else torch.zeros_like(c)
+            return torch.where(own, c - lo, n_own + slot)
+        self.graphs = (Graph(torch.stack([remap(fc), fr]), self.n_tot, fw, SKIP_EMPTY_ROWS),
+                       Graph(torch.stack([remap(tc), tr]), self.n_tot, tw, SKIP_EMPTY_ROWS))
+        # who needs which of my rows, and where it goes in their buffer
+        owner = (halo // rpr).cpu()
+        local_row = (halo - (halo // rpr) * rpr).cpu()
+        slots = torch.arange(n_own, self.n_tot)
+        need = {q: (local_row[owner == q].to(torch.int32), slots[owner == q].to(torch.int32)) for q in range(g.world)
+                if q != g.rank}
+        everyone = [None] * g.world
+        dist.all_gather_object(everyone, need, group=g.pg)
+        rows, slot, peer = [], [], []
+        for p_, wanted in enumerate(everyone):
+            if p_ == g.rank or g.rank not in wanted:
+                continue
+            r_, s_ = wanted[g.rank]
+            rows.append(r_); slot.append(s_); peer.append(torch.full((r_.numel(),), p_, dtype=torch.int32))
+        cat = lambda xs: (torch.cat(xs) if xs else torch.zeros(0, dtype=torch.int32)).to(dev)   # noqa: E731
+        self.push_rows, self.push_slots, self.push_peer = cat(rows), cat(slot), cat(peer)
+        self.push_count = int(self.push_rows.numel())
+        # the same plan per row, for the kernel that pushes while it aggregates (gda_spmm_halo_f32)
+        self.halo_mask = torch.zeros(max(n_own, 1), dtype=torch.int32, device=dev)
+        self.halo_slot = torch.zeros(max(n_own, 1) * g.world, dtype=torch.int32, device=dev)
+        if self.push_count:
+            r64, p64 = self.push_rows.long(), self.push_peer.long()
+            self.halo_mask.index_put_((r64,), torch.bitwise_left_shift(torch.ones_like(self.push_peer), self.push_peer),
+                                      accumulate=True)                       # (row, peer) pairs are distinct: add == or
+            self.halo_slot[r64 * g.world + p64] = self.push_slots
+        self._bufs = {}
+
+    def buffers(self, width):
+        b = self._bufs.get(width)
+        if b is None:
+            nbytes = max(self.n_tot, 1) * width * 4
+            syms = (SymBuffer(self.part.group, nbytes), SymBuffer(self.part.group, nbytes))
+            b = self._bufs[width] = (syms, tuple(s_.view(torch.float32, (self.n_tot, width)) for s_ in syms))
+        return b
+
+    def _push(self, view, sym, width):
+        if self.push_count:
+            g = self.part.group
+            gda.push_rows_f32(ops._p(view), width, ops._p(self.push_rows), ops._p(self.push_slots),
+                              ops._p(self.push_peer), self.push_count, sym.ptr_array, g.world, width, width, _stream())
+
+    def spmm_k(self, x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out):
+        part, (n, h) = self.part, x.shape
+        gr = self.graphs[1 if transpose else 0]
+        syms, views = self.buffers(h)
+        ws = gr.workspace(False, h)
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        part._barrier()                                   # every rank is done with the buffers of the last call
+        views[0][:n].copy_(x)
+        self._push(views[0], syms[0], h)
+        for i in range(k):
+            last = i == k - 1
+            part._barrier()                               # step i-1 (or the copy-in) and its halo pushes have landed
+            src, dst_v, dst_s = views[i & 1], views[(i + 1) & 1], syms[(i + 1) & 1]
+            prof = ops.PROFILE
+            if prof is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if last or not FUSED_HALO:
+                gda.spmm_f32(gr.handle, 0, ops._p(src), h, ops._p(out if last else dst_v), h, h,
+                             ops._p(bias if last else None), flags if last else 0, float(dropout_p if last else 0.0),
+                             seed, ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
+            else:                                         # aggregate and push the halo rows in one kernel
+                gda.spmm_halo_f32(gr.handle, ops._p(src), h, ops._p(dst_v), h, h, ops._p(self.halo_mask),
+                                  ops._p(self.halo_slot), dst_s.ptr_array, part.group.world, None, 0, 0.0, seed,
+                                  ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
+            if prof is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                prof.append((e0, e1, (n, h, "float32", 1, "weighted-halo")))
+            if not last and not FUSED_HALO:
+                self._push(dst_v, dst_s, h)
         return out
 
 

@@ -13,7 +13,7 @@ import torch
 
 from ._lib import gda, load
 
-SELF_LOOPS, IMPROVED, NORM_SYM_COL, NORM_SYM_ROW = 1, 2, 4, 8
+SELF_LOOPS, IMPROVED, NORM_SYM_COL, NORM_SYM_ROW, SKIP_EMPTY_ROWS = 1, 2, 4, 8, 16
 
 
 def _stream():

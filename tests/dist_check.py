@@ -41,10 +41,10 @@ def main():
     x = torch.randn(n, h, generator=torch.Generator().manual_seed(1)).to(dev)
     lo, hi = group.block(n)
     bias = torch.randn(h, generator=torch.Generator().manual_seed(2)).to(dev)
-    for mode in ("peer", "push"):            # in-kernel NVLink gathers / exchange fused into the producer (dist.py)
+    for mode in ("peer", "push", "halo"):    # in-kernel NVLink gathers / producer-side full push / halo exchange (dist.py)
         os.environ["GDA_DIST_MODE"] = mode
         part = PartitionedGraph(group, src.edge_index.to(dev), n)
-        assert part.push == (mode == "push")
+        assert part.mode == mode
         for k, transpose in ((1, False), (3, False), (2, True), (4, False)):
             ref = ops.spmm_k(full, x, k, transpose=transpose, bias=bias, relu=True)[lo:hi]
             out = part.spmm_k(x[lo:hi].contiguous(), k, transpose=transpose, bias=bias, relu=True)

@@ -115,25 +115,37 @@ def test_shard_batch_splits_graphs_contiguously():
 
 
 def test_packed_rows_format_roundtrip_on_the_host():
-    """Host half of the row-compressed pinned staging (pygda_b200/data.py: PackedRows): values, uint16 / int32
-    column ids and row pointers reproduce the matrix bit for bit (the device half is gda_unpack_rows_f32)."""
+    """Host half of the row-compressed pinned staging (pygda_b200/data.py: PackedRows): the values, the delta-coded
+    column ids (one byte per entry, 255 = escape that only advances) and the two row-pointer arrays reproduce the
+    matrix bit for bit under the decoding rule gda_unpack_rows_delta_f32 implements on the device."""
     import numpy as np
     from pygda_b200.data import Data, PackedRows
     g = torch.Generator().manual_seed(0)
     for n, f in ((300, 6775), (40, 70000), (5, 1)):
         x = torch.where(torch.rand(n, f, generator=g) < 0.05, torch.randn(n, f, generator=g), torch.zeros(()))
         x[0, f - 1] = 2.0
-        x[1].zero_()
+        x[1].zero_()                                          # an empty row
         if f > 3:
-            x[2, 3] = -0.0
+            x[2, 3] = -0.0                                    # kept: the BIT PATTERN is non-zero
+        if f > 2000:
+            x[3].zero_()
+            x[3, 700], x[3, 1465], x[3, f - 1] = 3.0, 4.0, 5.0      # a gap of exactly 3 * 255 and a long run of escapes
         p = PackedRows(x, chunk=64)
-        assert p.col_bytes == (2 if f <= 65536 else 4) and p.shape == (n, f)
-        cols = p.cols.numpy().view(np.uint16).astype(np.int64) if p.col_bytes == 2 else p.cols.numpy().astype(np.int64)
-        rows = torch.repeat_interleave(torch.arange(n), p.rowptr[1:] - p.rowptr[:-1])
-        dense = torch.zeros(n, f)
-        dense[rows, torch.from_numpy(cols)] = p.vals
-        assert torch.equal(dense.view(torch.int32), x.view(torch.int32))
-        assert int(p.rowptr[-1]) == p.vals.numel() == p.cols.numel()
+        assert p.shape == (n, f)
+        vals, dl = p.vals.numpy(), p.deltas.numpy()
+        vp, bp = p.val_ptr.numpy().astype(np.int64), p.byte_ptr.numpy().astype(np.int64)
+        dense = np.zeros((n, f), dtype=np.float32)
+        for r in range(n):
+            col, k = 0, 0
+            for byte in dl[bp[r]:bp[r + 1]]:
+                col += int(byte)
+                if byte != 255:
+                    dense[r, col] = vals[vp[r] + k]
+                    k += 1
+            assert k == vp[r + 1] - vp[r]
+        assert np.array_equal(dense.view(np.int32), x.numpy().view(np.int32))
+        assert int(vp[-1]) == p.vals.numel() and int(bp[-1]) == p.deltas.numel()
+        assert p.nbytes == 4 * p.vals.numel() + p.deltas.numel() + 2 * 4 * (n + 1)
     d = Data(x=torch.zeros(10, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.zeros(10, dtype=torch.long))
     assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
 
