@@ -253,6 +253,38 @@ int     gda_gemm_bf16x3(int transA, int transB, int64_t M, int64_t N, int64_t K,
                         float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
                         gda_stream_t stream);
 
+/* ------------------------------ first-layer GEMMs on a SPARSE input matrix X --
+ * The input features of the citation benchmarks are bag-of-words rows, a few per cent non-zero (config 2: 7 %).
+ * `self.lin(x)` (prop_gcn_conv.py:205) / `torch.matmul(x, self.weight)` (cached_gcn_conv.py:130) and the weight
+ * gradient of that product are evaluated from a TILE-PACKED copy of X -- 5 bytes per NON-ZERO instead of the 4 bytes
+ * per element of the dense split-bf16 pair -- that is expanded into dense swizzled (hi, lo) bf16 operand tiles in
+ * shared memory and multiplied on the tcgen05 tensor cores with the same three-term split as gda_gemm_bf16x3
+ * (fp32-accurate: same product terms, same K order).
+ *
+ * Tile-packed X [rows, cols] (pygda_b200.data.PackedTiles; also the pinned host staging form of the per-step
+ * `.to(device)`, a2gnn.py:311-312): sub-tile t = (row / 32) * nkb + col / 64, nkb = ceil(cols / 64); inside a
+ * sub-tile the entries are sorted by p = (row % 32) * 64 + col % 64; the entries of sub-tile t are
+ * [ptr[t], ptr[t+1]) of vals (fp32) and codes (uint8 = p & 255); seg[t][k], k = 0..7 (uint16, 16-byte aligned
+ * rows) = number of entries of the sub-tile with p < 256 (k + 1), so that entry i has p >> 8 = #{k < 7 :
+ * seg[t][k] <= i} -- an entry is decoded without looking at its neighbours.  The number of 32-row strips is padded
+ * to a multiple of 4: ptr has gda_xt_ptr_entries(rows, cols) int32 entries, seg one row fewer.
+ *
+ * gda_gemm_xt_fwd: C[rows, N] = X B^T (transB = 1, B stored [N, cols]) or X B (transB = 0, B stored [cols, N]);
+ *   B as a split-bf16 pair (gda_split_bf16, ldb in bf16 elements, multiple of 8).
+ * gda_gemm_xt_dw:  C = X^T G [cols, N] (out_transposed = 0) or its transpose G^T X [N, cols] (out_transposed = 1,
+ *   the layout of PyG's Linear weight); G [rows, N] as a split-bf16 pair (ldg multiple of 8).  The reduction over
+ *   the rows is split into whole waves of CTAs and reduced in fixed order (deterministic); workspace of
+ *   gda_gemm_xt_dw_workspace_bytes. */
+int64_t gda_xt_ptr_entries(int64_t rows, int64_t cols);
+int gda_gemm_xt_fwd(const float* vals, const void* codes, const int32_t* ptr, const void* seg,
+                    int64_t rows, int64_t cols, int transB, int64_t N, const void* b_hi, const void* b_lo,
+                    int64_t ldb, float* C, int64_t ldc, gda_stream_t stream);
+int64_t gda_gemm_xt_dw_workspace_bytes(int64_t rows, int64_t cols, int64_t N);
+int gda_gemm_xt_dw(const float* vals, const void* codes, const int32_t* ptr, const void* seg,
+                   int64_t rows, int64_t cols, int64_t N, const void* g_hi, const void* g_lo, int64_t ldg,
+                   int out_transposed, float* C, int64_t ldc, void* workspace, int64_t workspace_bytes,
+                   gda_stream_t stream);
+
 /* --------------------------------------- bf16 feature path (BASELINE config 3) --
  * "UDAGCN ... hid=256, bf16": activations and input features stored in bf16, parameters and every accumulation
  * in fp32.  gda_gemm_bf16: C = op(A) op(B) from plain bf16 operands on the tcgen05 kernel (ONE UMMA per K step
@@ -454,6 +486,10 @@ int gda_collate_graphs(const float* x_all, int F, const int64_t* edge_index_all,
 int gda_unpack_rows_delta_f32(const float* vals, const uint8_t* deltas, const int32_t* val_ptr,
                               const int32_t* byte_ptr, int64_t N, int64_t F, float* out, int64_t ldo,
                               int* error_flag, gda_stream_t stream);
+/* gda_unpack_tiles_f32: the same from the TILE-PACKED form of gda_gemm_xt_fwd / gda_gemm_xt_dw (sub-tiles of
+ * 32 rows x 64 columns): for consumers that need the dense matrix. */
+int gda_unpack_tiles_f32(const float* vals, const uint8_t* codes, const int32_t* ptr, const void* seg,
+                         int64_t N, int64_t F, float* out, int64_t ldo, int* error_flag, gda_stream_t stream);
 int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, const int64_t* rowptr, int64_t N,
                         int64_t F, float* out, int64_t ldo, gda_stream_t stream);
 /* gda_argmax_confusion: pred[r] = argmax_c logits[r, c] (first maximal index) and counts[y * C + p] += 1

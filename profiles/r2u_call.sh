@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export ROWS=50000
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_gemm_xt -c 1 -f -o gpurun_out/r2u_xt_fwd python profiles/bench_gemm_xt.py > gpurun_out/r2u_ncu_fwd.log 2>&1
+tail -2 gpurun_out/r2u_ncu_fwd.log

@@ -63,6 +63,10 @@ SIGNATURES = {
     "gda_gemm_bf16x3_supported": (i32, [i64, i64, i64, i64, i64]),
     "gda_gemm_bf16x3_workspace_bytes": (i64, [i64, i64, i64]),
     "gda_gemm_bf16x3": (i32, [i32, i32, i64, i64, i64, vp, vp, i64, vp, vp, i64, vp, i64, vp, i64, vp]),
+    "gda_xt_ptr_entries": (i64, [i64, i64]),
+    "gda_gemm_xt_fwd": (i32, [vp, vp, vp, vp, i64, i64, i32, i64, vp, vp, i64, vp, i64, vp]),
+    "gda_gemm_xt_dw_workspace_bytes": (i64, [i64, i64, i64]),
+    "gda_gemm_xt_dw": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, i64, i32, vp, i64, vp, i64, vp]),
     "gda_gemm_bf16_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "gda_gemm_bf16": (i32, [i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp, i64, vp]),
     "gda_cast_f32_bf16": (i32, [vp, vp, i64, vp]),
@@ -102,6 +106,7 @@ SIGNATURES = {
     "gda_wedges_destroy": (i32, [vp]),
     "gda_collate_graphs": (i32, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
     "gda_unpack_rows_delta_f32": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
+    "gda_unpack_tiles_f32": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gda_unpack_rows_f32": (i32, [vp, vp, i32, vp, i64, i64, vp, i64, vp]),
     "gda_argmax_confusion": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),

@@ -107,6 +107,32 @@ __global__ void k_unpack_rows_delta(const float* __restrict__ vals, const uint8_
   }
 }
 
+// Dense rebuild from the TILE-PACKED form (gemm_xt.cu / pygda_b200.data.PackedTiles): one warp per sub-tile of
+// 32 rows x 64 columns; entry i of a sub-tile sits at position ((#segment boundaries <= i) << 8) | code.
+__global__ void k_unpack_tiles(const float* __restrict__ vals, const uint8_t* __restrict__ codes,
+                               const int32_t* __restrict__ ptr, const uint16_t* __restrict__ seg,
+                               int64_t N, int64_t F, int nkb, int64_t ntiles, int64_t ldo, float* __restrict__ out,
+                               int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); t < ntiles; t += nwarps) {
+    const int e0 = __ldg(ptr + t), n = __ldg(ptr + t + 1) - e0;
+    int sg[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) sg[k] = __ldg(seg + t * 8 + k);
+    const int64_t row0 = (t / nkb) * 32, col0 = (t % nkb) * 64;
+    for (int i = lane; i < n; i += 32) {
+      int h = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) h += i >= sg[k];
+      const int p = (h << 8) | static_cast<int>(__ldg(codes + e0 + i));
+      const int64_t r = row0 + (p >> 6), c = col0 + (p & 63);
+      if (r < N && c < F) out[r * ldo + c] = __ldg(vals + e0 + i);
+      else if (err) *err = 1;
+    }
+  }
+}
+
 constexpr int kMaxClasses = 64;
 
 // argmax (first maximal index, like torch.argmax on the CPU) + confusion counts[label * C + pred]
@@ -228,6 +254,28 @@ int gda_unpack_rows_delta_f32(const float* vals, const uint8_t* deltas, const in
   if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
   k_unpack_rows_delta<<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, deltas, val_ptr, byte_ptr, N, F, ldo, out,
                                                                      error_flag);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_unpack_tiles_f32(const float* vals, const uint8_t* codes, const int32_t* ptr, const void* seg,
+                         int64_t N, int64_t F, float* out, int64_t ldo, int* error_flag, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(N >= 0 && F >= 0 && ldo >= F, "gda_unpack_tiles_f32: bad size");
+  if (N == 0 || F == 0) return GDA_OK;
+  GDA_REQUIRE(ptr && seg && out, "gda_unpack_tiles_f32: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  if (ldo == F) {
+    GDA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(N) * F, st));
+  } else {
+    GDA_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * F, static_cast<size_t>(N), st));
+  }
+  const int nkb = static_cast<int>(ceil_div(F, 64));
+  const int64_t ntiles = ceil_div(N, 32) * nkb;          // the padding strips hold no entries
+  int64_t blocks = ceil_div(ntiles, 8);
+  if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+  k_unpack_tiles<<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, codes, ptr, static_cast<const uint16_t*>(seg), N, F,
+                                                                nkb, ntiles, ldo, out, error_flag);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }

@@ -89,6 +89,128 @@ class PackedRows:
         return out
 
 
+class XTiles:
+    """DEVICE view of a tile-packed sparse matrix (``PackedTiles``): what ``gda_gemm_xt_fwd`` / ``gda_gemm_xt_dw``
+    read.  Attached to a dense device ``x`` as ``x._gda_tiles`` (``Data.to``) so that the first layer's products
+    run from the packed form (ops.GraphConvFn / ops.LinearFn)."""
+    __slots__ = ("vals", "codes", "ptr", "seg", "rows", "cols")
+
+    def __init__(self, vals, codes, ptr, seg, rows, cols):
+        self.vals, self.codes, self.ptr, self.seg = vals, codes, ptr, seg
+        self.rows, self.cols = int(rows), int(cols)
+
+    def tensors(self):
+        return {"_vals": self.vals, "_codes": self.codes, "_ptr": self.ptr, "_seg": self.seg}
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
+
+    def unpack_into(self, out, stream=None):
+        """Rebuild the dense [rows, cols] matrix in ``out`` (current stream): ``gda_unpack_tiles_f32``."""
+        from ._lib import gda
+        p = lambda t: C.c_void_p(t.data_ptr())                    # noqa: E731
+        gda.unpack_tiles_f32(p(self.vals), p(self.codes), p(self.ptr), p(self.seg), self.rows, self.cols,
+                             p(out), out.stride(0), C.c_void_p(0),
+                             C.c_void_p((stream or torch.cuda.current_stream(out.device)).cuda_stream))
+        return out
+
+
+class PackedTiles:
+    """TILE-PACKED copy of a sparse fp32 matrix -- the operand form of the first layer's tensor-core GEMMs
+    (csrc/gemm_xt.cu) AND the pinned staging form of the per-step ``.to(device)`` (pygda/models/a2gnn.py:311-312):
+    the host->device copy lands in the buffers the kernels read; the dense matrix is not needed on the path.
+
+    Sub-tile ``t = (row // 32) * nkb + col // 64`` (``nkb = ceil(cols / 64)``); inside a sub-tile the entries are
+    sorted by ``p = (row % 32) * 64 + col % 64``.  Entries of sub-tile ``t``: ``[ptr[t], ptr[t + 1])`` of ``vals``
+    (fp32) and ``codes`` (uint8 ``= p & 255``); ``seg[t, k]`` (int16 bit pattern of a uint16, ``k = 0..7``) = number
+    of entries of the sub-tile with ``p < 256 (k + 1)``, so entry ``i`` has ``p >> 8 = #{k < 7: seg[t, k] <= i}``:
+    5 bytes per non-zero + 20 bytes per sub-tile, and every entry decodes on its own (no prefix sums in the
+    kernels).  An entry is kept iff its BIT PATTERN is non-zero (-0.0 survives).  The strip count is padded to a
+    multiple of 4 (one 128-row operand tile).  Built with torch ops on whatever device ``x`` lives on (one-time
+    preparation, like the CSR of the graph)."""
+
+    def __init__(self, x, chunk=8192, pin=True):
+        n, f = x.shape
+        x = x.contiguous()
+        dev = x.device
+        nkb = -(-f // 64)
+        nstrips = -(-(-(-n // 32)) // 4) * 4
+        ntiles = nstrips * nkb
+        chunk = max(32, chunk // 32 * 32)
+        vals, codes, cnt8 = [], [], []
+        for s in range(0, n, chunk):
+            blk = x[s:s + chunk]
+            mask = blk.view(torch.int32) != 0
+            r, c = mask.nonzero(as_tuple=True)
+            key = ((r // 32) * nkb + c // 64) * 2048 + (r % 32) * 64 + c % 64
+            order = torch.argsort(key)
+            key = key[order]
+            vals.append(blk[mask][order])
+            codes.append((key & 255).to(torch.uint8))
+            ntl = -(-blk.size(0) // 32) * nkb
+            cnt8.append(torch.bincount(key >> 8, minlength=ntl * 8))     # per (sub-tile, 256-position segment)
+        cnt = torch.zeros(ntiles, 8, dtype=torch.int64, device=dev)
+        if cnt8:
+            flat = torch.cat(cnt8)
+            cnt.view(-1)[:flat.numel()] = flat
+        seg = torch.cumsum(cnt, 1)
+        ptr = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(seg[:, 7], 0)
+        if int(ptr[-1]) >= 2 ** 31:
+            raise ValueError("PackedTiles: more than 2^31 non-zeros; pin_memory(pack=False) keeps the dense form")
+        self.shape = (n, f)
+        pin_ = (lambda t: t.pin_memory()) if (pin and torch.cuda.is_available() and dev.type == "cpu") else (lambda t: t)
+        self.vals = pin_(torch.cat(vals) if vals else torch.zeros(0, device=dev))
+        self.codes = pin_(torch.cat(codes) if codes else torch.zeros(0, dtype=torch.uint8, device=dev))
+        self.ptr = pin_(ptr.to(torch.int32))
+        self.seg = pin_(seg.to(torch.int16).contiguous())           # counts <= 2048: the int16 bits ARE the uint16
+
+    def tensors(self):
+        """The arrays that cross PCIe, by staging name."""
+        return {"_vals": self.vals, "_codes": self.codes, "_ptr": self.ptr, "_seg": self.seg}
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
+
+    def view(self, dev=None):
+        """``XTiles`` over ``dev`` (DEVICE copies of ``tensors()``; default: this object's own arrays)."""
+        d = dev if dev is not None else self.tensors()
+        return XTiles(d["_vals"], d["_codes"], d["_ptr"], d["_seg"], *self.shape)
+
+    def unpack_into(self, dev, out, stream=None):
+        """Rebuild the dense matrix in ``out`` [N, F] from DEVICE copies ``dev`` of ``tensors()`` (current stream)."""
+        self.view(dev).unpack_into(out, stream)
+
+    def to_dense(self, device, non_blocking=True):
+        """Dense device matrix rebuilt from a fresh host->device copy of the packed arrays; the copy stays attached
+        as ``._gda_tiles`` -- the first layer multiplies from it, the dense form serves every other consumer."""
+        n, f = self.shape
+        dev = torch.device(device)
+        d = {k: t.to(dev, non_blocking=non_blocking) for k, t in self.tensors().items()}
+        out = torch.empty(n, f, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self.unpack_into(d, out)
+        for t in d.values():
+            t.record_stream(torch.cuda.current_stream(dev))
+        out._gda_tiles = self.view(d)
+        return out
+
+    def decode(self):
+        """Dense matrix by a plain sequential decode on the host (tests; not a product path)."""
+        n, f = self.shape
+        nkb = -(-f // 64)
+        out = np.zeros((n, f), dtype=np.float32)
+        vals, codes = self.vals.cpu().numpy(), self.codes.cpu().numpy()
+        ptr, seg = self.ptr.cpu().numpy(), self.seg.cpu().numpy().astype(np.int64)
+        for t in range(len(ptr) - 1):
+            for i in range(ptr[t + 1] - ptr[t]):
+                pos = int((seg[t, :7] <= i).sum()) * 256 + int(codes[ptr[t] + i])
+                out[(t // nkb) * 32 + pos // 64, (t % nkb) * 64 + pos % 64] = vals[ptr[t] + i]
+        return torch.from_numpy(out)
+
+
 PACK_DENSITY = 0.25      # pin_memory() keeps x row-compressed below this fraction of non-zeros
 
 
@@ -146,8 +268,10 @@ class Data:
 
     def pin_memory(self, pack="auto"):
         """Pinned host copy for the per-step ``.to(device)`` of the fit loops.  ``pack``: keep a sparse fp32 ``x``
-        row-compressed in the pinned staging area (``PackedRows``) -- "auto" does so below ``PACK_DENSITY``
-        non-zeros; ``.x`` of the result stays the caller's host tensor, ``.to(device)`` rebuilds it densely."""
+        compressed in the pinned staging area -- "auto" does so below ``PACK_DENSITY`` non-zeros, tile-packed
+        (``PackedTiles``: the form the first layer's GEMMs read; "rows" selects the older row-compressed
+        ``PackedRows``); ``.x`` of the result stays the caller's host tensor, ``.to(device)`` rebuilds it densely
+        and keeps the packed device copy attached for the first layer."""
         out = self.__class__.__new__(self.__class__)
         x = self.__dict__.get("x")
         do_pack = False
@@ -163,7 +287,7 @@ class Data:
                 continue
             out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v
         if do_pack:
-            out.__dict__["_packed_x"] = PackedRows(x)
+            out.__dict__["_packed_x"] = PackedRows(x) if pack == "rows" else PackedTiles(x)
         src, ei = self.edge_index, out.__dict__.get("edge_index")
         if torch.is_tensor(ei) and ei is not src:
             for attr in ("_gda_partition", "_gda_key", "_gda_keepalive"):
@@ -280,6 +404,10 @@ class NeighborLoader:
         for v in d.__dict__.values():                    # allocated on the side stream, consumed on this one
             if torch.is_tensor(v) and v.is_cuda:
                 v.record_stream(main)
+                tiles = getattr(v, "_gda_tiles", None)   # the packed copy the first layer reads travels with x
+                if tiles is not None:
+                    for t in tiles.tensors().values():
+                        t.record_stream(main)
         yield d
 
     def __iter__(self):

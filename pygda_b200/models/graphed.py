@@ -28,9 +28,15 @@ class StagedBatch:
     The reference's loop copies the batch to the device at the top of every step (pygda/models/a2gnn.py:311-312) and
     only then computes.  Here the copy of epoch e+1 is issued on a copy stream into one of two device staging slots
     while epoch e's graph runs; at the top of epoch e+1 the slot is consumed on the compute stream: a row-compressed
-    ``x`` is rebuilt densely into the static ``x`` buffer (``gda_unpack_rows_f32``, bit for bit), the other tensors
+    ``x`` is rebuilt densely into the static ``x`` buffer (``gda_unpack_tiles_f32``, bit for bit), the other tensors
     are copied device-to-device, and the cached split-bf16 operand pair of ``x`` is recomputed from it
-    (``ops.ConstCache.refresh``) -- every epoch's data crosses PCIe and is consumed; nothing is re-allocated."""
+    (``ops.ConstCache.refresh``) -- every epoch's data crosses PCIe and is consumed; nothing is re-allocated.
+
+    When the first layer multiplies from the TILE-PACKED form itself (``ops.x_tiles``: sparse bag-of-words
+    features, csrc/gemm_xt.cu) the epoch's packed arrays are copied device-to-device into the static packed
+    buffers the captured kernels read, and that is all: no kernel of the step reads the dense ``x`` (it keeps epoch
+    0's rebuild for consumers outside the step, e.g. ``predict``), so neither the dense rebuild nor the operand
+    split is repeated."""
 
     def __init__(self, host_batch, device):
         self.dev = torch.device(device)
@@ -48,6 +54,9 @@ class StagedBatch:
                     self.fields[k] = v.to(torch.int32).pin_memory()
                 else:
                     self.fields[k] = v if v.is_pinned() else v.pin_memory()
+        self.tiles = ops.x_tiles(self.static.x, 128) if self.packed is not None else None
+        if self.tiles is not None and self.tiles is not getattr(self.static.x, "_gda_tiles", None):
+            self.tiles = None
         self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in self.fields.items()}
                       for _ in range(2)]
         self.copied, self.consumed = [None, None], [None, None]
@@ -70,13 +79,17 @@ class StagedBatch:
         main = torch.cuda.current_stream(self.dev)
         main.wait_event(self.copied[slot])
         s = self.slots[slot]
-        if self.packed is not None:
+        if self.tiles is not None:
+            for k, t in self.tiles.tensors().items():
+                t.copy_(s[k], non_blocking=True)
+        elif self.packed is not None:
             self.packed.unpack_into(s, self.static.x)
         for k, v in s.items():
             if not k.startswith("_"):
                 getattr(self.static, k).copy_(v, non_blocking=True)
-        ops.split_cache.refresh(self.static.x)
-        ops.bf16_cache.refresh(self.static.x)
+        if self.tiles is None:
+            ops.split_cache.refresh(self.static.x)
+            ops.bf16_cache.refresh(self.static.x)
         ev = torch.cuda.Event()
         ev.record(main)
         self.consumed[slot] = ev

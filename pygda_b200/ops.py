@@ -286,6 +286,66 @@ def gemm_split(a, b, trans_a, trans_b, m, n, k):
     return out
 
 
+# ---- first-layer products from a TILE-PACKED sparse input matrix (csrc/gemm_xt.cu) ----
+XT_DENSITY = 0.10        # above this the sub-tiles outgrow the expanders' register prefetch: dense split path
+XT_ENABLED = True
+
+
+def _make_tiles(x):
+    """Tile-packed form of a device-resident CONSTANT dense matrix, or False when it is not sparse enough."""
+    from .data import PackedTiles
+    x = _f32c(x)
+    nnz = int((x.view(torch.int32) != 0).sum())
+    if nnz > XT_DENSITY * x.numel():
+        return False
+    return PackedTiles(x, pin=False).view()
+
+
+tiles_cache = ConstCache(_make_tiles, lambda t, x: None, lambda t: t.nbytes if t else 0, capacity=8)
+
+
+def x_tiles(x, n_out):
+    """``XTiles`` to multiply ``x`` [rows, cols] from, or None: the packed copy ``Data.to`` attached to a staged
+    ``x`` (``_gda_tiles``), or -- for a device-resident matrix marked constant (``mark_constant`` / the full-batch
+    loaders) -- a packed form built once (``tiles_cache``) when at most ``XT_DENSITY`` of it is non-zero."""
+    if not XT_ENABLED or x.dim() != 2 or x.dtype != torch.float32 or x.requires_grad:
+        return None
+    if not tc_eligible(x.shape[0], max(int(n_out), 64), x.shape[1]):
+        return None
+    t = getattr(x, "_gda_tiles", None)
+    if t is None and getattr(x, "_gda_const", False) and getattr(x, "_gda_key", None) is None:
+        t = tiles_cache.get(x)
+    if not t or t.vals.numel() > XT_DENSITY * x.numel():
+        return None
+    return t
+
+
+def _xt_args(t):
+    return _p(t.vals), _p(t.codes), _p(t.ptr), _p(t.seg), t.rows, t.cols
+
+
+def xt_fwd(t, w, w_in_out):
+    """x @ w (``w_in_out``: w [cols, N]) or x @ w^T (w [N, cols]) from the tile-packed x."""
+    ws = Split(w)
+    n = w.shape[1] if w_in_out else w.shape[0]
+    out = torch.empty(t.rows, n, dtype=torch.float32, device=w.device)
+    gda.gemm_xt_fwd(*_xt_args(t), int(not w_in_out), n, _p(ws.hi), _p(ws.lo), ws.ld, _p(out), out.stride(0),
+                    _stream())
+    return out, ws
+
+
+def xt_dw(t, g, w_in_out):
+    """Weight gradient of ``xt_fwd``: x^T g [cols, N] (``w_in_out``) or g^T x [N, cols]; returns (dW, split of g)."""
+    g = _f32c(g)
+    gs = Split(g)
+    n = g.shape[1]
+    out = torch.empty((t.cols, n) if w_in_out else (n, t.cols), dtype=torch.float32, device=g.device)
+    ws = _workspace(load().gda_gemm_xt_dw_workspace_bytes(t.rows, t.cols, n), g.device)
+    gda.gemm_xt_dw(*_xt_args(t), n, _p(gs.hi), _p(gs.lo), gs.ld, int(not w_in_out), _p(out), out.stride(0), _p(ws),
+                   ws.numel(), _stream())
+    return out, gs
+
+
 def _pad_to(t, dim, size):
     """Zero-padded copy of a 2-D tensor along ``dim``."""
     shape = list(t.shape)
@@ -434,7 +494,11 @@ class GraphConvFn(torch.autograd.Function):
         x = _f32c(x)
         w = _f32c(weight)
         const_x = not x.requires_grad          # input features: split once, re-used every pass
-        h, xs, ws = mm(x, w, trans_b=not w_in_out, cache_a=const_x)
+        tiles = x_tiles(x, w.shape[1] if w_in_out else w.shape[0])
+        if tiles is not None:                  # sparse input features: multiplied from their tile-packed form
+            (h, ws), xs = xt_fwd(tiles, w, w_in_out), None
+        else:
+            h, xs, ws = mm(x, w, trans_b=not w_in_out, cache_a=const_x)
         if k > 0:
             y = spmm_k(graph, h, k, bias=bias)
         elif bias is not None:
@@ -445,6 +509,7 @@ class GraphConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, w)
         ctx.graph, ctx.k, ctx.w_in_out, ctx.has_bias = graph, k, w_in_out, bias is not None
         ctx.splits = (xs, ws)
+        ctx.tiles = tiles
         return y
 
     @staticmethod
@@ -457,7 +522,9 @@ class GraphConvFn(torch.autograd.Function):
         gw = gx = gs = None
         if ctx.needs_input_grad[1]:
             # W [out,in]: dW = g0^T x ; W [in,out]: dW = x^T g0
-            if ctx.w_in_out:
+            if ctx.tiles is not None:
+                gw, gs = xt_dw(ctx.tiles, g0, ctx.w_in_out)
+            elif ctx.w_in_out:
                 gw, _, gs = mm(x, g0, trans_a=True, a_split=xs)
             else:
                 gw, gs, _ = mm(g0, x, trans_a=True, b_split=xs)
@@ -472,12 +539,17 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x, w = _f32c(x), _f32c(weight)
-        y, xs, ws = mm(x, w, trans_b=True, cache_a=not x.requires_grad)
+        tiles = x_tiles(x, w.shape[0])
+        if tiles is not None:
+            (y, ws), xs = xt_fwd(tiles, w, False), None
+        else:
+            y, xs, ws = mm(x, w, trans_b=True, cache_a=not x.requires_grad)
         if bias is not None:
             gda.bias_act_dropout_fwd(_p(y), _p(bias), _p(y), y.shape[0], y.shape[1], 0, 0.0, 0, _NULL, _stream())
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.splits = (xs, ws)
+        ctx.tiles = tiles
         return y
 
     @staticmethod
@@ -487,7 +559,10 @@ class LinearFn(torch.autograd.Function):
         gy = _f32c(gy)
         gx = gw = gs = None
         if ctx.needs_input_grad[1]:
-            gw, gs, _ = mm(gy, x, trans_a=True, b_split=xs)
+            if ctx.tiles is not None:
+                gw, gs = xt_dw(ctx.tiles, gy, False)
+            else:
+                gw, gs, _ = mm(gy, x, trans_a=True, b_split=xs)
         if ctx.needs_input_grad[0]:
             gx, _, _ = mm(gy, w, a_split=gs, b_split=ws)
         gb = colsum(gy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
