@@ -523,6 +523,31 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "batched": batched,
                 "how": "CUDA events around each aggregation launch in an instrumented repeat of the timed steps"}
 
+    # layer-1 products from the tile-packed sparse X (csrc/gemm_xt.cu): tensor-bound, not HBM-bound -- the record says
+    # how far from the dense-bf16 tensor peak the three-term split runs and how few bytes it moves
+    def xt_record(kind):
+        ts = [(a.elapsed_time(b), meta) for (a, b, meta) in recs if len(meta) == 5 and meta[2] == kind]
+        if not ts:
+            return None
+        ms_ = statistics.mean(t_ for t_, _ in ts)
+        rows_, cols_, _, n_, nnz_ = ts[0][1]
+        flops = 3 * 2.0 * rows_ * cols_ * n_                       # three bf16 UMMA terms per product (fp32-accurate)
+        bytes_ = 5 * nnz_ + 20 * (-(-rows_ // 32)) * (-(-cols_ // 64)) + 4 * rows_ * n_ * (2 if kind == "xt_dw" else 1) \
+            + 4 * cols_ * n_
+        tpeak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        return {"kernel": "k_gemm_xt<%s> (X [%d x %d], %.1f %% non-zero, tile-packed; N = %d)"
+                          % ("dW = G^T X" if kind == "xt_dw" else "X W^T", rows_, cols_, 100.0 * nnz_ / (rows_ * cols_), n_),
+                "bound": "tensor", "us_per_launch": ms_ * 1e3, "launches_per_step": len(ts) / n_prof,
+                "tensor_flops_per_launch": flops, "achieved": flops / (ms_ * 1e-3) / 1e12, "peak": tpeak,
+                "unit": "TFLOP/s", "frac": flops / (ms_ * 1e-3) / 1e12 / tpeak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, back to back)",
+                "alg_bytes_per_launch": bytes_, "dense_operand_bytes_it_replaces": 4 * rows_ * cols_,
+                "note": "useful fp32 flops are a third of the tensor flops (Ah*Bh + Ah*Bl + Al*Bh); the dense "
+                        "split-bf16 kernel it replaces streams 4 bytes per ELEMENT of X and is HBM-bound"}
+    gemm_rec = {k_: v_ for k_, v_ in (("forward", xt_record("xt_fwd")), ("weight_gradient", xt_record("xt_dw"))) if v_}
+    if gemm_rec:
+        roofline["gemm"] = gemm_rec
+
     # ---------------- end to end from pinned host buffers (`e2e`) ----------------
     if args.skip_e2e:
         if rank == 0:
@@ -569,9 +594,13 @@ def run_gpu_arm(args, rank, world, local_rank):
         if run_h is not None:
             gs = model.graphed_step
             h2d = gs.h2d_bytes_per_step                 # counted from the tensors StagedBatch copies every epoch
+            tiled = all(sb is not None and sb.tiles is not None for sb in gs.staged)
             e2e_note = ("fit() default: CUDA-graph replay (%d kernels), next epoch's host->device copy "
-                        "double-buffered behind it, consumed by unpack + operand-split kernels before each replay"
-                        % gs.launches_per_replay)
+                        "double-buffered behind it; %s" % (
+                            gs.launches_per_replay,
+                            "x crosses PCIe TILE-PACKED (5 bytes per non-zero) and lands in the buffers the first "
+                            "layer's tensor-core GEMMs read: no dense rebuild, no operand split" if tiled else
+                            "consumed by unpack + operand-split kernels before each replay"))
             ep = [1]
 
             def graphed_h(i):
@@ -649,8 +678,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "how": e2e_note,
-                    "staging": ("pinned host inputs, x row-compressed (lossless; only its non-zeros cross PCIe, dense "
-                                "matrix rebuilt on the GPU)" if packed else "pinned host inputs, dense"),
+                    "staging": ("pinned host inputs, x tile-packed (lossless; only its non-zeros cross PCIe: 5 bytes per "
+                                "non-zero + 20 bytes per 32 x 64 sub-tile)" if packed else "pinned host inputs, dense"),
                     "eager_serial": ({"value": e2e_eager, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "how": "cuda_graph=False, prefetch=False: copy, then compute (round 1's e2e.value)"}
                                      if e2e_eager is not None else None),

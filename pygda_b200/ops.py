@@ -320,6 +320,22 @@ def x_tiles(x, n_out):
     return t
 
 
+def _prof_begin():
+    """bench.py's instrumented repeat (``PROFILE`` is a list): a CUDA event before the launch."""
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, meta):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((e0, e1, meta))
+
+
 def _xt_args(t):
     return _p(t.vals), _p(t.codes), _p(t.ptr), _p(t.seg), t.rows, t.cols
 
@@ -329,8 +345,10 @@ def xt_fwd(t, w, w_in_out):
     ws = Split(w)
     n = w.shape[1] if w_in_out else w.shape[0]
     out = torch.empty(t.rows, n, dtype=torch.float32, device=w.device)
+    ev = _prof_begin()
     gda.gemm_xt_fwd(*_xt_args(t), int(not w_in_out), n, _p(ws.hi), _p(ws.lo), ws.ld, _p(out), out.stride(0),
                     _stream())
+    _prof_end(ev, (t.rows, t.cols, "xt_fwd", n, int(t.vals.numel())))
     return out, ws
 
 
@@ -341,8 +359,10 @@ def xt_dw(t, g, w_in_out):
     n = g.shape[1]
     out = torch.empty((t.cols, n) if w_in_out else (n, t.cols), dtype=torch.float32, device=g.device)
     ws = _workspace(load().gda_gemm_xt_dw_workspace_bytes(t.rows, t.cols, n), g.device)
+    ev = _prof_begin()
     gda.gemm_xt_dw(*_xt_args(t), n, _p(gs.hi), _p(gs.lo), gs.ld, int(not w_in_out), _p(out), out.stride(0), _p(ws),
                    ws.numel(), _stream())
+    _prof_end(ev, (t.rows, t.cols, "xt_dw", n, int(t.vals.numel())))
     return out, gs
 
 
