@@ -487,9 +487,11 @@ def run_gpu_arm(args, rank, world, local_rank):
         pass
     # The factored (unit-weight) kernel reads no edge weights: 4 bytes per non-zero fewer, + the dinv vector.
     def alg_bytes(kind, nb_):
-        idx = 4 * (n_nodes + 1) + (4 * nnz + 4 * n_nodes if kind == "unit-weight" else 8 * nnz)
+        idx = 4 * (n_nodes + 1) + (4 * nnz + 4 * n_nodes if str(kind).startswith("unit-weight") else 8 * nnz)
         return idx + nb_ * 2 * 4 * n_nodes * H
     kname = {"unit-weight": "k_spmm_unw<4,16,...> (factored D S D form: no per-edge weights)",
+             "unit-weight-halo": "k_spmm_unw<4,...> on the rank's rectangular block (factored D S D form; halo rows "
+                                 "pushed by their owners after every step)",
              "weighted": "k_spmm_tasks<float,4,4,...>"}
     b_alg = alg_bytes(kind1, 1)
     achieved = b_alg / (spmm_ms * 1e-3) / 1e9
@@ -505,7 +507,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                    "alg_bytes_per_launch": b_alg2, "us_per_launch": ms2 * 1e3,
                    "achieved": b_alg2 / (ms2 * 1e-3) / 1e9, "frac": b_alg2 / (ms2 * 1e-3) / 1e9 / peak,
                    "launches_per_step": len(times2) / n_prof}
-    gather_bytes = 4 * (n_nodes + 1) + (4 if kind1 == "unit-weight" else 8) * nnz + 4 * nnz * H + 4 * n_nodes * H
+    gather_bytes = 4 * (n_nodes + 1) + (4 if str(kind1).startswith("unit-weight") else 8) * nnz + 4 * nnz * H + 4 * n_nodes * H
     roofline = {"bound": "hbm", "kernel": "%s (A_hat x, H=128, N=100k, nnz=%d)" % (kname.get(kind1, kind1), nnz),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

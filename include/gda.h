@@ -133,6 +133,18 @@ int gda_spmm_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* X,
 int gda_graph_unit_weights(const gda_graph_t* g, int transpose, int H, int nb);
 int gda_row_scale_f32(const gda_graph_t* g, int nb, const float* X, int64_t ldx, int64_t x_batch_stride, float* Z,
                       int64_t ldz, int64_t z_batch_stride, int H, gda_stream_t stream);
+/* Rectangular LOCAL blocks of a partitioned graph (halo mode of the multi-GPU path, pygda_b200/dist.py): the block of
+ * a rank keeps the normalised weights of the WHOLE graph, whose degrees the library cannot recompute from the block.
+ * gda_graph_export_dinv copies deg^-1/2 of a normalised graph ([N] floats); gda_graph_set_unit_dinv installs such a
+ * vector (the rank's own rows; halo rows unused) on a block whose weights are dinv[row] * dinv[col] of a unit-weight
+ * graph, which makes the block eligible for the factored chain (gda_graph_unit_weights / gda_spmm_unw_nb_f32): halo
+ * rows arrive already scaled by their owners.  gda_row_scale_rows_f32 = gda_row_scale_f32 over the first `rows` rows
+ * only (the rank's own rows; the halo slots are written by the peers). */
+int gda_graph_export_dinv(const gda_graph_t* g, float* dinv_out, gda_stream_t stream);
+int gda_graph_set_unit_dinv(gda_graph_t* g, const float* dinv, gda_stream_t stream);
+int gda_row_scale_rows_f32(const gda_graph_t* g, int64_t rows, int nb, const float* X, int64_t ldx,
+                           int64_t x_batch_stride, float* Z, int64_t ldz, int64_t z_batch_stride, int H,
+                           gda_stream_t stream);
 int gda_spmm_unw_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride,
                         float* Y, int64_t ldy, int64_t y_batch_stride, int H, int last, const float* bias, int epi_flags,
                         float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
@@ -212,6 +224,13 @@ int gda_spmm_halo_f32(const gda_graph_t* block, const float* X, int64_t ldx, flo
                       const int32_t* halo_mask, const int32_t* halo_slot, void* const* peer_base, int num_peers,
                       const float* bias, int epi_flags, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                       void* workspace, int64_t workspace_bytes, gda_stream_t stream);
+/* gda_spmm_unw_halo_f32: one INTERMEDIATE step z' = D^2 S z of the factored chain on such a block (made eligible by
+ * gda_graph_set_unit_dinv), nb = 1 or 2 stacked matrices, with the same fused halo exchange; matrix b of the stack
+ * lives peer_batch_stride[q] * b elements into rank q's buffer (the ranks' blocks differ in size). */
+int gda_spmm_unw_halo_f32(const gda_graph_t* block, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride, float* Y,
+                          int64_t ldy, int64_t y_batch_stride, int H, const int32_t* halo_mask, const int32_t* halo_slot,
+                          void* const* peer_base, const int64_t* peer_batch_stride, int num_peers, void* workspace,
+                          int64_t workspace_bytes, gda_stream_t stream);
 int gda_push_rows_f32(const float* src, int64_t ld, const int32_t* rows, const int32_t* slots, const int32_t* peer,
                       int64_t count, void* const* peer_base, int num_peers, int64_t peer_ld, int H,
                       gda_stream_t stream);

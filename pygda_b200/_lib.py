@@ -36,6 +36,9 @@ SIGNATURES = {
     "gda_spmm_nb_f32": (i32, [vp, i32, i32, vp, i64, i64, vp, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_graph_unit_weights": (i32, [vp, i32, i32, i32]),
     "gda_row_scale_f32": (i32, [vp, i32, vp, i64, i64, vp, i64, i64, i32, vp]),
+    "gda_graph_export_dinv": (i32, [vp, vp, vp]),
+    "gda_graph_set_unit_dinv": (i32, [vp, vp, vp]),
+    "gda_row_scale_rows_f32": (i32, [vp, i64, i32, vp, i64, i64, vp, i64, i64, i32, vp]),
     "gda_spmm_unw_nb_f32": (i32, [vp, i32, i32, vp, i64, i64, vp, i64, i64, i32, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_k_nb_f32": (i32, [vp, i32, i32, i32, vp, i64, i64, vp, i64, i64, vp, vp, i32, vp, i32, f32, u64, vp, vp,
                                 i64, vp]),
@@ -45,6 +48,7 @@ SIGNATURES = {
                                       vp, vp, vp, vp]),
     "gda_peer_barrier_dev": (i32, [vp, i32, i32, vp, vp, vp]),
     "gda_spmm_halo_f32": (i32, [vp, vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
+    "gda_spmm_unw_halo_f32": (i32, [vp, i32, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
     "gda_push_rows_f32": (i32, [vp, i64, vp, vp, vp, i64, vp, i32, i64, i32, vp]),
     "gda_spmm_push_f32": (i32, [vp, i32, vp, vp, i32, i32, i64, i64, i32, vp, i32, f32, u64, vp, vp, i64, vp]),
     "gda_spmm_push_k_f32": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, i64, vp, vp, vp,

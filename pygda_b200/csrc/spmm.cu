@@ -861,13 +861,20 @@ __device__ __forceinline__ void gather_sum(float (&acc)[NB][4], unsigned (&cj)[4
     }
 }
 
-template <int U, int CTAS, bool EPI, int NB>
+// HALO (rectangular block of a partition, dist.py): the finished row is also stored into the halo slot of every rank
+// that references it (halo_mask / halo_slot as in k_spmm_tasks<HALO>); matrix b of the stack lives hs.b[q] bytes into
+// rank q's buffer.
+struct HaloStride { uint64_t b[GDA_MAX_PEERS]; };
+
+template <int U, int CTAS, bool EPI, int NB, bool HALO = false>
 __global__ void __launch_bounds__(GDA_ROWS_BLOCK, CTAS)
 k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict__ colidx,
            const float* __restrict__ dinv, int last, const int* __restrict__ long_rows,
            const int* __restrict__ long_seg_ptr, const int* __restrict__ seg_long, int* __restrict__ counters,
            const float* __restrict__ X, unsigned ldxb, float* __restrict__ Y, unsigned ldyb, int H,
-           Epilogue epi, float* __restrict__ partial, uint64_t xbsb, uint64_t ybsb, int nrows) {
+           Epilogue epi, float* __restrict__ partial, uint64_t xbsb, uint64_t ybsb, int nrows,
+           const int* __restrict__ halo_mask = nullptr, const int* __restrict__ halo_slot = nullptr,
+           PeerTable outs = PeerTable{}, int nout = 0, HaloStride hs = HaloStride{}) {
   static_assert(U == 4, "batches of four");
   const int lane = threadIdx.x & 31;
   const int c0 = lane * 4;
@@ -910,12 +917,19 @@ k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict
       const unsigned row = cur.y & 0x01FFFFFFu;
       const float d = __ldg(dinv + row);
       const float sc = last ? d : d * d;
+      const int hm = HALO ? __ldg(halo_mask + row) : 0;
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[b][v] *= sc;
         if (EPI) apply_epilogue<4>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
         VecIO<float, 4>::store(reinterpret_cast<float*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+        if (HALO && hm) {
+          for (int q = 0; q < nout; ++q)
+            if ((hm >> q) & 1)
+              VecIO<float, 4>::store(reinterpret_cast<float*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(float) +
+                                                              b * hs.b[q] + static_cast<uint64_t>(__ldg(halo_slot + row * nout + q)) * ldyb), acc[b]);
+        }
       }
     } else {                                             // segment of a long row: ordered reduction by the last arrival
       const int sgid = static_cast<int>(cur.y & 0x01FFFFFFu);
@@ -949,6 +963,13 @@ k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict
           for (int v = 0; v < 4; ++v) acc[b][v] *= sc;
           if (EPI) apply_epilogue<4>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
           VecIO<float, 4>::store(reinterpret_cast<float*>(reinterpret_cast<char*>(Y + c0) + b * ybsb + static_cast<uint64_t>(row) * ldyb), acc[b]);
+          if (HALO) {
+            const int hm = __ldg(halo_mask + row);
+            for (int q = 0; q < nout; ++q)
+              if ((hm >> q) & 1)
+                VecIO<float, 4>::store(reinterpret_cast<float*>(static_cast<char*>(const_cast<void*>(outs.p[q])) + c0 * sizeof(float) +
+                                                                b * hs.b[q] + static_cast<uint64_t>(__ldg(halo_slot + row * nout + q)) * ldyb), acc[b]);
+          }
         }
         if (lane == 0) counters[L] = 0;
       }
@@ -1248,7 +1269,9 @@ bool unw_path(const gda_graph* g, const Csr& c, int H, int64_t ldx, int64_t ldy,
 
 int spmm_unw(const gda_graph* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t zbs, float* Y, int64_t ldy,
              int64_t ybs, int H, int last, const float* bias, int epi_flags, float dropout_p, uint64_t seed,
-             const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+             const uint64_t* seed_offset, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+             const int* halo_mask = nullptr, const int* halo_slot = nullptr, const PeerTable* outs = nullptr, int nout = 0,
+             const HaloStride* hs = nullptr) {
   const Csr& c = transpose ? g->csr_t : g->csr;
   GDA_REQUIRE(Z && Y && Z != Y, "gda_spmm_unw: bad feature pointers");
   GDA_REQUIRE(g->N * ldz < (int64_t(1) << 32) && g->N * ldy < (int64_t(1) << 32), "gda_spmm_unw: N * ld must be below 2^32");
@@ -1271,6 +1294,19 @@ int spmm_unw(const gda_graph* g, int transpose, int nb, const float* Z, int64_t 
   k_spmm_unw<4, CC, E, B><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(                              \
       c.tasks, c.num_tasks, c.colidx, g->dinv, last, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, Z, ldzb, Y, \
       ldyb, H, epi, partial, zb, yb, static_cast<int>(g->N))
+  if (halo_mask) {                                       // intermediate step of a halo-mode chain: no epilogue
+    GDA_REQUIRE(!has_epi && !last && halo_slot && outs && hs && nout >= 1, "gda_spmm_unw_halo: bad halo arguments");
+    if (nb == 2)
+      k_spmm_unw<4, 10, false, 2, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+          c.tasks, c.num_tasks, c.colidx, g->dinv, 0, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, Z, ldzb, Y, ldyb,
+          H, epi, partial, zb, yb, static_cast<int>(g->N), halo_mask, halo_slot, *outs, nout, *hs);
+    else
+      k_spmm_unw<4, 12, false, 1, true><<<static_cast<unsigned>(tb), GDA_ROWS_BLOCK, 0, st>>>(
+          c.tasks, c.num_tasks, c.colidx, g->dinv, 0, c.long_rows, c.long_seg_ptr, c.seg_long, c.counters, Z, ldzb, Y, ldyb,
+          H, epi, partial, zb, yb, static_cast<int>(g->N), halo_mask, halo_slot, *outs, nout, *hs);
+    GDA_LAUNCH_CHECK();
+    return GDA_OK;
+  }
   if (nb == 2) { if (has_epi) GDA_UNW_LAUNCH(10, true, 2); else GDA_UNW_LAUNCH(10, false, 2); }
   else if (per_sm == 12) { if (has_epi) GDA_UNW_LAUNCH(12, true, 1); else GDA_UNW_LAUNCH(12, false, 1); }
   else { if (has_epi) GDA_UNW_LAUNCH(16, true, 1); else GDA_UNW_LAUNCH(16, false, 1); }
@@ -1310,6 +1346,42 @@ int gda_row_scale_f32(const gda_graph_t* g, int nb, const float* X, int64_t ldx,
   return GDA_OK;
 }
 
+int gda_row_scale_rows_f32(const gda_graph_t* g, int64_t rows, int nb, const float* X, int64_t ldx, int64_t x_batch_stride,
+                           float* Z, int64_t ldz, int64_t z_batch_stride, int H, gda_stream_t stream) {
+  GDA_REQUIRE(g && g->dinv, "gda_row_scale_rows_f32: graph without a normalisation vector");
+  GDA_REQUIRE(rows >= 0 && rows <= g->N, "gda_row_scale_rows_f32: rows outside [0, N]");
+  GDA_REQUIRE(nb >= 1 && H > 0 && H % 4 == 0 && ldx % 4 == 0 && ldz % 4 == 0 && x_batch_stride % 4 == 0 &&
+                  z_batch_stride % 4 == 0,
+              "gda_row_scale_rows_f32: H, leading dimensions and batch strides must be multiples of 4");
+  GDA_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(Z) % 16 == 0,
+              "gda_row_scale_rows_f32: pointers must be 16-byte aligned");
+  if (rows == 0) return GDA_OK;
+  GDA_REQUIRE(X && Z, "gda_row_scale_rows_f32: NULL pointer");
+  const int64_t total = static_cast<int64_t>(nb) * rows * (H / 4);
+  int64_t blocks = gda::ceil_div(total, 256);
+  if (blocks > gda::kNumSMs * 16) blocks = gda::kNumSMs * 16;
+  gda::k_row_scale<<<static_cast<unsigned>(blocks), 256, 0, gda::as_stream(stream)>>>(
+      X, ldx, x_batch_stride, Z, ldz, z_batch_stride, g->dinv, rows, H / 4, nb);
+  GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_graph_export_dinv(const gda_graph_t* g, float* dinv_out, gda_stream_t stream) {
+  GDA_REQUIRE(g && g->dinv && dinv_out, "gda_graph_export_dinv: graph without a normalisation vector, or NULL output");
+  GDA_CUDA(cudaMemcpyAsync(dinv_out, g->dinv, sizeof(float) * g->N, cudaMemcpyDeviceToDevice, gda::as_stream(stream)));
+  return GDA_OK;
+}
+
+int gda_graph_set_unit_dinv(gda_graph_t* g, const float* dinv, gda_stream_t stream) {
+  GDA_REQUIRE(g && dinv, "gda_graph_set_unit_dinv: NULL argument");
+  GDA_REQUIRE(!g->peer_packed, "gda_graph_set_unit_dinv: not for partitioned (peer-packed) graphs");
+  if (g->N == 0) return GDA_OK;
+  if (!g->dinv) GDA_CUDA(cudaMalloc(&g->dinv, sizeof(float) * g->N));
+  GDA_CUDA(cudaMemcpyAsync(g->dinv, dinv, sizeof(float) * g->N, cudaMemcpyDeviceToDevice, gda::as_stream(stream)));
+  g->unit_weights = true;
+  return GDA_OK;
+}
+
 int gda_spmm_unw_nb_f32(const gda_graph_t* g, int transpose, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride,
                         float* Y, int64_t ldy, int64_t y_batch_stride, int H, int last, const float* bias, int epi_flags,
                         float dropout_p, uint64_t seed, const uint64_t* seed_offset, void* workspace,
@@ -1318,6 +1390,24 @@ int gda_spmm_unw_nb_f32(const gda_graph_t* g, int transpose, int nb, const float
   if (g->N == 0) return GDA_OK;
   return gda::spmm_unw(g, transpose, nb, Z, ldz, z_batch_stride, Y, ldy, y_batch_stride, H, last, bias, epi_flags,
                        dropout_p, seed, seed_offset, workspace, workspace_bytes, gda::as_stream(stream));
+}
+
+int gda_spmm_unw_halo_f32(const gda_graph_t* block, int nb, const float* Z, int64_t ldz, int64_t z_batch_stride, float* Y,
+                          int64_t ldy, int64_t y_batch_stride, int H, const int32_t* halo_mask, const int32_t* halo_slot,
+                          void* const* peer_base, const int64_t* peer_batch_stride, int num_peers, void* workspace,
+                          int64_t workspace_bytes, gda_stream_t stream) {
+  GDA_REQUIRE(block && halo_mask && halo_slot && peer_base && peer_batch_stride, "gda_spmm_unw_halo_f32: NULL argument");
+  GDA_REQUIRE(num_peers >= 1 && num_peers <= GDA_MAX_PEERS, "gda_spmm_unw_halo_f32: bad peer count");
+  if (block->N == 0) return GDA_OK;
+  gda::PeerTable ot;
+  gda::HaloStride hs;
+  for (int i = 0; i < GDA_MAX_PEERS; ++i) {
+    ot.p[i] = peer_base[i < num_peers ? i : 0];
+    hs.b[i] = static_cast<uint64_t>(peer_batch_stride[i < num_peers ? i : 0]) * sizeof(float);
+    GDA_REQUIRE(reinterpret_cast<uintptr_t>(ot.p[i]) % 16 == 0 && hs.b[i] % 16 == 0, "gda_spmm_unw_halo_f32: peer buffers must be 16-byte aligned");
+  }
+  return gda::spmm_unw(block, 0, nb, Z, ldz, z_batch_stride, Y, ldy, y_batch_stride, H, 0, nullptr, 0, 0.f, 0, nullptr,
+                       workspace, workspace_bytes, gda::as_stream(stream), halo_mask, halo_slot, &ot, num_peers, &hs);
 }
 
 int64_t gda_spmm_workspace_bytes(const gda_graph_t* g, int transpose, int H) {

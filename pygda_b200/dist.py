@@ -208,20 +208,28 @@ class PartitionedGraph:
         gda.peer_barrier_dev(self.flags.ptr_array, self.group.rank, self.group.world, ops._p(self.epoch_dev),
                              C.c_void_p(self.group.error.data_ptr()), _stream())
 
-    def spmm_k(self, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, seed_offset=None):
-        """A_hat^k x over the partition: x and the result are this rank's [n_local, H] blocks."""
+    def supports_nb(self, h, nb):
+        """True when ``nb`` stacked matrices can be aggregated in one pass (halo mode, H = 128)."""
+        return nb == 1 or (nb == 2 and self._halo is not None and h == 128)
+
+    def spmm_k(self, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, seed=0, seed_offset=None, nb=1):
+        """A_hat^k x over the partition: x and the result are this rank's [n_local, H] blocks (``nb`` of them
+        stacked: the paired bottleneck evaluations, halo mode only)."""
         x = ops._f32c(x)
-        n, h = x.shape
-        if n != self.num_nodes:
-            raise ValueError(f"x has {n} rows, this rank owns {self.num_nodes}")
+        rows, h = x.shape
+        n = rows // nb
+        if n != self.num_nodes or n * nb != rows:
+            raise ValueError(f"x has {rows} rows, this rank owns {self.num_nodes} (x {nb})")
+        if not self.supports_nb(h, nb):
+            raise NotImplementedError("stacked matrices are aggregated in one pass in halo mode at H = 128 only")
         g = self.group
         ws = self.workspace(transpose, h)
-        out = torch.empty(n, h, dtype=torch.float32, device=self.device)
+        out = torch.empty(rows, h, dtype=torch.float32, device=self.device)
         flags = (ops.EPI_RELU if relu else 0) | (ops.EPI_DROPOUT if dropout_p > 0 else 0)
         if self.push and h == 128:
             return self._spmm_k_push(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, ws, out)
         if self._halo is not None and h == 128:
-            return self._halo.spmm_k(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out)
+            return self._halo.spmm_k(x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out, nb)
         bufs = self._buffers(h)
         if ops.PROFILE is None:
             # barrier + copy-in + k x (barrier, peer aggregation) behind ONE call: k+2 fewer host round trips
@@ -344,30 +352,62 @@ class _HaloPlan:
                                       accumulate=True)                       # (row, peer) pairs are distinct: add == or
             self.halo_slot[r64 * g.world + p64] = self.push_slots
         self._bufs = {}
+        # The factored chain (D S (D^2 S)^(k-1) D, no per-edge weights: the single-GPU default) on the block: the
+        # block's weights are dinv[row] * dinv[col] of the WHOLE unit-weight graph, halo rows arrive scaled by their
+        # owners, so only this rank's own dinv entries are needed (gda_graph_set_unit_dinv).
+        self.unit = False
+        if load().gda_graph_unit_weights(full.handle, 0, 128, 1) == 1 and os.environ.get("GDA_HALO_UNW", "1") != "0":
+            dinv_full = torch.empty(part.global_nodes, dtype=torch.float32, device=dev)
+            gda.graph_export_dinv(full.handle, ops._p(dinv_full), _stream())
+            dinv_blk = torch.zeros(max(self.n_tot, 1), dtype=torch.float32, device=dev)
+            dinv_blk[:n_own] = dinv_full[lo:hi]
+            for gr in self.graphs:
+                gda.graph_set_unit_dinv(gr.handle, ops._p(dinv_blk), _stream())
+            torch.cuda.current_stream(dev).synchronize()           # dinv_blk / dinv_full may be freed now
+            self.unit = all(load().gda_graph_unit_weights(gr.handle, 0, 128, nb_) == 1
+                            for gr in self.graphs for nb_ in (1, 2))
+        # two stacked matrices: matrix m lives at rows [m * n_tot, (m + 1) * n_tot) of a rank's buffers -- n_tot differs
+        # from rank to rank, so a pushed row of matrix 1 lands n_tot OF THE RECEIVER rows further down
+        all_tot = [None] * g.world
+        dist.all_gather_object(all_tot, self.n_tot, group=g.pg)
+        self.peer_n_tot = [int(v) for v in all_tot]
+        self.push2 = None
+        if self.push_count:
+            peer_tot = torch.tensor(self.peer_n_tot, dtype=torch.int32, device=dev)[self.push_peer.long()]
+            self.push2 = (torch.cat([self.push_rows, self.push_rows + self.n_tot]),
+                          torch.cat([self.push_slots, self.push_slots + peer_tot]),
+                          torch.cat([self.push_peer, self.push_peer]))
 
-    def buffers(self, width):
-        b = self._bufs.get(width)
+    def buffers(self, width, nb=1):
+        b = self._bufs.get((width, nb))
         if b is None:
-            nbytes = max(self.n_tot, 1) * width * 4
+            nbytes = nb * max(self.n_tot, 1) * width * 4
             syms = (SymBuffer(self.part.group, nbytes), SymBuffer(self.part.group, nbytes))
-            b = self._bufs[width] = (syms, tuple(s_.view(torch.float32, (self.n_tot, width)) for s_ in syms))
+            b = self._bufs[(width, nb)] = (syms, tuple(s_.view(torch.float32, (nb * self.n_tot, width)) for s_ in syms))
         return b
 
-    def _push(self, view, sym, width):
+    def _push(self, view, sym, width, nb=1):
         if self.push_count:
             g = self.part.group
-            gda.push_rows_f32(ops._p(view), width, ops._p(self.push_rows), ops._p(self.push_slots),
-                              ops._p(self.push_peer), self.push_count, sym.ptr_array, g.world, width, width, _stream())
+            rows, slots, peer = (self.push_rows, self.push_slots, self.push_peer) if nb == 1 else self.push2
+            gda.push_rows_f32(ops._p(view), width, ops._p(rows), ops._p(slots), ops._p(peer), nb * self.push_count,
+                              sym.ptr_array, g.world, width, width, _stream())
 
-    def spmm_k(self, x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out):
-        part, (n, h) = self.part, x.shape
+    def spmm_k(self, x, k, transpose, bias, flags, dropout_p, seed, seed_offset, out, nb=1):
+        part, h = self.part, x.shape[1]
+        n, nt = x.shape[0] // nb, self.n_tot
         gr = self.graphs[1 if transpose else 0]
-        syms, views = self.buffers(h)
-        ws = gr.workspace(False, h)
+        syms, views = self.buffers(h, nb)
+        ws = gr.workspace(False, h * nb)
         seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        unit = self.unit
         part._barrier()                                   # every rank is done with the buffers of the last call
-        views[0][:n].copy_(x)
-        self._push(views[0], syms[0], h)
+        if unit:                                          # z0 = D x on this rank's own rows
+            gda.row_scale_rows_f32(gr.handle, n, nb, ops._p(x), h, n * h, ops._p(views[0]), h, nt * h, h, _stream())
+        else:
+            for m in range(nb):
+                views[0][m * nt:m * nt + n].copy_(x[m * n:(m + 1) * n])
+        self._push(views[0], syms[0], h, nb)
         for i in range(k):
             last = i == k - 1
             part._barrier()                               # step i-1 (or the copy-in) and its halo pushes have landed
@@ -376,6 +416,27 @@ class _HaloPlan:
             if prof is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
+            if unit or nb > 1:
+                y, ys = (out, n * h) if last else (dst_v, nt * h)
+                tail = (ops._p(bias if last else None), flags if last else 0, float(dropout_p if last else 0.0), seed,
+                        ops._p(seed_offset), ops._p(ws), ws.numel(), _stream())
+                fused = unit and not last and FUSED_HALO
+                if fused:                                 # z' = D^2 S z, halo rows stored to their consumers as they finish
+                    strides = (C.c_int64 * part.group.world)(*[t_ * h for t_ in self.peer_n_tot])
+                    gda.spmm_unw_halo_f32(gr.handle, nb, ops._p(src), h, nt * h, ops._p(y), h, ys, h,
+                                          ops._p(self.halo_mask), ops._p(self.halo_slot), dst_s.ptr_array, strides,
+                                          part.group.world, ops._p(ws), ws.numel(), _stream())
+                elif unit:                                # (y = D S z on the last step): no edge weights
+                    gda.spmm_unw_nb_f32(gr.handle, 0, nb, ops._p(src), h, nt * h, ops._p(y), h, ys, h, int(last), *tail)
+                else:
+                    gda.spmm_nb_f32(gr.handle, 0, nb, ops._p(src), h, nt * h, ops._p(y), h, ys, h, *tail)
+                if prof is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    prof.append((e0, e1, (n, h, "float32", nb, "unit-weight-halo" if unit else "weighted-halo")))
+                if not last and not fused:
+                    self._push(dst_v, dst_s, h, nb)
+                continue
             if last or not FUSED_HALO:
                 gda.spmm_f32(gr.handle, 0, ops._p(src), h, ops._p(out if last else dst_v), h, h,
                              ops._p(bias if last else None), flags if last else 0, float(dropout_p if last else 0.0),

@@ -25,6 +25,7 @@ class DistA2GNN(A2GNN):
             raise NotImplementedError("the partitioned path covers node-level A2GNN with the MMD loss")
         self.group = group
         self.overlap_streams = True
+        self.pair_evaluations = True
 
     def init_model(self, **kwargs):
         net = super().init_model(**kwargs)
@@ -54,17 +55,35 @@ class DistA2GNN(A2GNN):
         main = torch.cuda.current_stream()
         side = self._side_stream() if self.overlap_streams else main
         side.wait_stream(main)
+        # the two bottleneck evaluations per domain (a2gnn.py:181/192, 193/211) in one stacked pass, as on one GPU
+        # (A2GNNBase.feat_bottleneck_pair), when the partition can aggregate two matrices per exchange (halo mode)
+        def pair_ok(data, k):
+            part = getattr(data.edge_index, "_gda_partition", None)
+            if part is None or not self.pair_evaluations:
+                return False
+            gr = part.graph(data.edge_index, 1 | 4)
+            return k == 0 or gr.supports_nb(self.hid_dim, 2)
         with torch.cuda.stream(side):
             s1 = net.first_conv(source_data.x, source_data.edge_index, self.s_pnums)
-            source_logits = net(source_data, self.s_pnums, first_layer=s1)
+            if pair_ok(source_data, self.s_pnums):
+                s_feat_1, source_features = net.feat_bottleneck_pair(
+                    source_data.x, source_data.edge_index, None, self.s_pnums, first_layer=s1)
+                source_logits = net.feat_classifier(s_feat_1, source_data.edge_index, None, prop_nums=1)
+            else:
+                source_logits = net(source_data, self.s_pnums, first_layer=s1)
+                source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, None, self.s_pnums,
+                                                      first_layer=s1)
             ce_local = ops.softmax_cross_entropy(source_logits, source_data.y)
             frac = source_data.x.shape[0] / float(source_data.num_nodes_global)
             train_loss = AllReduceSum.apply(ops.combine([(ce_local, frac)]), pg)   # global mean CE
-            source_features = net.feat_bottleneck(source_data.x, source_data.edge_index, None, self.s_pnums,
-                                                  first_layer=s1)
         t1 = net.first_conv(target_data.x, target_data.edge_index, self.t_pnums)
-        target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, None, self.t_pnums,
-                                              first_layer=t1)
+        t_pair = pair_ok(target_data, self.t_pnums)
+        if t_pair:
+            target_features, t_feat_2 = net.feat_bottleneck_pair(
+                target_data.x, target_data.edge_index, None, self.t_pnums, first_layer=t1)
+        else:
+            target_features = net.feat_bottleneck(target_data.x, target_data.edge_index, None, self.t_pnums,
+                                                  first_layer=t1)
         if side is not main:
             main.wait_stream(side)
             for t in (source_logits, train_loss, source_features):
@@ -76,7 +95,10 @@ class DistA2GNN(A2GNN):
         ar = torch.arange(times * b, device=s_rows.device).view(times, b)
         mmd_loss = ops.MMDFn.apply(s_rows, t_rows, ar, ar.clone(), 2.0, 5)          # replicated on every rank
         loss = ops.combine([(train_loss, 1.0), (mmd_loss, float(self.weight))])
-        target_logits = net(target_data, self.t_pnums, first_layer=t1)
+        if t_pair:
+            target_logits = net.feat_classifier(t_feat_2, target_data.edge_index, None, prop_nums=1)
+        else:
+            target_logits = net(target_data, self.t_pnums, first_layer=t1)
         return loss, source_logits, target_logits
 
     def backward_and_step(self, loss, optimizer):

@@ -93,7 +93,8 @@ class PropGCNConv(nn.Module):
         as one stacked GEMM and one batched aggregation per step (ops.PairGraphConvActFn)."""
         k = int(prop_nums)
         graph = self._graph(xa, edge_index, edge_weight) if k > 0 else None
-        if graph is not None and hasattr(graph, "spmm_k"):        # partitioned graph: one matrix per call
+        if graph is not None and hasattr(graph, "spmm_k") and not graph.supports_nb(self.out_channels, 2):
+            # partitioned graph outside halo mode: one matrix per exchange
             import torch.nn.functional as F
             return tuple(ops.act_dropout(ops.graph_conv(x, self.lin.weight, self.bias, graph, k), F.relu,
                                          dropout_p, True) for x in (xa, xb))

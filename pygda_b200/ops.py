@@ -126,11 +126,9 @@ def spmm_k(graph, x, k, transpose=False, bias=None, relu=False, dropout_p=0.0, s
     """A_hat^k X with ping-pong buffers; the epilogue is applied on the last step."""
     if k == 0:
         raise ValueError("spmm_k needs k >= 1")
-    if hasattr(graph, "spmm_k"):          # row-partitioned graph: NVLink peer path (pygda_b200/dist.py)
-        if nb != 1:
-            raise NotImplementedError("the peer path aggregates one matrix per call")
+    if hasattr(graph, "spmm_k"):          # row-partitioned graph: NVLink path (pygda_b200/dist.py)
         return graph.spmm_k(x, k, transpose=transpose, bias=bias, relu=relu, dropout_p=dropout_p, seed=seed,
-                            seed_offset=seed_offset)
+                            seed_offset=seed_offset, nb=nb)
     if x.dtype == torch.float32 and PROFILE is not None and x.is_contiguous() and \
             unit_weight_chain(graph, transpose, x.shape[1], nb, k):
         return _spmm_k_unw_profiled(graph, x, k, transpose, bias, relu, dropout_p, seed, seed_offset, nb)

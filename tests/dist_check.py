@@ -54,6 +54,18 @@ def main():
             ok &= bool(torch.equal(out, again))
             if rank == 0:
                 print(f"{mode} spmm k={k} T={transpose}: rel err {e:.2e}, remote fraction {part.remote_fraction:.2f}")
+        if mode == "halo":
+            # two stacked matrices per exchange (the paired bottleneck evaluations): each equals its own single pass
+            x2 = torch.cat([x[lo:hi], x[lo:hi].flip(1)]).contiguous()
+            for k, transpose in ((1, False), (3, False), (4, True)):
+                both = part.spmm_k(x2, k, transpose=transpose, bias=bias, relu=True, nb=2)
+                one_a = part.spmm_k(x2[:hi - lo].contiguous(), k, transpose=transpose, bias=bias, relu=True)
+                one_b = part.spmm_k(x2[hi - lo:].contiguous(), k, transpose=transpose, bias=bias, relu=True)
+                same = bool(torch.equal(both[:hi - lo], one_a)) and bool(torch.equal(both[hi - lo:], one_b))
+                ok &= same
+                if rank == 0:
+                    print(f"halo spmm nb=2 k={k} T={transpose}: identical to two single passes: {same}, "
+                          f"factored (unit-weight) chain: {part._halo.unit}")
         group.check()
         del part
     os.environ.pop("GDA_DIST_MODE", None)
