@@ -661,6 +661,36 @@ __device__ __forceinline__ void gather_batch(float (&acc)[NB][VEC], int myc, flo
       for (int v = 0; v < VEC; ++v) acc[b][v] = fmaf(wv[u], xv[u][b][v], acc[b][v]);
 }
 
+// Ordered sum of the segment partials of a split long row (the last segment to arrive reduces): same order as a plain
+// loop -- bit-identical -- but the loads of eight segments are in flight together.  The biggest hub of the config-2
+// graph has > 100 segments; summed four at a time with scalar loads this one warp was the tail of the launch
+// (profiles/r2_d_structure/segment_length_ab.log: 50.7 us with long rows vs 41.3 us without).
+template <int VEC>
+__device__ __forceinline__ void sum_partials(float (&acc)[VEC], const float* __restrict__ base, int nseg, int64_t stride) {
+  static_assert(VEC % 4 == 0, "partials are read 16 bytes at a time");
+  int sgi = 0;
+  for (; sgi + 8 <= nseg; sgi += 8) {
+    float4 t[8][VEC / 4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q)
+        t[u][q] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<int64_t>(sgi + u) * stride) + q);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q) {
+        acc[4 * q] += t[u][q].x; acc[4 * q + 1] += t[u][q].y; acc[4 * q + 2] += t[u][q].z; acc[4 * q + 3] += t[u][q].w;
+      }
+  }
+  for (; sgi < nseg; ++sgi)
+#pragma unroll
+    for (int q = 0; q < VEC / 4; ++q) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(base + static_cast<int64_t>(sgi) * stride) + q);
+      acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+    }
+}
+
 // NB > 1: NB feature matrices (xbsb / ybsb bytes apart, `nrows` rows each) share the graph -- one index read and one
 // dependency chain per row for NB gathers (the two bottleneck evaluations of a domain, models/a2gnn.py).
 // PUSH (partitioned graphs with little locality, dist.py): the output row is stored into the row block of this rank
@@ -791,10 +821,15 @@ k_spmm_tasks(const uint2* __restrict__ tasks, int num_tasks, const int* __restri
         for (int b = 0; b < NB; ++b) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) acc[b][v] = 0.f;
-          for (int sgi = 0; sgi < nseg; ++sgi) {
-            const float* srcp = partial + static_cast<int64_t>(first + sgi) * (NB * H) + b * H + c0;
+          if (VEC % 4 == 0) {
+            sum_partials<(VEC % 4 == 0 ? VEC : 4)>(reinterpret_cast<float(&)[(VEC % 4 == 0 ? VEC : 4)]>(acc[b]),
+                                                   partial + static_cast<int64_t>(first) * (NB * H) + b * H + c0, nseg, NB * H);
+          } else {
+            for (int sgi = 0; sgi < nseg; ++sgi) {
+              const float* srcp = partial + static_cast<int64_t>(first + sgi) * (NB * H) + b * H + c0;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[b][v] += __ldcg(srcp + v);
+              for (int v = 0; v < VEC; ++v) acc[b][v] += __ldcg(srcp + v);
+            }
           }
           if (EPI) apply_epilogue<VEC>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
           if (PUSH) {
@@ -954,11 +989,7 @@ k_spmm_unw(const uint2* __restrict__ tasks, int num_tasks, const int* __restrict
         for (int b = 0; b < NB; ++b) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) acc[b][v] = 0.f;
-          for (int sgi = 0; sgi < nseg; ++sgi) {
-            const float* srcp = partial + static_cast<int64_t>(first + sgi) * (NB * H) + b * H + c0;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) acc[b][v] += __ldcg(srcp + v);
-          }
+          sum_partials<4>(acc[b], partial + static_cast<int64_t>(first) * (NB * H) + b * H + c0, nseg, NB * H);
 #pragma unroll
           for (int v = 0; v < 4; ++v) acc[b][v] *= sc;
           if (EPI) apply_epilogue<4>(acc[b], epi, static_cast<int64_t>(b) * nrows + row, c0, H);
