@@ -675,7 +675,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "mmd_weight": CFG["weight"], "optimizer": "Adam lr=0.01 wd=0.005",
                        "epoch_definition": "full-batch: 1 epoch = 1 optimiser step; F1/logging excluded",
                        "parallelism": parallelism, "issue": graph_note,
-                       "l2_policy": "inputs larger than L2 (x is 2.7 GB per domain, streamed every step); "
+                       "l2_policy": "working set larger than L2 (tile-packed x, 0.24 GB per domain, streamed 4x per "
+                                    "step; ~20 fp32 [100k,128] activation matrices of 51 MB written and re-read); "
                                     "no explicit flush",
                        "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
