@@ -121,9 +121,13 @@ int splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float alp
 int simt_splits(int64_t M, int64_t N, int64_t K) {
   const int bn = N > 32 ? 128 : 32;
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, bn);
-  if (tiles >= 2 * kNumSMs || K < 4096) return 1;
+  // A reduction with few output tiles is split over K until the SMs are covered, down to 128 of K per split.  (Round 1
+  // split only for K >= 4096 in chunks of >= 1024: the critic's weight gradients of AdaGCN's mini-batch step --
+  // [40 | 128, rows <= 1536] x [rows, 128], ONE 128 x 128 tile -- ran 95 times per step on a single CTA for 268 us each,
+  // 70 % of the step's GPU time: profiles/r2_l_config5_host/.)
+  if (tiles >= 2 * kNumSMs || K < 256) return 1;
   int64_t want = ceil_div(2 * kNumSMs, tiles);
-  int64_t maxs = ceil_div(K, 1024);
+  int64_t maxs = ceil_div(K, 128);
   int64_t s = want < maxs ? want : maxs;
   return s < 1 ? 1 : static_cast<int>(s);
 }

@@ -194,18 +194,46 @@ __global__ void k_export_coo(const int* __restrict__ src, const int* __restrict_
   out[nnz + p] = dst[p];
 }
 
+// Graph storage comes from the device's stream-ordered memory pool (cudaMallocAsync) with the release threshold
+// raised, so that the ~25 allocations of a graph build cost microseconds instead of ~0.2 ms each: graph-level
+// estimators build two graphs per MINI-BATCH (a new edge_index every step) -- 4.9 ms per build, a fifth of the
+// host-bound AdaGCN step, with plain cudaMalloc / cudaFree (profiles/r2_l_config5_host/).
+thread_local cudaStream_t t_alloc_stream = nullptr;
+
+struct AllocScope {          // the stream the build runs on: allocations and scratch frees are ordered on it
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t s) : prev(t_alloc_stream) {
+    t_alloc_stream = s;
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != pool_ready_dev) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~uint64_t(0);
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready_dev = dev;
+    }
+  }
+  ~AllocScope() { t_alloc_stream = prev; }
+};
+
 template <typename T>
 int dev_alloc(T** p, int64_t n) {
   *p = nullptr;
   // + 64 bytes of slack: the aggregation kernels prefetch the next batch's column indices with unconditional loads
   // that may run up to 3 entries past the last non-zero (spmm.cu: k_spmm_unw)
-  GDA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * static_cast<size_t>(n > 0 ? n : 1) + 64));
+  GDA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), sizeof(T) * static_cast<size_t>(n > 0 ? n : 1) + 64, t_alloc_stream));
   return GDA_OK;
 }
 
-struct Scratch {   // frees temporaries on every exit path
+inline void dev_free(void* p) {        // graph members: the owner has synchronised the device (see ~gda_graph)
+  if (p) cudaFreeAsync(p, nullptr);
+}
+
+struct Scratch {   // frees temporaries on every exit path (ordered after the build's kernels on its stream)
   std::vector<void*> ptrs;
-  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  ~Scratch() { for (void* p : ptrs) if (p) cudaFreeAsync(p, t_alloc_stream); }
   template <typename T> int get(T** p, int64_t n) {
     int rc = dev_alloc(p, n);
     if (rc == GDA_OK) ptrs.push_back(*p);
@@ -311,10 +339,15 @@ int build_long_rows(Csr& c, int64_t N, int seg, Scratch& sc, cudaStream_t st) {
 }
 
 void free_csr(Csr& c) {
-  cudaFree(c.rowptr); cudaFree(c.colidx); cudaFree(c.vals);
-  cudaFree(c.long_rows); cudaFree(c.long_seg_ptr); cudaFree(c.seg_long); cudaFree(c.counters);
-  cudaFree(c.tasks);
+  dev_free(c.rowptr); dev_free(c.colidx); dev_free(c.vals);
+  dev_free(c.long_rows); dev_free(c.long_seg_ptr); dev_free(c.seg_long); dev_free(c.counters);
+  dev_free(c.tasks);
   c = Csr{};
+}
+
+void free_graph_members(gda_graph* g) {
+  dev_free(g->coo_src); dev_free(g->coo_dst); dev_free(g->coo_w); dev_free(g->dinv);
+  free_csr(g->csr); free_csr(g->csr_t);
 }
 
 }  // namespace
@@ -323,6 +356,7 @@ int graph_create(const int64_t* ei, int64_t E, int64_t N, const float* w, int fl
                  gda_graph** out) {
   GDA_REQUIRE(out != nullptr, "gda_graph_create: out is NULL");
   *out = nullptr;
+  AllocScope alloc_scope(st);
   GDA_REQUIRE(N >= 0 && E >= 0, "gda_graph_create: negative size");
   GDA_REQUIRE(E == 0 || ei != nullptr, "gda_graph_create: edge_index is NULL");
   GDA_REQUIRE(E + N < (int64_t(1) << 31) - 1, "gda_graph_create: E + N must fit in int32");
@@ -469,6 +503,7 @@ int graph_partition(const gda_graph* g, int64_t row_lo, int64_t row_hi, int64_t 
                     gda_graph** out) {
   GDA_REQUIRE(g && out, "gda_graph_partition: NULL argument");
   *out = nullptr;
+  AllocScope alloc_scope(st);
   GDA_REQUIRE(!g->peer_packed, "gda_graph_partition: already a partition");
   GDA_REQUIRE(!g->csr.may_have_empty_rows, "gda_graph_partition: needs a graph built with self loops");
   GDA_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= g->N, "gda_graph_partition: bad row range");
@@ -532,6 +567,7 @@ int graph_export_csr(const gda_graph* g, int transpose, int32_t* rowptr, int32_t
 }  // namespace gda
 
 gda_graph::~gda_graph() {
-  cudaFree(coo_src); cudaFree(coo_dst); cudaFree(coo_w); cudaFree(dinv);
-  gda::free_csr(csr); gda::free_csr(csr_t);
+  // kernels on ANY stream may still read the graph (cudaFree used to wait for them implicitly, once per pointer)
+  cudaDeviceSynchronize();
+  gda::free_graph_members(this);
 }

@@ -30,7 +30,7 @@ FUSED_HALO = os.environ.get("GDA_HALO_FUSED", "1") != "0"     # A/B switch: 0 = 
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def rows_per_rank(n, world):

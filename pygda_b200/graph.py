@@ -17,7 +17,7 @@ SELF_LOOPS, IMPROVED, NORM_SYM_COL, NORM_SYM_ROW, SKIP_EMPTY_ROWS = 1, 2, 4, 8, 
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _ptr(t):

@@ -12,13 +12,18 @@ import torch
 from ._lib import gda, load
 
 EPI_RELU, EPI_DROPOUT = 1, 2
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
 _NULL = C.c_void_p(0)
 # bench.py sets this to a list to collect (start_event, end_event, (N, H, dtype)) per aggregation launch
 PROFILE = None
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The calling thread's CURRENT CUDA stream as a raw handle.  torch.cuda.current_stream() builds a Stream object
+    through several Python layers (16 us per call -- 9 ms of the 47 ms host-bound AdaGCN mini-batch step,
+    profiles/r2_l_config5_host); the raw accessor is the same query without them."""
+    return C.c_void_p(_raw_stream(_cur_device()))
 
 
 def _p(t):
@@ -1095,10 +1100,19 @@ def global_mean_pool(x, batch, size=None):
     if batch is None:
         ptr = torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device)
         return SegmentMeanFn.apply(x, ptr)
+    # the segment pointers are a function of ``batch`` alone: computed once per batch tensor (AdaGCN's step pools the
+    # same mini-batch 22 times, adagcn.py:169-198 -- a device->host sync, a bincount and a scan each time otherwise)
+    cached = getattr(batch, "_gda_pool_ptr", None)
+    if cached is not None and cached[0] == (batch._version, size):
+        return SegmentMeanFn.apply(x, cached[1])
     g = int(batch.max().item()) + 1 if size is None else int(size)
     counts = torch.bincount(batch, minlength=g)
     ptr = torch.zeros(g + 1, dtype=torch.int64, device=x.device)
     ptr[1:] = torch.cumsum(counts, 0)
+    try:
+        batch._gda_pool_ptr = ((batch._version, size), ptr)
+    except Exception:                                  # noqa: BLE001 -- exotic tensor subclasses: just do not cache
+        pass
     return SegmentMeanFn.apply(x, ptr)
 
 

@@ -73,7 +73,7 @@ class Adam:
                 p.grad = None
             else:
                 gda.fill_f32(C.c_void_p(p.grad.data_ptr()), p.grad.numel(), 0.0,
-                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                             C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())))
 
     def _bucket(self):
         """Assign every live parameter to a bucket consistent with its history; returns the buckets to step."""
@@ -99,7 +99,7 @@ class Adam:
 
     @torch.no_grad()
     def step(self):
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
         self._nstep += 1
         for g in self._bucket():
             live = list(zip(g.params, g.exp_avg, g.exp_avg_sq))
