@@ -291,6 +291,7 @@ def gemm_split(a, b, trans_a, trans_b, m, n, k):
 
 # ---- first-layer products from a TILE-PACKED sparse input matrix (csrc/gemm_xt.cu) ----
 XT_DENSITY = 0.10        # above this the sub-tiles outgrow the expanders' register prefetch: dense split path
+XT_MIN_COLS = 512        # fewer than 8 K blocks per CTA: the pipeline never fills, the dense kernel streams as fast
 XT_ENABLED = True
 
 
@@ -311,7 +312,7 @@ def x_tiles(x, n_out):
     """``XTiles`` to multiply ``x`` [rows, cols] from, or None: the packed copy ``Data.to`` attached to a staged
     ``x`` (``_gda_tiles``), or -- for a device-resident matrix marked constant (``mark_constant`` / the full-batch
     loaders) -- a packed form built once (``tiles_cache``) when at most ``XT_DENSITY`` of it is non-zero."""
-    if not XT_ENABLED or x.dim() != 2 or x.dtype != torch.float32 or x.requires_grad:
+    if not XT_ENABLED or x.dim() != 2 or x.dtype != torch.float32 or x.requires_grad or x.shape[1] < XT_MIN_COLS:
         return None
     if not tc_eligible(x.shape[0], max(int(n_out), 64), x.shape[1]):
         return None
