@@ -154,6 +154,9 @@ def check(rc, what):
         raise GdaError(f"{what} failed (code {rc}): {msg}")
 
 
+NVTX = os.environ.get("GDA_NVTX") == "1"      # one NVTX range per C-ABI call (timelines: nsys / ncu --nvtx)
+
+
 class _Caller:
     """``gda.<name>(...)`` with status checking: ``from pygda_b200._lib import gda``."""
 
@@ -161,8 +164,18 @@ class _Caller:
         full = "gda_" + name
         fn = getattr(load(), full)
         if full in _STATUS:
-            def wrapped(*a, _fn=fn, _n=full):
-                check(_fn(*a), _n)
+            if NVTX:
+                import torch
+
+                def wrapped(*a, _fn=fn, _n=full, _push=torch.cuda.nvtx.range_push, _pop=torch.cuda.nvtx.range_pop):
+                    _push(_n)
+                    try:
+                        check(_fn(*a), _n)
+                    finally:
+                        _pop()
+            else:
+                def wrapped(*a, _fn=fn, _n=full):
+                    check(_fn(*a), _n)
             setattr(self, name, wrapped)
             return wrapped
         setattr(self, name, fn)

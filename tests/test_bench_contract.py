@@ -20,8 +20,11 @@ def _check_common(line):
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    line = json.load(open(os.path.join(ROOT, "profiles", "r1_j_final", "bench.json")))
+    raw = open(os.path.join(ROOT, "profiles", "r2_m_final", "bench.json")).read()
+    line = json.loads([l for l in raw.splitlines() if l.startswith("{")][-1])
     _check_common(line)
+    g = line["roofline"]["gemm"]["forward"]                  # round 2: the tile-packed first layer reports its own bound
+    assert g["bound"] == "tensor" and g["unit"] == "TFLOP/s" and abs(g["frac"] - g["achieved"] / g["peak"]) < 1e-9
     assert line["value"] > 0 and line["gpu_launches"] > 0 and line["warmup"] >= 3
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["e2e"]["value"] != line["value"]

@@ -150,6 +150,44 @@ def test_packed_rows_format_roundtrip_on_the_host():
     assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
 
 
+def test_packed_tiles_format_roundtrip_on_the_host():
+    """Host half of the TILE-PACKED form (pygda_b200/data.py: PackedTiles) -- the operand form of the first layer's
+    tensor-core GEMMs (csrc/gemm_xt.cu) and the pinned staging form of a sparse x: sub-tiles of 32 rows x 64 columns in
+    strip-major order, entries sorted by position, one low-position byte per entry, eight cumulative segment counts per
+    sub-tile.  Decoded with the rule the kernels implement (entry i sits at ((# segment boundaries <= i) << 8) | code),
+    the arrays reproduce the matrix bit for bit; the strip count is padded to a multiple of 4."""
+    import numpy as np
+    from pygda_b200.data import Data, PackedTiles
+    g = torch.Generator().manual_seed(0)
+    for n, f, dens in ((300, 6775, 0.05), (33, 70, 0.5), (5, 1, 1.0), (129, 4100, 0.0005), (64, 64, 1.0)):
+        x = torch.where(torch.rand(n, f, generator=g) < dens, torch.randn(n, f, generator=g), torch.zeros(()))
+        x[0, f - 1] = 2.0
+        if n > 1:
+            x[1].zero_()                                      # an empty row
+        if f > 3:
+            x[2 % n, 3] = -0.0                                # kept: the BIT PATTERN is non-zero
+        p = PackedTiles(x, chunk=64, pin=False)
+        nkb, nstrips = -(-f // 64), -(-(-(-n // 32)) // 4) * 4
+        assert p.shape == (n, f) and p.ptr.numel() == nstrips * nkb + 1 and tuple(p.seg.shape) == (nstrips * nkb, 8)
+        vals, codes = p.vals.numpy(), p.codes.numpy()
+        ptr, seg = p.ptr.numpy().astype(np.int64), p.seg.numpy().astype(np.int64)
+        assert int(ptr[-1]) == p.vals.numel() == p.codes.numel() == int((x.view(torch.int32) != 0).sum())
+        assert np.all(np.diff(seg, axis=1) >= 0) and np.array_equal(seg[:, 7], np.diff(ptr))
+        dense = np.zeros((n, f), dtype=np.float32)
+        for t in range(nstrips * nkb):
+            last = -1
+            for i in range(ptr[t + 1] - ptr[t]):
+                pos = int((seg[t, :7] <= i).sum()) * 256 + int(codes[ptr[t] + i])
+                assert pos > last and pos < 2048                  # strictly ascending inside a sub-tile
+                last = pos
+                dense[(t // nkb) * 32 + pos // 64, (t % nkb) * 64 + pos % 64] = vals[ptr[t] + i]
+        assert np.array_equal(dense.view(np.int32), x.numpy().view(np.int32))
+        assert torch.equal(p.decode().view(torch.int32), x.view(torch.int32))
+        assert p.nbytes == 5 * p.vals.numel() + 4 * (nstrips * nkb + 1) + 16 * nstrips * nkb
+    d = Data(x=torch.zeros(10, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.zeros(10, dtype=torch.long))
+    assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
+
+
 def test_graph_loader_batches_follow_torchs_own_sampler():
     """PyG's DataLoader is torch's DataLoader with a graph collate: for the same torch seed our loader must yield the
     same graphs per batch and consume the CPU generator identically (pygda/models/a2gnn.py:276-286)."""
