@@ -206,75 +206,96 @@ __global__ void k_mmd_finalize(MmdWs ws, int times, float* loss_out) {
   *loss_out = static_cast<float>(s / times);
 }
 
-// grad tile: rows i0..i0+63 of sample t, feature columns c0..c0+63
-__global__ void __launch_bounds__(THREADS)
+// grad tile: rows i0..i0+127 of sample t, feature columns c0..c0+127, one slice of the j (reduction) range.
+// 256 threads, 8 x 8 outputs each (two 4-row and two 4-column groups, 64 apart): per j step a thread reads four float4
+// from shared memory for 64 FMAs.  (Round 1's 64 x 64 tile with 4 x 4 outputs per thread read five words per 16 FMAs and
+// ran at 15 TFLOP/s: 330 us for the 5.1 GFLOP of the config-2 step, 5 % of it, on the critical path after both branches.)
+constexpr int BT = 128, BJ = 16;
+
+__global__ void __launch_bounds__(THREADS, 2)
 k_mmd_bwd(const float* __restrict__ src, int64_t lds, const float* __restrict__ tgt, int64_t ldt, int d,
           const int64_t* __restrict__ src_idx, const int64_t* __restrict__ tgt_idx, int b, int times,
           const float* __restrict__ grad_scale, float* __restrict__ gsrc, int64_t ldgs,
-          float* __restrict__ gtgt, int64_t ldgt, MmdWs ws) {
-  constexpr int JK = 16;
-  __shared__ float Gs[JK][TILE + 1];          // G[i, j] stored [j][i]
-  __shared__ float Xs[JK][TILE + 4];          // x_j[c]  stored [j][c]
-  // blockIdx.z = sample * JSPLIT + slice of the j (reduction) range: 4x more CTAs than tiles
-  const int n = 2 * b, t = blockIdx.z / JSPLIT, js = blockIdx.z % JSPLIT;
-  const int jchunk = ((n + JSPLIT - 1) / JSPLIT + JK - 1) / JK * JK;
+          float* __restrict__ gtgt, int64_t ldgt, MmdWs ws, int jsplit) {
+  // two shared-memory stages: the global loads of block k + 1 are in flight (in registers) while block k is multiplied
+  __shared__ __align__(16) float Gs[2][BJ][BT + 4];       // G[i, j] stored [j][i]
+  __shared__ __align__(16) float Xs[2][BJ][BT + 4];       // x_j[c]  stored [j][c]
+  const int n = 2 * b, t = blockIdx.z / jsplit, js = blockIdx.z % jsplit;
+  const int jchunk = ((n + jsplit - 1) / jsplit + BJ - 1) / BJ * BJ;
   const int jbeg = js * jchunk, jend = min(n, jbeg + jchunk);
-  const int i0 = blockIdx.y * TILE, c0 = blockIdx.x * TILE;
+  const int i0 = blockIdx.y * BT, c0 = blockIdx.x * BT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const float* G = ws.G + (int64_t)t * n * n;
-  float acc[4][4];
+  constexpr int PER = BT * BJ / THREADS;                   // 8 elements of each tile per thread
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int j0 = jbeg; j0 < jend; j0 += JK) {
+  float rg[PER], rx[PER];
+  auto fetch = [&](int j0) {
 #pragma unroll
-    for (int s = 0; s < TILE * JK / THREADS; ++s) {
+    for (int s = 0; s < PER; ++s) {
       const int e = tid + s * THREADS;
       {   // G tile: j fastest in memory
-        const int j = e % JK, i = e / JK;
-        const int gi = i0 + i, gj = j0 + j;
-        Gs[j][i] = (gi < n && gj < jend) ? G[(int64_t)gi * n + gj] : 0.f;
+        const int gi = i0 + e / BJ, gj = j0 + e % BJ;
+        rg[s] = (gi < n && gj < jend) ? __ldg(G + (int64_t)gi * n + gj) : 0.f;
       }
       {   // X tile: c fastest in memory
-        const int c = e % TILE, j = e / TILE;
-        const int gj = j0 + j, gc = c0 + c;
-        float v = 0.f;
-        if (gj < jend && gc < d) v = __ldg(sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gj) + gc);
-        Xs[j][c] = v;
+        const int gj = j0 + e / BT, gc = c0 + e % BT;
+        rx[s] = (gj < jend && gc < d) ? __ldg(sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gj) + gc) : 0.f;
       }
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf) {
 #pragma unroll
-    for (int jj = 0; jj < JK; ++jj) {
-      float a[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Gs[jj][ty * 4 + i];
-      const float4 xv = *reinterpret_cast<const float4*>(&Xs[jj][tx * 4]);
-      const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], xx[j], acc[i][j]);
+    for (int s = 0; s < PER; ++s) {
+      const int e = tid + s * THREADS;
+      Gs[buf][e % BJ][e / BJ] = rg[s];
+      Xs[buf][e / BT][e % BT] = rx[s];
     }
+  };
+
+  int buf = 0;
+  if (jbeg < jend) { fetch(jbeg); stash(0); }
+  __syncthreads();
+  for (int j0 = jbeg; j0 < jend; j0 += BJ) {
+    const bool more = j0 + BJ < jend;
+    if (more) fetch(j0 + BJ);
+#pragma unroll
+    for (int jj = 0; jj < BJ; ++jj) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Gs[buf][jj][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Gs[buf][jj][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Xs[buf][jj][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Xs[buf][jj][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float x[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], x[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);          // the other stage: nobody reads it during this block
     __syncthreads();
+    buf ^= 1;
   }
 
   const float scale = 4.f * (*grad_scale) / static_cast<float>(times);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gi = i0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int gi = i0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (gi >= n) continue;
     const float rs = (js == 0) ? ws.rowsum[(int64_t)t * n + gi] : 0.f;   // row-sum term added once
     const float* xi = sample_row(src, lds, tgt, ldt, src_idx, tgt_idx, t, b, gi);
     float* dst = (gi < b) ? gsrc + src_idx[(int64_t)t * b + gi] * ldgs
                           : gtgt + tgt_idx[(int64_t)t * b + (gi - b)] * ldgt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gc = c0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int gc = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (gc >= d) continue;
-      atomicAdd(dst + gc, scale * (rs * __ldg(xi + gc) - acc[i][j]));
+      const float own = (js == 0) ? rs * __ldg(xi + gc) : 0.f;
+      atomicAdd(dst + gc, scale * (own - acc[i][j]));
     }
   }
 }
@@ -326,9 +347,15 @@ int gda_mmd_bwd(const float* src, int64_t lds, const float* tgt, int64_t ldt, in
     return fail(GDA_E_WORKSPACE, "gda_mmd_bwd: workspace too small");
   const int n = 2 * b;
   MmdWs ws = carve(workspace, times, n);
-  dim3 grid(static_cast<unsigned>(ceil_div(d, TILE)), static_cast<unsigned>(ceil_div(n, TILE)), times * JSPLIT);
+  // slices of the reduction range: fill the 2 x 148 resident CTAs without going far past them
+  const int64_t tiles = ceil_div(d, BT) * ceil_div(n, BT) * times;
+  int jsplit = static_cast<int>((2 * kNumSMs) / (tiles > 0 ? tiles : 1));
+  if (jsplit < 1) jsplit = 1;
+  if (jsplit > 8) jsplit = 8;
+  while (jsplit > 1 && ceil_div(n, jsplit) < 4 * BJ) --jsplit;
+  dim3 grid(static_cast<unsigned>(ceil_div(d, BT)), static_cast<unsigned>(ceil_div(n, BT)), times * jsplit);
   k_mmd_bwd<<<grid, THREADS, 0, as_stream(stream)>>>(src, lds, tgt, ldt, d, src_idx, tgt_idx, b, times, grad_scale,
-                                                    gsrc, ldgs, gtgt, ldgt, ws);
+                                                    gsrc, ldgs, gtgt, ldgt, ws, jsplit);
   GDA_LAUNCH_CHECK();
   return GDA_OK;
 }
