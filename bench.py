@@ -620,7 +620,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             e2e_note = ("fit() default: CUDA-graph replay (%d kernels), next epoch's host->device copy "
                         "double-buffered behind it; %s" % (
                             gs.launches_per_replay,
-                            "x crosses PCIe TILE-PACKED (5 bytes per non-zero) and lands in the buffers the first "
+                            "x crosses PCIe TILE-PACKED with exponent-packed values (4.65 bytes per non-zero: 3 bytes of "
+                            "sign + mantissa, a 4-bit exponent code, a position byte; lossless) into the buffers the first "
                             "layer's tensor-core GEMMs read: no dense rebuild, no operand split" if tiled else
                             "consumed by unpack + operand-split kernels before each replay"))
             ep = [1]
@@ -707,7 +708,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "h2d_bytes_per_step_per_gpu": h2d,
                     "steps": e2e_steps, "how": e2e_note,
-                    "staging": ("pinned host inputs, x tile-packed (lossless; only its non-zeros cross PCIe: 5 bytes per "
+                    "staging": ("pinned host inputs, x tile-packed (lossless; only its non-zeros cross PCIe: 4.65 bytes per "
                                 "non-zero + 20 bytes per 32 x 64 sub-tile)" if packed else "pinned host inputs, dense"),
                     "eager_serial": ({"value": e2e_eager, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                       "how": "cuda_graph=False, prefetch=False: copy, then compute (round 1's e2e.value)"}

@@ -509,6 +509,13 @@ int gda_unpack_rows_delta_f32(const float* vals, const uint8_t* deltas, const in
  * 32 rows x 64 columns): for consumers that need the dense matrix. */
 int gda_unpack_tiles_f32(const float* vals, const uint8_t* codes, const int32_t* ptr, const void* seg,
                          int64_t N, int64_t F, float* out, int64_t ldo, int* error_flag, gda_stream_t stream);
+/* gda_unpack_values_f32: fp32 values from the exponent-packed staging form (pygda_b200.data.PackedTiles): value i =
+ * 3 bytes of m24 (little endian: sign << 23 | mantissa) + the 4-bit code i of ecode (low nibble first): exponent =
+ * meta[0] + code; code 15 marks an escape -- the first min(meta[1], esc_capacity) entries of (esc_idx, esc_val) hold
+ * those values verbatim (also every zero / denormal / inf / nan).  Bit-exact for any input.  m24 holds
+ * 3 * ceil(n / 4) * 4 bytes, ecode ceil(n / 4) * 2 bytes (padded with zeros); out must be 16-byte aligned. */
+int gda_unpack_values_f32(const void* m24, const void* ecode, const int32_t* meta, const int32_t* esc_idx,
+                          const float* esc_val, int64_t esc_capacity, int64_t n, float* out, gda_stream_t stream);
 int gda_unpack_rows_f32(const float* vals, const void* cols, int col_bytes, const int64_t* rowptr, int64_t N,
                         int64_t F, float* out, int64_t ldo, gda_stream_t stream);
 /* gda_argmax_confusion: pred[r] = argmax_c logits[r, c] (first maximal index) and counts[y * C + p] += 1

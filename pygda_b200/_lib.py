@@ -111,6 +111,7 @@ SIGNATURES = {
     "gda_collate_graphs": (i32, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, vp, vp, vp, vp]),
     "gda_unpack_rows_delta_f32": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
     "gda_unpack_tiles_f32": (i32, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp]),
+    "gda_unpack_values_f32": (i32, [vp, vp, vp, vp, vp, i64, i64, vp, vp]),
     "gda_unpack_rows_f32": (i32, [vp, vp, i32, vp, i64, i64, vp, i64, vp]),
     "gda_argmax_confusion": (i32, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "gda_segment_mean_fwd": (i32, [vp, i64, vp, i64, i32, vp, vp]),

@@ -133,6 +133,41 @@ __global__ void k_unpack_tiles(const float* __restrict__ vals, const uint8_t* __
   }
 }
 
+// fp32 values staged with their exponents entropy-packed (pygda_b200.data.PackedTiles, the pinned staging form of a
+// sparse x): per value 3 bytes = sign << 23 | mantissa, and a 4-bit exponent code = exponent - meta[0] (15 = escape:
+// the value is in the escape list).  Lossless for ANY fp32 input; 3.5 instead of 4 bytes per value when the exponents
+// cluster (row-normalised bag-of-words features span ~12 binades).  One thread rebuilds four values.
+__global__ void k_unpack_values(const uint32_t* __restrict__ m24, const uint16_t* __restrict__ ecode,
+                                const int32_t* __restrict__ meta, int64_t n, float* __restrict__ out) {
+  const uint32_t base = static_cast<uint32_t>(__ldg(meta));
+  const int64_t groups = (n + 3) / 4;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < groups; t += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t w0 = __ldg(m24 + 3 * t), w1 = __ldg(m24 + 3 * t + 1), w2 = __ldg(m24 + 3 * t + 2);
+    const uint32_t e = __ldg(ecode + t);
+    const uint32_t v[4] = {w0 & 0xFFFFFFu, (w0 >> 24) | ((w1 & 0xFFFFu) << 8), (w1 >> 16) | ((w2 & 0xFFu) << 16), w2 >> 8};
+    uint32_t bits[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t code = (e >> (4 * k)) & 15u;
+      bits[k] = ((v[k] >> 23) << 31) | ((base + code) << 23) | (v[k] & 0x7FFFFFu);     // escapes are patched afterwards
+    }
+    if (4 * t + 4 <= n) {
+      reinterpret_cast<uint4*>(out)[t] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+    } else {
+      for (int k = 0; 4 * t + k < n; ++k) out[4 * t + k] = __uint_as_float(bits[k]);
+    }
+  }
+}
+
+__global__ void k_patch_values(const int32_t* __restrict__ idx, const float* __restrict__ val, const int32_t* __restrict__ meta,
+                               int64_t cap, int64_t n, float* __restrict__ out) {
+  const int64_t cnt = min(static_cast<int64_t>(__ldg(meta + 1)), cap);
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < cnt; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = __ldg(idx + j);
+    if (i >= 0 && i < n) out[i] = __ldg(val + j);
+  }
+}
+
 constexpr int kMaxClasses = 64;
 
 // argmax (first maximal index, like torch.argmax on the CPU) + confusion counts[label * C + pred]
@@ -277,6 +312,31 @@ int gda_unpack_tiles_f32(const float* vals, const uint8_t* codes, const int32_t*
   k_unpack_tiles<<<static_cast<unsigned>(blocks), 256, 0, st>>>(vals, codes, ptr, static_cast<const uint16_t*>(seg), N, F,
                                                                 nkb, ntiles, ldo, out, error_flag);
   GDA_LAUNCH_CHECK();
+  return GDA_OK;
+}
+
+int gda_unpack_values_f32(const void* m24, const void* ecode, const int32_t* meta, const int32_t* esc_idx,
+                          const float* esc_val, int64_t esc_capacity, int64_t n, float* out, gda_stream_t stream) {
+  using namespace gda;
+  GDA_REQUIRE(n >= 0 && esc_capacity >= 0, "gda_unpack_values_f32: negative size");
+  if (n == 0) return GDA_OK;
+  GDA_REQUIRE(m24 && ecode && meta && out, "gda_unpack_values_f32: NULL pointer");
+  GDA_REQUIRE(esc_capacity == 0 || (esc_idx && esc_val), "gda_unpack_values_f32: NULL escape list");
+  GDA_REQUIRE(reinterpret_cast<uintptr_t>(m24) % 4 == 0 && reinterpret_cast<uintptr_t>(ecode) % 2 == 0 &&
+                  reinterpret_cast<uintptr_t>(out) % 16 == 0,
+              "gda_unpack_values_f32: m24 must be 4-byte, ecode 2-byte, out 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  int64_t blocks = ceil_div(ceil_div(n, 4), 256);
+  if (blocks > int64_t(kNumSMs) * 16) blocks = int64_t(kNumSMs) * 16;
+  k_unpack_values<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const uint32_t*>(m24),
+                                                                 static_cast<const uint16_t*>(ecode), meta, n, out);
+  GDA_LAUNCH_CHECK();
+  if (esc_capacity > 0) {
+    int64_t pb = ceil_div(esc_capacity, 256);
+    if (pb > 1024) pb = 1024;
+    k_patch_values<<<static_cast<unsigned>(pb), 256, 0, st>>>(esc_idx, esc_val, meta, esc_capacity, n, out);
+    GDA_LAUNCH_CHECK();
+  }
   return GDA_OK;
 }
 

@@ -93,11 +93,14 @@ class XTiles:
     """DEVICE view of a tile-packed sparse matrix (``PackedTiles``): what ``gda_gemm_xt_fwd`` / ``gda_gemm_xt_dw``
     read.  Attached to a dense device ``x`` as ``x._gda_tiles`` (``Data.to``) so that the first layer's products
     run from the packed form (ops.GraphConvFn / ops.LinearFn)."""
-    __slots__ = ("vals", "codes", "ptr", "seg", "rows", "cols")
+    __slots__ = ("vals", "codes", "ptr", "seg", "rows", "cols", "dense_version")
 
     def __init__(self, vals, codes, ptr, seg, rows, cols):
         self.vals, self.codes, self.ptr, self.seg = vals, codes, ptr, seg
         self.rows, self.cols = int(rows), int(cols)
+        # ``_version`` of the dense tensor this view is attached to, at attach time: an in-place edit of the dense
+        # matrix afterwards makes the packed copy stale, and ops.x_tiles then ignores it
+        self.dense_version = None
 
     def tensors(self):
         return {"_vals": self.vals, "_codes": self.codes, "_ptr": self.ptr, "_seg": self.seg}
@@ -130,10 +133,13 @@ class PackedTiles:
     multiple of 4 (one 128-row operand tile).  Built with torch ops on whatever device ``x`` lives on (one-time
     preparation, like the CSR of the graph)."""
 
-    def __init__(self, x, chunk=8192, pin=True):
+    def __init__(self, x, chunk=8192, pin=True, compress_values=None):
         n, f = x.shape
         x = x.contiguous()
         dev = x.device
+        # the pinned HOST staging form also packs the exponents of the values (3.5 instead of 4 bytes per value,
+        # lossless: ``compress``); a device-built copy is the operand form itself and keeps plain fp32 values
+        self.compressed = (pin and dev.type == "cpu") if compress_values is None else bool(compress_values)
         nkb = -(-f // 64)
         nstrips = -(-(-(-n // 32)) // 4) * 4
         ntiles = nstrips * nkb
@@ -161,14 +167,88 @@ class PackedTiles:
             raise ValueError("PackedTiles: more than 2^31 non-zeros; pin_memory(pack=False) keeps the dense form")
         self.shape = (n, f)
         pin_ = (lambda t: t.pin_memory()) if (pin and torch.cuda.is_available() and dev.type == "cpu") else (lambda t: t)
-        self.vals = pin_(torch.cat(vals) if vals else torch.zeros(0, device=dev))
+        self._pin = pin_
+        self.vals = torch.cat(vals) if vals else torch.zeros(0, device=dev)
+        if not self.compressed:
+            self.vals = pin_(self.vals)
         self.codes = pin_(torch.cat(codes) if codes else torch.zeros(0, dtype=torch.uint8, device=dev))
         self.ptr = pin_(ptr.to(torch.int32))
         self.seg = pin_(seg.to(torch.int16).contiguous())           # counts <= 2048: the int16 bits ARE the uint16
+        if self.compressed:
+            self.compress()
+
+    def compress(self):
+        """(Re)build the exponent-packed staging arrays from ``self.vals``: per value 3 bytes ``sign << 23 | mantissa``
+        (``m24``) and a 4-bit code ``exponent - base`` (``ecode``, 15 = escape, value kept verbatim in ``esc_idx`` /
+        ``esc_val``); ``vmeta = [base, number of escapes, 0, 0]``.  ``base`` is the 15-binade window that covers most
+        values.  Bit-exact for any fp32 input (``gda_unpack_values_f32`` / ``decompress_values``)."""
+        v = self.vals
+        nnz = v.numel()
+        g4 = -(-nnz // 4)
+        bits = v.view(torch.int32)
+        exp = (bits >> 23) & 0xFF
+        v24 = (bits & 0x7FFFFF) | (((bits >> 31) & 1) << 23)
+        hist = torch.bincount(exp, minlength=256).to(torch.int64)
+        win = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), hist]), 0)
+        cover = win[15:256 + 1] - win[0:256 - 15 + 1]               # values with exponent in [base, base + 15)
+        base = int(torch.argmax(cover)) if nnz else 0
+        code = exp - base
+        esc = (code < 0) | (code > 14)
+        code = torch.where(esc, torch.full_like(code, 15), code)
+        m24 = torch.zeros(4 * g4, 3, dtype=torch.uint8)
+        m24[:nnz, 0] = (v24 & 255).to(torch.uint8)
+        m24[:nnz, 1] = ((v24 >> 8) & 255).to(torch.uint8)
+        m24[:nnz, 2] = ((v24 >> 16) & 255).to(torch.uint8)
+        c4 = torch.zeros(4 * g4, dtype=torch.int32)
+        c4[:nnz] = code
+        ecode = (c4[0::2] | (c4[1::2] << 4)).to(torch.uint8)
+        esc_idx = esc.nonzero(as_tuple=True)[0].to(torch.int32)
+        n_esc = int(esc_idx.numel())
+        cap = max(n_esc, 1)
+        new = {"m24": m24.reshape(-1), "ecode": ecode.contiguous(),
+               "vmeta": torch.tensor([base, n_esc, 0, 0], dtype=torch.int32),
+               "esc_idx": torch.zeros(cap, dtype=torch.int32), "esc_val": torch.zeros(cap, dtype=torch.float32)}
+        new["esc_idx"][:n_esc] = esc_idx
+        new["esc_val"][:n_esc] = v[esc]
+        for k, t in new.items():
+            old = getattr(self, k, None)
+            if old is not None and old.shape == t.shape:
+                old.copy_(t)                                         # keep the pinned buffers a staging plan holds
+            else:
+                setattr(self, k, self._pin(t))
+
+    def decompress_values(self):
+        """fp32 values rebuilt from the exponent-packed arrays on the host (tests; the device does it in
+        ``gda_unpack_values_f32``)."""
+        nnz = self.vals.numel()
+        m = self.m24.view(-1, 3)[:nnz].to(torch.int32)
+        v24 = m[:, 0] | (m[:, 1] << 8) | (m[:, 2] << 16)
+        e = self.ecode.to(torch.int32)
+        code = torch.stack([e & 15, e >> 4], 1).reshape(-1)[:nnz]
+        base, n_esc = int(self.vmeta[0]), int(self.vmeta[1])
+        bits = ((v24 >> 23) << 31) | ((base + code) << 23) | (v24 & 0x7FFFFF)
+        out = bits.view(torch.float32).clone()
+        out[self.esc_idx[:n_esc].long()] = self.esc_val[:n_esc]
+        return out
 
     def tensors(self):
         """The arrays that cross PCIe, by staging name."""
-        return {"_vals": self.vals, "_codes": self.codes, "_ptr": self.ptr, "_seg": self.seg}
+        t = {"_codes": self.codes, "_ptr": self.ptr, "_seg": self.seg}
+        if self.compressed:
+            t.update({"_m24": self.m24, "_ecode": self.ecode, "_vmeta": self.vmeta, "_esc_idx": self.esc_idx,
+                      "_esc_val": self.esc_val})
+        else:
+            t["_vals"] = self.vals
+        return t
+
+    def unpack_values_into(self, dev, vals, stream=None):
+        """fp32 ``vals`` (device, [nnz]) from DEVICE copies ``dev`` of the exponent-packed arrays (current stream)."""
+        from ._lib import gda
+        p = lambda t: C.c_void_p(t.data_ptr())                    # noqa: E731
+        gda.unpack_values_f32(p(dev["_m24"]), p(dev["_ecode"]), p(dev["_vmeta"]), p(dev["_esc_idx"]),
+                              p(dev["_esc_val"]), dev["_esc_idx"].numel(), vals.numel(), p(vals),
+                              C.c_void_p((stream or torch.cuda.current_stream(vals.device)).cuda_stream))
+        return vals
 
     @property
     def nbytes(self):
@@ -177,11 +257,20 @@ class PackedTiles:
     def view(self, dev=None):
         """``XTiles`` over ``dev`` (DEVICE copies of ``tensors()``; default: this object's own arrays)."""
         d = dev if dev is not None else self.tensors()
-        return XTiles(d["_vals"], d["_codes"], d["_ptr"], d["_seg"], *self.shape)
+        if "_vals" in d:
+            vals = d["_vals"]
+        else:                                                   # exponent-packed staging copy: rebuild the fp32 values
+            vals = torch.empty(self.vals.numel(), dtype=torch.float32, device=d["_codes"].device)
+            self.unpack_values_into(d, vals)
+        return XTiles(vals, d["_codes"], d["_ptr"], d["_seg"], *self.shape)
 
     def unpack_into(self, dev, out, stream=None):
         """Rebuild the dense matrix in ``out`` [N, F] from DEVICE copies ``dev`` of ``tensors()`` (current stream)."""
         self.view(dev).unpack_into(out, stream)
+
+    @property
+    def staged_nbytes(self):
+        return self.nbytes
 
     def to_dense(self, device, non_blocking=True):
         """Dense device matrix rebuilt from a fresh host->device copy of the packed arrays; the copy stays attached
@@ -191,10 +280,12 @@ class PackedTiles:
         d = {k: t.to(dev, non_blocking=non_blocking) for k, t in self.tensors().items()}
         out = torch.empty(n, f, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            self.unpack_into(d, out)
-        for t in d.values():
+            tiles = self.view(d)
+            tiles.unpack_into(out)
+        for t in list(d.values()) + [tiles.vals]:
             t.record_stream(torch.cuda.current_stream(dev))
-        out._gda_tiles = self.view(d)
+        out._gda_tiles = tiles
+        tiles.dense_version = out._version
         return out
 
     def decode(self):

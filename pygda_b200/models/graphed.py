@@ -81,7 +81,10 @@ class StagedBatch:
         s = self.slots[slot]
         if self.tiles is not None:
             for k, t in self.tiles.tensors().items():
-                t.copy_(s[k], non_blocking=True)
+                if k in s:
+                    t.copy_(s[k], non_blocking=True)
+            if "_vals" not in s:                          # exponent-packed staging: rebuild the fp32 values in place
+                self.packed.unpack_values_into(s, self.tiles.vals)
         elif self.packed is not None:
             self.packed.unpack_into(s, self.static.x)
         for k, v in s.items():

@@ -317,6 +317,8 @@ def x_tiles(x, n_out):
     if not tc_eligible(x.shape[0], max(int(n_out), 64), x.shape[1]):
         return None
     t = getattr(x, "_gda_tiles", None)
+    if t is not None and t.dense_version is not None and t.dense_version != x._version:
+        t = None                               # the dense matrix was edited in place after the packed copy was made
     if t is None and getattr(x, "_gda_const", False) and getattr(x, "_gda_key", None) is None:
         t = tiles_cache.get(x)
     if not t or t.vals.numel() > XT_DENSITY * x.numel():

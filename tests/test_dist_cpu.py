@@ -184,6 +184,14 @@ def test_packed_tiles_format_roundtrip_on_the_host():
         assert np.array_equal(dense.view(np.int32), x.numpy().view(np.int32))
         assert torch.equal(p.decode().view(torch.int32), x.view(torch.int32))
         assert p.nbytes == 5 * p.vals.numel() + 4 * (nstrips * nkb + 1) + 16 * nstrips * nkb
+        # the exponent-packed form of the values (what the pinned staging copy carries): lossless for any bit pattern
+        x[0, 0] = float("inf")
+        if f > 5:
+            x[0, 1], x[0, 2], x[0, 4], x[0, 5] = float("nan"), 1e-42, -3.5e20, -1e-4
+        q = PackedTiles(x, chunk=64, pin=False, compress_values=True)
+        assert "_vals" not in q.tensors() and q.m24.numel() == 12 * -(-q.vals.numel() // 4)
+        assert q.ecode.numel() == 2 * -(-q.vals.numel() // 4) and int(q.vmeta[1]) >= 1
+        assert torch.equal(q.decompress_values().view(torch.int32), q.vals.view(torch.int32))
     d = Data(x=torch.zeros(10, 8), edge_index=torch.zeros(2, 0, dtype=torch.long), y=torch.zeros(10, dtype=torch.long))
     assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
 

@@ -109,6 +109,9 @@ def test_staged_data_carries_the_packed_copy_and_the_first_layer_uses_it():
     on = d.to("cuda")
     assert torch.equal(on.x.cpu().view(torch.int32), x.view(torch.int32))
     assert ops.x_tiles(on.x, h) is on.x._gda_tiles
+    edited = d.to("cuda")
+    edited.x.mul_(2.0)                                       # in-place edit: the attached packed copy is stale now
+    assert ops.x_tiles(edited.x, h) is None
     graph = graph_for(on.edge_index, n)
     w = torch.randn(h, f, generator=g).cuda().requires_grad_()
     b = torch.zeros(h, device="cuda", requires_grad=True)
@@ -142,3 +145,21 @@ def test_resident_constant_features_are_packed_once():
     y.backward(torch.ones_like(y))
     assert_close(y, x.double() @ w.double().t(), 3e-5, "linear from the packed constant")
     assert_close(w.grad, torch.ones(2000, 128, device="cuda").double().t() @ x.double(), 3e-5, "its weight gradient")
+
+
+def test_exponent_packed_staging_values_are_rebuilt_bit_for_bit():
+    """The pinned staging form packs the exponents of the values (3.5 bytes per value); gda_unpack_values_f32 rebuilds
+    every fp32 bit pattern on the device -- also inf / nan / denormals / negative zero and values outside the
+    15-binade window (the escape list)."""
+    from pygda_b200.data import PackedTiles
+    x = _sparse(700, 900, 0.07, seed=31)
+    x = x / x.sum(1, keepdim=True).clamp(min=1e-9)
+    x[0, 0], x[0, 1], x[0, 2], x[0, 3], x[0, 4], x[1, 0] = float("inf"), float("nan"), -0.0, 1e-42, -3.5e20, -1e-4
+    host = PackedTiles(x, pin=True)
+    assert host.compressed and int(host.vmeta[1]) >= 5 and "_vals" not in host.tensors()
+    assert host.nbytes < 0.93 * PackedTiles(x, pin=False).nbytes
+    assert torch.equal(host.decompress_values().view(torch.int32), host.vals.view(torch.int32))
+    dense = host.to_dense("cuda")
+    torch.cuda.synchronize()
+    assert torch.equal(dense._gda_tiles.vals.cpu().view(torch.int32), host.vals.view(torch.int32))
+    assert torch.equal(dense.cpu().view(torch.int32), x.view(torch.int32))

@@ -87,6 +87,8 @@ def test_staged_step_consumes_the_bytes_copied_for_that_epoch():
     assert_close(again, base, 1e-6, "unchanged inputs")
     torch.cuda.synchronize()
     sb.__dict__["_packed_x"].vals.mul_(2.0)                         # host edit; copy #3 is already in flight
+    if getattr(sb.__dict__["_packed_x"], "compressed", False):      # exponent-packed staging arrays: rebuilt IN PLACE
+        sb.__dict__["_packed_x"].compress()                         # (same pinned buffers the staging plan copies from)
     g()                                                             # consumes #3 (may or may not see the edit), issues #4
     edited = g()[1].clone()                                         # consumes #4: issued after the edit
     assert_close(edited, 2.0 * base, 1e-5, "source logits follow the re-sent host data (linear first layer, no bias)")
