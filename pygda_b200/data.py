@@ -376,7 +376,8 @@ class Data:
             if k == "x" and do_pack:
                 out.__dict__[k] = v
                 continue
-            out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) and not v.is_cuda else v
+            pinnable = torch.is_tensor(v) and not v.is_cuda and torch.cuda.is_available()
+            out.__dict__[k] = v.pin_memory() if pinnable else v
         if do_pack:
             out.__dict__["_packed_x"] = PackedRows(x) if pack == "rows" else PackedTiles(x)
         src, ei = self.edge_index, out.__dict__.get("edge_index")

@@ -196,6 +196,30 @@ def test_packed_tiles_format_roundtrip_on_the_host():
     assert d.h2d_nbytes() == 10 * 8 * 4 + 10 * 8
 
 
+def test_pin_memory_stages_a_sparse_x_tile_packed_and_counts_its_bytes():
+    """Data.pin_memory(): a sparse fp32 x is kept tile-packed with exponent-packed values in the staging area (the
+    caller's tensor stays ``.x``), a dense one is pinned as it is; h2d_nbytes() counts what ``.to(cuda)`` would copy."""
+    from pygda_b200.data import Data, PackedRows, PackedTiles
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(torch.randn(200, 900, generator=g) - 1.5)
+    x = x / x.sum(1, keepdim=True).clamp(min=1e-9)
+    ei = torch.randint(0, 200, (2, 700), generator=g)
+    d = Data(x=x, edge_index=ei, y=torch.zeros(200, dtype=torch.long))
+    p = d.pin_memory()
+    packed = p.__dict__["_packed_x"]
+    assert isinstance(packed, PackedTiles) and packed.compressed and p.x is x
+    assert torch.equal(packed.decode().view(torch.int32), x.view(torch.int32))
+    assert torch.equal(packed.decompress_values().view(torch.int32), packed.vals.view(torch.int32))
+    other = ei.numel() * 8 + 200 * 8
+    assert p.h2d_nbytes() == packed.nbytes + other
+    nnz = int((x != 0).sum())
+    assert packed.nbytes < 4.8 * nnz + 20 * packed.seg.shape[0] + 64          # 3.5 B value + 1 B position (+ escapes)
+    assert isinstance(d.pin_memory(pack="rows").__dict__["_packed_x"], PackedRows)
+    dense = Data(x=torch.randn(50, 40, generator=g), edge_index=ei[:, :10] % 50, y=torch.zeros(50, dtype=torch.long))
+    assert "_packed_x" not in dense.pin_memory().__dict__
+    assert "_packed_x" not in d.pin_memory(pack=False).__dict__
+
+
 def test_graph_loader_batches_follow_torchs_own_sampler():
     """PyG's DataLoader is torch's DataLoader with a graph collate: for the same torch seed our loader must yield the
     same graphs per batch and consume the CPU generator identically (pygda/models/a2gnn.py:276-286)."""
