@@ -4,17 +4,19 @@
 //
 // The dense kernel (gemm_tc.cu) streams X as a split-bf16 pair -- 4 bytes per element, 2.7 GB per pass at
 // BASELINE config 2 (100 k x 6775), HBM-bound at ~0.5 ms while the tensor pipe idles half of the time.  Here X
-// stays TILE-PACKED in HBM (5 bytes per NON-ZERO: fp32 value + one delta-coded position byte, ~0.24 GB) and the
+// stays TILE-PACKED in HBM (5 bytes per NON-ZERO: fp32 value + one position byte, ~0.24 GB) and the
 // dense 128 x 64 operand tiles exist only in shared memory: four "expander" warps zero a stage, decode their
-// 32-row x 64-column sub-tile (warp prefix sum over the position deltas), split every value into
+// 32-row x 64-column sub-tile (every entry on its own: see the format below), split every value into
 // hi = bf16(v), lo = bf16(v - hi) and scatter both into the SWIZZLE_128B layout the UMMA descriptors expect;
 // `fence.proxy.async` + an mbarrier arrive hand the stage to the MMA warp.  W / G (dense, small or streamed once)
 // still arrive by TMA.  Same three product terms per K step as the dense kernel (Ah*Bh + Ah*Bl + Al*Bh) in the same
 // K order; Ah*Bl is kept in a second accumulator and added in the epilogue (one N = 256 UMMA on [Bh | Bl] reads Ah
-// from shared memory once -- the kernel is bound by shared-memory bandwidth, not by HBM or the tensor pipe).
+// from shared memory once).  What bounds the kernel is the L2 -> SM stream of the dense operand and the expanders'
+// pace, not HBM: it runs at 0.82 of the measured sustained bf16 tensor rate.
 //
-// Tile-packed X ("XT", built by pygda_b200.data.PackedTiles; the pinned host staging form IS this form, so the
-// per-step host->device copy lands directly in the buffers this kernel reads):
+// Tile-packed X ("XT", built by pygda_b200.data.PackedTiles; the pinned host staging form is this form with the
+// values exponent-packed, so the per-step host->device copy lands in the buffers this kernel reads after one
+// streaming kernel that rebuilds the fp32 values, gda_unpack_values_f32):
 //   sub-tile t = strip * nkb + kb, strip = row / 32, kb = col / 64 (nkb = ceil(cols / 64));
 //   position of an entry inside its sub-tile p = (row % 32) * 64 + (col % 64) in [0, 2048), entries sorted by p;
 //   entries of sub-tile t: [ptr[t], ptr[t+1]) in vals (fp32) and codes (uint8 = p & 255);
